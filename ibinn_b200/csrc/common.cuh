@@ -1,0 +1,70 @@
+// Shared device helpers for the ibinn_b200 kernels (sm_100a only).
+#pragma once
+#ifndef IBINN_EMU
+#include <cuda_runtime.h>
+#include <stdint.h>
+#define IBINN_LAUNCH(kernel, grid, block, smem, stream, ...) \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define IBINN_DYN_SMEM(type, name)                                  \
+    extern __shared__ __align__(1024) unsigned char ibinn_dyn_raw[]; \
+    type* name = reinterpret_cast<type*>(ibinn_dyn_raw)
+#endif
+#include "../../include/ibinn_b200.h"
+
+#define IBINN_THREADS 256
+
+// status of the launch just enqueued: 0 or the (positive) cudaError_t
+static inline int ibinn_launch_status() { return (int)cudaGetLastError(); }
+
+template <class F>
+static inline int ibinn_set_smem(F kernel, size_t bytes) {
+    if (bytes > 227 * 1024) return IBINN_EINVAL;
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum over the whole block (blockDim.x multiple of 32, <= 1024); result valid in every thread.
+// `scratch` needs 33 floats.  Deterministic (fixed order).
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[w] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < nw; ++i) t += scratch[i];
+    return t;
+}
+
+// "last block done" ticket: returns true in every thread of the block that arrives last.
+// counter must be zero before the launch; the caller resets it (the last block) after use.
+__device__ __forceinline__ bool last_block_ticket(unsigned* counter, unsigned nblocks, int* s_flag) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(counter, 1u);
+        *s_flag = (t == nblocks - 1u) ? 1 : 0;
+    }
+    __syncthreads();
+    bool last = (*s_flag != 0);
+    if (last) __threadfence();
+    return last;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }

@@ -1,0 +1,502 @@
+// Affine coupling kernels of the IB-INN nodes (HBM-bound elementwise + per-sample log-det):
+//   * AIO_Block: tanh-clamped affine coupling + ActNorm + fixed orthogonal 1x1 "soft permutation"
+//     fused in one kernel per direction (reference all_in_one_block.py:61-114);
+//   * DownsampleCouplingBlock: space-to-depth fused with the affine coupling
+//     (reference downsampling_coupling_block.py:49-97);
+//   * GLOWCouplingBlock (FrEIA v0.2, used at inn_architecture.py:161): atan-clamped affine halves.
+// One CTA owns one sample, so the per-sample log-det is a fixed-order in-CTA reduction
+// (warp shuffles + one shared-memory pass) and is written, never atomically accumulated.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ int round4(int v) { return (v + 3) & ~3; }
+
+// ------------------------------------------------------------------------------------ AIO
+struct AioP {
+    const float* x; const float* a; const float* w; const float* an; const float* off;
+    float* out; float* jac;
+    int B, C, HW; float clamp, alpha;
+    // backward only
+    const float* g_out; const float* g_jac; const float* out_saved;
+    float* g_x; float* g_a; float* g_an; float* g_off; float* partials; unsigned* counter;
+};
+
+// MODE 0: forward   out = (w . [x1 | x2*exp(sig)+t]) * exp(an) + off ; jac = sum sig + HW*sum an
+// MODE 1: unpermute u = w_inv . ((y - off) * exp(-an))                (first half of the inverse)
+template <int MODE>
+__global__ void __launch_bounds__(IBINN_THREADS) aio_mix_kernel(const AioP p) {
+    IBINN_DYN_SMEM(float, smem);
+    __shared__ float s_scr[40];
+    const int C = p.C, HW = p.HW, HWp = round4(HW), Cp = round4(C);
+    const int c1 = C - C / 2, c2 = C / 2;
+    float* s_u = smem;                 // [C][HWp]
+    float* s_w = s_u + (size_t)C * HWp;  // [C(in)][Cp(out)]
+    float* s_sc = s_w + (size_t)C * Cp;  // [C] exp(+-an)
+    float* s_of = s_sc + Cp;             // [C]
+    const int tid = threadIdx.x, b = blockIdx.x;
+    const float* xb = p.x + (size_t)b * C * HW;
+
+    for (int e = tid; e < C * Cp; e += IBINN_THREADS) {
+        const int i = e / Cp, o = e - i * Cp;
+        s_w[e] = (o < C) ? __ldg(p.w + (size_t)o * C + i) : 0.f;
+    }
+    for (int c = tid; c < C; c += IBINN_THREADS) {
+        s_sc[c] = expf(MODE == 0 ? p.an[c] : -p.an[c]);
+        s_of[c] = p.off[c];
+    }
+    if (MODE == 1) __syncthreads();
+
+    float jsum = 0.f;
+    for (int e = tid; e < C * HW; e += IBINN_THREADS) {
+        const int c = e / HW, q = e - c * HW;
+        float u = __ldg(xb + e);
+        if (MODE == 0) {
+            if (c >= c1) {
+                const float* ab = p.a + (size_t)b * 2 * c2 * HW;
+                const float s = __ldg(ab + (size_t)(c - c1) * HW + q);
+                const float t = __ldg(ab + (size_t)(c2 + c - c1) * HW + q);
+                const float sig = p.clamp * tanhf(p.alpha * s);
+                u = fmaf(u, expf(sig), t);
+                jsum += sig;
+            }
+        } else {
+            u = (u - s_of[c]) * s_sc[c];
+        }
+        s_u[(size_t)c * HWp + q] = u;
+    }
+    // zero the pixel padding so that the 4-wide reads below stay finite
+    if (HWp != HW)
+        for (int c = tid; c < C; c += IBINN_THREADS)
+            for (int q = HW; q < HWp; ++q) s_u[(size_t)c * HWp + q] = 0.f;
+    __syncthreads();
+
+    const int npg = HWp / 4, nog = Cp / 4;
+    float* ob = p.out + (size_t)b * C * HW;
+    const bool vec = (HW % 4) == 0;
+    for (int item = tid; item < npg * nog; item += IBINN_THREADS) {
+        const int pg = item % npg, og = item / npg;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int i = 0; i < C; ++i) {
+            const float4 uv = ld4(s_u + (size_t)i * HWp + pg * 4);
+            const float4 wv = ld4(s_w + (size_t)i * Cp + og * 4);
+            const float uu[4] = {uv.x, uv.y, uv.z, uv.w};
+            const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[o][j] = fmaf(ww[o], uu[j], acc[o][j]);
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+            const int oc = og * 4 + o;
+            if (oc >= C) continue;
+            float r[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) r[j] = (MODE == 0) ? fmaf(acc[o][j], s_sc[oc], s_of[oc]) : acc[o][j];
+            float* dst = ob + (size_t)oc * HW + pg * 4;
+            if (vec) st4(dst, make_float4(r[0], r[1], r[2], r[3]));
+            else
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (pg * 4 + j < HW) dst[j] = r[j];
+        }
+    }
+    if (MODE == 0) {
+        const float tot = block_sum(jsum, s_scr);
+        if (tid == 0) {
+            float san = 0.f;
+            for (int c = 0; c < C; ++c) san += p.an[c];
+            p.jac[b] = tot + (float)HW * san;
+        }
+    }
+}
+
+// second half of the inverse: x2 = (u2 - t) * exp(-sig), in place on u; jac = -sum sig - HW*sum an
+__global__ void __launch_bounds__(IBINN_THREADS) aio_affine_inverse_kernel(const AioP p) {
+    __shared__ float s_scr[40];
+    const int C = p.C, HW = p.HW, c1 = C - C / 2, c2 = C / 2;
+    const int tid = threadIdx.x, b = blockIdx.x;
+    float* ub = p.out + (size_t)b * C * HW + (size_t)c1 * HW;
+    const float* ab = p.a + (size_t)b * 2 * c2 * HW;
+    float jsum = 0.f;
+    for (int e = tid; e < c2 * HW; e += IBINN_THREADS) {
+        const float sig = p.clamp * tanhf(p.alpha * __ldg(ab + e));
+        ub[e] = (ub[e] - __ldg(ab + (size_t)c2 * HW + e)) * expf(-sig);
+        jsum += sig;
+    }
+    const float tot = block_sum(jsum, s_scr);
+    if (tid == 0) {
+        float san = 0.f;
+        for (int c = 0; c < C; ++c) san += p.an[c];
+        p.jac[b] = -tot - (float)HW * san;
+    }
+}
+
+// backward of MODE 0.  Needs x, a, out (the block output = next block's input) and g_out.
+__global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
+    IBINN_DYN_SMEM(float, smem);
+    __shared__ int s_flag;
+    const int C = p.C, HW = p.HW, HWp = round4(HW), Cp = round4(C);
+    const int c1 = C - C / 2, c2 = C / 2;
+    float* s_u = smem;                   // g_v [C][HWp]
+    float* s_w = s_u + (size_t)C * HWp;  // [C(out)][Cp(in)]
+    const int tid = threadIdx.x, b = blockIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t ib = (size_t)b * C * HW;
+    const float gj = p.g_jac ? __ldg(p.g_jac + b) : 0.f;
+
+    for (int e = tid; e < C * Cp; e += IBINN_THREADS) {
+        const int o = e / Cp, i = e - o * Cp;
+        s_w[e] = (i < C) ? __ldg(p.w + (size_t)o * C + i) : 0.f;
+    }
+    // phase A: one warp per output channel: g_v = g_out * exp(an), per-channel partial sums
+    for (int o = wid; o < C; o += IBINN_THREADS / 32) {
+        const float sc = expf(p.an[o]), of = p.off[o];
+        float so = 0.f, sn = 0.f;
+        for (int q = lane; q < HWp; q += 32) {
+            float gv = 0.f;
+            if (q < HW) {
+                const float g = __ldg(p.g_out + ib + (size_t)o * HW + q);
+                const float y = __ldg(p.out_saved + ib + (size_t)o * HW + q);
+                so += g;
+                sn = fmaf(g, y - of, sn);
+                gv = g * sc;
+            }
+            s_u[(size_t)o * HWp + q] = gv;
+        }
+        so = warp_sum(so);
+        sn = warp_sum(sn);
+        if (lane == 0) {
+            p.partials[((size_t)b * 2 + 0) * C + o] = so;
+            p.partials[((size_t)b * 2 + 1) * C + o] = sn + (float)HW * gj;
+        }
+    }
+    __syncthreads();
+
+    // phase B: g_u = w^T g_v, then the affine-coupling backward per element
+    const int npg = HWp / 4, nig = Cp / 4;
+    const bool vec = (HW % 4) == 0;
+    const float* ab = p.a + (size_t)b * 2 * c2 * HW;
+    float* gab = p.g_a + (size_t)b * 2 * c2 * HW;
+    const float ak = p.alpha * p.clamp;
+    for (int item = tid; item < npg * nig; item += IBINN_THREADS) {
+        const int pg = item % npg, ig = item / npg;
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int o = 0; o < C; ++o) {
+            const float4 uv = ld4(s_u + (size_t)o * HWp + pg * 4);
+            const float4 wv = ld4(s_w + (size_t)o * Cp + ig * 4);
+            const float uu[4] = {uv.x, uv.y, uv.z, uv.w};
+            const float ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ww[i], uu[j], acc[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ic = ig * 4 + i;
+            if (ic >= C) continue;
+            float gx[4];
+            if (ic < c1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) gx[j] = acc[i][j];
+            } else {
+                const int k = ic - c1;
+                float gs[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int q = pg * 4 + j;
+                    gx[j] = 0.f; gs[j] = 0.f;
+                    if (q < HW) {
+                        const float s = __ldg(ab + (size_t)k * HW + q);
+                        const float th = tanhf(p.alpha * s);
+                        const float es = expf(p.clamp * th);
+                        const float x2 = __ldg(p.x + ib + (size_t)ic * HW + q);
+                        const float gu = acc[i][j];
+                        gx[j] = gu * es;
+                        gs[j] = (gu * x2 * es + gj) * ak * (1.f - th * th);
+                    }
+                }
+                float* ds = gab + (size_t)k * HW + pg * 4;
+                float* dt = gab + (size_t)(c2 + k) * HW + pg * 4;
+                if (vec) {
+                    st4(ds, make_float4(gs[0], gs[1], gs[2], gs[3]));
+                    st4(dt, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (pg * 4 + j < HW) { ds[j] = gs[j]; dt[j] = acc[i][j]; }
+                }
+            }
+            float* dx = p.g_x + ib + (size_t)ic * HW + pg * 4;
+            if (vec) st4(dx, make_float4(gx[0], gx[1], gx[2], gx[3]));
+            else
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (pg * 4 + j < HW) dx[j] = gx[j];
+        }
+    }
+
+    // ActNorm parameter gradients: last CTA sums the per-sample partials in sample order
+    if (!last_block_ticket(p.counter, gridDim.x, &s_flag)) return;
+    for (int e = tid; e < 2 * C; e += IBINN_THREADS) {
+        double t = 0.;
+        for (int bb = 0; bb < p.B; ++bb) t += (double)p.partials[(size_t)bb * 2 * C + e];
+        if (e < C) { if (p.g_off) p.g_off[e] += (float)t; }
+        else if (p.g_an) p.g_an[e - C] += (float)t;
+    }
+    if (tid == 0) *p.counter = 0u;
+}
+
+static size_t aio_smem(int C, int HW) {
+    const int HWp = (HW + 3) & ~3, Cp = (C + 3) & ~3;
+    return ((size_t)C * HWp + (size_t)C * Cp + 2 * Cp + 16) * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------ S2D
+struct S2dP {
+    const float* x; long long x_bs; const float* a; float* out; long long out_bs; float* jac; int jac_acc;
+    const float* g_out; long long g_bs; const float* g_jac; float* g_x; long long gx_bs; float* g_a;
+    int B, cp, H, W; float clamp, alpha;
+};
+
+// MODE 0 forward, 1 inverse (x <- out), 2 backward
+template <int MODE>
+__global__ void __launch_bounds__(IBINN_THREADS) s2d_kernel(const S2dP p) {
+    __shared__ float s_scr[40];
+    const int Ho = p.H / 2, Wo = p.W / 2, HWo = Ho * Wo, n = 4 * p.cp * HWo;
+    const int tid = threadIdx.x, b = blockIdx.x;
+    const float* ab = p.a + (size_t)b * 8 * p.cp * HWo;
+    const float gj = (MODE == 2 && p.g_jac) ? __ldg(p.g_jac + b) : 0.f;
+    const float ak = p.alpha * p.clamp;
+    float jsum = 0.f;
+    for (int e = tid; e < n; e += IBINN_THREADS) {
+        const int oc = e / HWo, q = e - oc * HWo;
+        const int h = q / Wo, w = q - h * Wo;
+        const int c = oc >> 2, dy = (oc >> 1) & 1, dx = oc & 1;
+        const size_t xi = ((size_t)c * p.H + 2 * h + dy) * p.W + 2 * w + dx;
+        const float s = __ldg(ab + e);
+        const float th = tanhf(p.alpha * s);
+        const float sig = p.clamp * th;
+        if (MODE == 0) {
+            const float t = __ldg(ab + (size_t)n + e);
+            p.out[(size_t)b * p.out_bs + e] = fmaf(__ldg(p.x + (size_t)b * p.x_bs + xi), expf(sig), t);
+            jsum += sig;
+        } else if (MODE == 1) {
+            const float t = __ldg(ab + (size_t)n + e);
+            // here `x` is the output tensor (full resolution) and `out` the block-side tensor
+            const_cast<float*>(p.x)[(size_t)b * p.x_bs + xi] = (p.out[(size_t)b * p.out_bs + e] - t) * expf(-sig);
+            jsum -= sig;
+        } else {
+            const float es = expf(sig);
+            const float g = __ldg(p.g_out + (size_t)b * p.g_bs + e);
+            const float xv = __ldg(p.x + (size_t)b * p.x_bs + xi);
+            p.g_x[(size_t)b * p.gx_bs + xi] = g * es;
+            float* gab = p.g_a + (size_t)b * 8 * p.cp * HWo;
+            gab[e] = (g * xv * es + gj) * ak * (1.f - th * th);
+            gab[(size_t)n + e] = g;
+        }
+    }
+    if (MODE != 2) {
+        const float tot = block_sum(jsum, s_scr);
+        if (tid == 0) p.jac[b] = (p.jac_acc ? p.jac[b] : 0.f) + tot;
+    }
+}
+
+// ------------------------------------------------------------------------------------ GLOW
+struct GlowP {
+    const float* x; long long x_rs; const float* r; float* y; long long y_rs; float* jac; int jac_acc;
+    const float* g_y; long long gy_rs; const float* g_jac; float* g_x; long long gx_rs; float* g_r;
+    int B, L; float clamp;
+};
+
+__device__ __forceinline__ float glow_le(float s, float clamp) { return clamp * 0.636f * atanf(s / clamp); }
+
+template <int MODE>
+__global__ void __launch_bounds__(IBINN_THREADS) glow_kernel(const GlowP p) {
+    __shared__ float s_scr[40];
+    const int tid = threadIdx.x, b = blockIdx.x, L = p.L;
+    const float* rb = p.r + (size_t)b * 2 * L;
+    const float gj = (MODE == 2 && p.g_jac) ? __ldg(p.g_jac + b) : 0.f;
+    float jsum = 0.f;
+    for (int i = tid; i < L; i += IBINN_THREADS) {
+        const float s = __ldg(rb + i);
+        const float le = glow_le(s, p.clamp);
+        if (MODE == 0) {
+            p.y[(size_t)b * p.y_rs + i] = fmaf(expf(le), __ldg(p.x + (size_t)b * p.x_rs + i), __ldg(rb + L + i));
+            jsum += le;
+        } else if (MODE == 1) {
+            p.y[(size_t)b * p.y_rs + i] = (__ldg(p.x + (size_t)b * p.x_rs + i) - __ldg(rb + L + i)) * expf(-le);
+            jsum -= le;
+        } else {
+            const float e = expf(le);
+            const float g = __ldg(p.g_y + (size_t)b * p.gy_rs + i);
+            const float xv = __ldg(p.x + (size_t)b * p.x_rs + i);
+            const float q = s / p.clamp;
+            p.g_x[(size_t)b * p.gx_rs + i] = g * e;
+            p.g_r[(size_t)b * 2 * L + i] = (g * xv * e + gj) * (0.636f / (1.f + q * q));
+            p.g_r[(size_t)b * 2 * L + L + i] = g;
+        }
+    }
+    if (MODE != 2) {
+        const float tot = block_sum(jsum, s_scr);
+        if (tid == 0) p.jac[b] = (p.jac_acc ? p.jac[b] : 0.f) + tot;
+    }
+}
+
+}  // namespace
+
+#define IBINN_ENTRY_GUARD()                   \
+    do {                                      \
+        int e_ = ibinn_check_device();        \
+        if (e_) return e_;                    \
+    } while (0)
+
+extern "C" int ibinn_aio_coupling_forward(const float* x, const float* a, const float* w, const float* act_norm,
+                                          const float* act_offset, float* out, float* jac, int B, int C, int H, int W,
+                                          float clamp, float alpha, ibinn_stream_t stream) {
+    IBINN_ENTRY_GUARD();
+    if (!x || !w || !act_norm || !act_offset || !out || !jac || (C > 1 && !a)) return IBINN_ENULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return IBINN_EINVAL;
+    AioP p{};
+    p.x = x; p.a = a; p.w = w; p.an = act_norm; p.off = act_offset; p.out = out; p.jac = jac;
+    p.B = B; p.C = C; p.HW = H * W; p.clamp = clamp; p.alpha = alpha;
+    size_t sm = aio_smem(C, H * W);
+    int e = ibinn_set_smem(aio_mix_kernel<0>, sm);
+    if (e) return e;
+    IBINN_LAUNCH(aio_mix_kernel<0>, dim3(B), dim3(IBINN_THREADS), sm, (cudaStream_t)stream, p);
+    return ibinn_launch_status();
+}
+
+extern "C" int ibinn_aio_unpermute(const float* y, const float* w_inv, const float* act_norm, const float* act_offset,
+                                   float* u, int B, int C, int H, int W, ibinn_stream_t stream) {
+    IBINN_ENTRY_GUARD();
+    if (!y || !w_inv || !act_norm || !act_offset || !u) return IBINN_ENULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return IBINN_EINVAL;
+    AioP p{};
+    p.x = y; p.w = w_inv; p.an = act_norm; p.off = act_offset; p.out = u;
+    p.B = B; p.C = C; p.HW = H * W;
+    size_t sm = aio_smem(C, H * W);
+    int e = ibinn_set_smem(aio_mix_kernel<1>, sm);
+    if (e) return e;
+    IBINN_LAUNCH(aio_mix_kernel<1>, dim3(B), dim3(IBINN_THREADS), sm, (cudaStream_t)stream, p);
+    return ibinn_launch_status();
+}
+
+extern "C" int ibinn_aio_affine_inverse(float* u, const float* a, const float* act_norm, float* jac, int B, int C, int H,
+                                        int W, float clamp, float alpha, ibinn_stream_t stream) {
+    IBINN_ENTRY_GUARD();
+    if (!u || !act_norm || !jac || (C > 1 && !a)) return IBINN_ENULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return IBINN_EINVAL;
+    AioP p{};
+    p.out = u; p.a = a; p.an = act_norm; p.jac = jac; p.B = B; p.C = C; p.HW = H * W; p.clamp = clamp; p.alpha = alpha;
+    IBINN_LAUNCH(aio_affine_inverse_kernel, dim3(B), dim3(IBINN_THREADS), 0, (cudaStream_t)stream, p);
+    return ibinn_launch_status();
+}
+
+extern "C" int ibinn_aio_coupling_backward(const float* g_out, const float* g_jac, const float* x, const float* a,
+                                           const float* out, const float* w, const float* act_norm,
+                                           const float* act_offset, float* g_x, float* g_a, float* g_act_norm,
+                                           float* g_act_offset, float* partials, uint32_t* counter, int B, int C, int H,
+                                           int W, float clamp, float alpha, ibinn_stream_t stream) {
+    IBINN_ENTRY_GUARD();
+    if (!g_out || !x || !out || !w || !act_norm || !act_offset || !g_x || !partials || !counter) return IBINN_ENULL;
+    if (C > 1 && (!a || !g_a)) return IBINN_ENULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return IBINN_EINVAL;
+    AioP p{};
+    p.g_out = g_out; p.g_jac = g_jac; p.x = x; p.a = a; p.out_saved = out; p.w = w; p.an = act_norm; p.off = act_offset;
+    p.g_x = g_x; p.g_a = g_a; p.g_an = g_act_norm; p.g_off = g_act_offset; p.partials = partials; p.counter = counter;
+    p.B = B; p.C = C; p.HW = H * W; p.clamp = clamp; p.alpha = alpha;
+    size_t sm = aio_smem(C, H * W);
+    int e = ibinn_set_smem(aio_bwd_kernel, sm);
+    if (e) return e;
+    IBINN_LAUNCH(aio_bwd_kernel, dim3(B), dim3(IBINN_THREADS), sm, (cudaStream_t)stream, p);
+    return ibinn_launch_status();
+}
+
+static int s2d_check(int B, int cp, int H, int W) {
+    if (B <= 0 || cp <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return IBINN_EINVAL;
+    return 0;
+}
+
+extern "C" int ibinn_s2d_coupling_forward(const float* x, int64_t x_bs, const float* a, float* out, int64_t out_bs,
+                                          float* jac, int jac_accumulate, int B, int cp, int H, int W, float clamp,
+                                          float alpha, ibinn_stream_t stream) {
+    IBINN_ENTRY_GUARD();
+    if (!x || !a || !out || !jac) return IBINN_ENULL;
+    int e = s2d_check(B, cp, H, W);
+    if (e) return e;
+    S2dP p{};
+    p.x = x; p.x_bs = x_bs; p.a = a; p.out = out; p.out_bs = out_bs; p.jac = jac; p.jac_acc = jac_accumulate;
+    p.B = B; p.cp = cp; p.H = H; p.W = W; p.clamp = clamp; p.alpha = alpha;
+    IBINN_LAUNCH(s2d_kernel<0>, dim3(B), dim3(IBINN_THREADS), 0, (cudaStream_t)stream, p);
+    return ibinn_launch_status();
+}
+
+extern "C" int ibinn_s2d_coupling_inverse(const float* y, int64_t y_bs, const float* a, float* x, int64_t x_bs,
+                                          float* jac, int jac_accumulate, int B, int cp, int H, int W, float clamp,
+                                          float alpha, ibinn_stream_t stream) {
+    IBINN_ENTRY_GUARD();
+    if (!x || !a || !y || !jac) return IBINN_ENULL;
+    int e = s2d_check(B, cp, H, W);
+    if (e) return e;
+    S2dP p{};
+    p.x = x; p.x_bs = x_bs; p.a = a; p.out = const_cast<float*>(y); p.out_bs = y_bs; p.jac = jac; p.jac_acc = jac_accumulate;
+    p.B = B; p.cp = cp; p.H = H; p.W = W; p.clamp = clamp; p.alpha = alpha;
+    IBINN_LAUNCH(s2d_kernel<1>, dim3(B), dim3(IBINN_THREADS), 0, (cudaStream_t)stream, p);
+    return ibinn_launch_status();
+}
+
+extern "C" int ibinn_s2d_coupling_backward(const float* g_out, int64_t g_bs, const float* g_jac, const float* x,
+                                           int64_t x_bs, const float* a, float* g_x, int64_t gx_bs, float* g_a, int B,
+                                           int cp, int H, int W, float clamp, float alpha, ibinn_stream_t stream) {
+    IBINN_ENTRY_GUARD();
+    if (!g_out || !x || !a || !g_x || !g_a) return IBINN_ENULL;
+    int e = s2d_check(B, cp, H, W);
+    if (e) return e;
+    S2dP p{};
+    p.g_out = g_out; p.g_bs = g_bs; p.g_jac = g_jac; p.x = x; p.x_bs = x_bs; p.a = a; p.g_x = g_x; p.gx_bs = gx_bs; p.g_a = g_a;
+    p.B = B; p.cp = cp; p.H = H; p.W = W; p.clamp = clamp; p.alpha = alpha;
+    IBINN_LAUNCH(s2d_kernel<2>, dim3(B), dim3(IBINN_THREADS), 0, (cudaStream_t)stream, p);
+    return ibinn_launch_status();
+}
+
+extern "C" int ibinn_glow_affine_forward(const float* x, int64_t x_rs, const float* r, float* y, int64_t y_rs, float* jac,
+                                         int jac_accumulate, int B, int L, float clamp, ibinn_stream_t stream) {
+    IBINN_ENTRY_GUARD();
+    if (!x || !r || !y || !jac) return IBINN_ENULL;
+    if (B <= 0 || L <= 0) return IBINN_EINVAL;
+    GlowP p{};
+    p.x = x; p.x_rs = x_rs; p.r = r; p.y = y; p.y_rs = y_rs; p.jac = jac; p.jac_acc = jac_accumulate; p.B = B; p.L = L; p.clamp = clamp;
+    IBINN_LAUNCH(glow_kernel<0>, dim3(B), dim3(IBINN_THREADS), 0, (cudaStream_t)stream, p);
+    return ibinn_launch_status();
+}
+
+extern "C" int ibinn_glow_affine_inverse(const float* y, int64_t y_rs, const float* r, float* x, int64_t x_rs, float* jac,
+                                         int jac_accumulate, int B, int L, float clamp, ibinn_stream_t stream) {
+    IBINN_ENTRY_GUARD();
+    if (!x || !r || !y || !jac) return IBINN_ENULL;
+    if (B <= 0 || L <= 0) return IBINN_EINVAL;
+    GlowP p{};
+    p.x = y; p.x_rs = y_rs; p.r = r; p.y = x; p.y_rs = x_rs; p.jac = jac; p.jac_acc = jac_accumulate; p.B = B; p.L = L; p.clamp = clamp;
+    IBINN_LAUNCH(glow_kernel<1>, dim3(B), dim3(IBINN_THREADS), 0, (cudaStream_t)stream, p);
+    return ibinn_launch_status();
+}
+
+extern "C" int ibinn_glow_affine_backward(const float* g_y, int64_t gy_rs, const float* g_jac, const float* x, int64_t x_rs,
+                                          const float* r, float* g_x, int64_t gx_rs, float* g_r, int B, int L, float clamp,
+                                          ibinn_stream_t stream) {
+    IBINN_ENTRY_GUARD();
+    if (!g_y || !x || !r || !g_x || !g_r) return IBINN_ENULL;
+    if (B <= 0 || L <= 0) return IBINN_EINVAL;
+    GlowP p{};
+    p.g_y = g_y; p.gy_rs = gy_rs; p.g_jac = g_jac; p.x = x; p.x_rs = x_rs; p.r = r; p.g_x = g_x; p.gx_rs = gx_rs; p.g_r = g_r;
+    p.B = B; p.L = L; p.clamp = clamp;
+    IBINN_LAUNCH(glow_kernel<2>, dim3(B), dim3(IBINN_THREADS), 0, (cudaStream_t)stream, p);
+    return ibinn_launch_status();
+}

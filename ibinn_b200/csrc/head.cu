@@ -1,0 +1,289 @@
+// Class-conditional Gaussian-mixture head and the Information-Bottleneck loss terms
+// (reference model.py:113-126 `cluster_distances`, model.py:144-163 loss dict) in one pass over z,
+// plus the hand-derived backward.
+//
+// Distances are evaluated as sum_d (z_d - mu_kd)^2 (not the expanded -2 z.mu + |z|^2 + |mu|^2 the
+// reference uses): same value in exact arithmetic, no cancellation in fp32.
+#include "common.cuh"
+
+namespace {
+
+struct HeadP {
+    const float* z; const float* jac; const float* mu; const float* phi; const float* y;
+    float* Lx; float* logits; float* Lc; float* Ly; float* correct; float* lse; float* means;
+    float* partials; unsigned* counter;
+    int B, C, D;
+};
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// log_softmax(phi) into s_lw (C floats); call with all threads, then __syncthreads().
+__device__ __forceinline__ void log_softmax_phi(const float* phi, int C, float* s_lw) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        float m = -INFINITY;
+        for (int k = lane; k < C; k += 32) m = fmaxf(m, __ldg(phi + k));
+        m = warp_max(m);
+        float s = 0.f;
+        for (int k = lane; k < C; k += 32) s += expf(__ldg(phi + k) - m);
+        s = warp_sum(s);
+        const float l = m + logf(s);
+        for (int k = lane; k < C; k += 32) s_lw[k] = __ldg(phi + k) - l;
+    }
+}
+
+__global__ void __launch_bounds__(IBINN_THREADS) head_fwd_kernel(const HeadP p) {
+    IBINN_DYN_SMEM(float, smem);
+    __shared__ int s_flag;
+    const int B = p.B, C = p.C, D = p.D;
+    float* s_z = smem;          // [D]
+    float* s_zz = s_z + D;      // [C]
+    float* s_lw = s_zz + C;     // [C]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, b = blockIdx.x;
+    for (int d = tid; d < D; d += IBINN_THREADS) s_z[d] = __ldg(p.z + (size_t)b * D + d);
+    log_softmax_phi(p.phi, C, s_lw);
+    __syncthreads();
+    for (int k = wid; k < C; k += IBINN_THREADS / 32) {
+        const float* mk = p.mu + (size_t)k * D;
+        float acc = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            const float t = s_z[d] - __ldg(mk + d);
+            acc = fmaf(t, t, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) s_zz[k] = acc;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        const float jac = __ldg(p.jac + b);
+        float m = -INFINITY;
+        for (int k = lane; k < C; k += 32) m = fmaxf(m, -0.5f * s_zz[k] + s_lw[k]);
+        m = warp_max(m);
+        float s = 0.f;
+        for (int k = lane; k < C; k += 32) s += expf(-0.5f * s_zz[k] + s_lw[k] - m);
+        s = warp_sum(s);
+        const float lse = m + logf(s);
+        float sl = 0.f;
+        for (int k = lane; k < C; k += 32) {
+            const float lg = -0.5f * s_zz[k];
+            p.logits[(size_t)b * C + k] = lg;
+            sl += lg;
+        }
+        sl = warp_sum(sl);
+        float lc = 0.f, ly = 0.f;
+        float by = -INFINITY, bl = -INFINITY; int iy = 0x7fffffff, il = 0x7fffffff;
+        if (p.y) {
+            for (int k = lane; k < C; k += 32) {
+                const float yk = __ldg(p.y + (size_t)b * C + k);
+                const float lg = -0.5f * s_zz[k];
+                lc = fmaf(s_zz[k], rintf(yk), lc);
+                ly = fmaf(yk, lg - lse, ly);   // log_softmax(l)_k - logw_k with l_k = lg + logw_k
+                if (yk > by) { by = yk; iy = k; }
+                if (lg > bl) { bl = lg; il = k; }
+            }
+            lc = warp_sum(lc);
+            ly = warp_sum(ly);
+            // arg max with first-index tie break (torch.max semantics)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float oy = __shfl_xor_sync(0xffffffffu, by, o); const int oiy = __shfl_xor_sync(0xffffffffu, iy, o);
+                if (oy > by || (oy == by && oiy < iy)) { by = oy; iy = oiy; }
+                const float ol = __shfl_xor_sync(0xffffffffu, bl, o); const int oil = __shfl_xor_sync(0xffffffffu, il, o);
+                if (ol > bl || (ol == bl && oil < il)) { bl = ol; il = oil; }
+            }
+        }
+        if (lane == 0) {
+            const float lx = (-lse - jac) / (float)D;
+            p.Lx[b] = lx;
+            p.lse[b] = lse;
+            float* pr = p.partials + (size_t)b * 5;
+            pr[0] = lx; pr[1] = sl;
+            if (p.y) {
+                const float c = (0.5f * lc - jac) / (float)D;
+                const float ok = (iy == il) ? 1.f : 0.f;
+                p.Lc[b] = c; p.Ly[b] = ly; p.correct[b] = ok;
+                pr[2] = c; pr[3] = ly; pr[4] = ok;
+            } else { pr[2] = 0.f; pr[3] = 0.f; pr[4] = 0.f; }
+        }
+    }
+    if (!last_block_ticket(p.counter, gridDim.x, &s_flag)) return;
+    if (tid < 5) {
+        double t = 0.;
+        for (int bb = 0; bb < B; ++bb) t += (double)p.partials[(size_t)bb * 5 + tid];
+        p.means[tid] = (float)(t / (tid == 1 ? (double)B * C : (double)B));
+    }
+    if (tid == 0) *p.counter = 0u;
+}
+
+struct HeadBwdP {
+    const float* z; const float* mu; const float* phi; const float* y; const float* logits; const float* lse;
+    const float* gLx; const float* gLc; const float* gLy; const float* gLogits;   // may be NULL
+    int sLx, sLc, sLy, sLogits;                                                   // element strides (0 = broadcast scalar)
+    float scale_vec, scale_logits;                                                // applied to the incoming grads
+    float* G; float* Glw; float* g_jac;                                           // (B,C), (B,C), (B)
+    float* g_z; float* g_mu; float* g_phi; int acc_mu, acc_phi;
+    int B, C, D, dchunk;
+};
+
+// per sample: G = dLoss/dzz, Glw = dLoss/dlogw contributions, g_jac
+__global__ void __launch_bounds__(IBINN_THREADS) head_bwd_g_kernel(const HeadBwdP p) {
+    __shared__ float s_lw[1024];
+    const int C = p.C, b = blockIdx.x, tid = threadIdx.x;
+    log_softmax_phi(p.phi, C, s_lw);
+    __syncthreads();
+    const float invD = 1.f / (float)p.D;
+    const float glx = p.gLx ? __ldg(p.gLx + (size_t)b * p.sLx) * p.scale_vec : 0.f;
+    const float glc = p.gLc ? __ldg(p.gLc + (size_t)b * p.sLc) * p.scale_vec : 0.f;
+    const float gly = p.gLy ? __ldg(p.gLy + (size_t)b * p.sLy) * p.scale_vec : 0.f;
+    const float lse = __ldg(p.lse + b);
+    __shared__ float s_scr[40];
+    float sy = 0.f;
+    if (p.y) for (int k = tid; k < C; k += IBINN_THREADS) sy += __ldg(p.y + (size_t)b * C + k);
+    sy = block_sum(sy, s_scr);
+    for (int k = tid; k < C; k += IBINN_THREADS) {
+        const float lg = __ldg(p.logits + (size_t)b * C + k);
+        const float pk = expf(lg + s_lw[k] - lse);
+        float g = glx * pk * 0.5f * invD;
+        if (p.y) {
+            const float yk = __ldg(p.y + (size_t)b * C + k);
+            g += gly * (-0.5f * yk + 0.5f * pk * sy) + glc * rintf(yk) * 0.5f * invD;
+        }
+        if (p.gLogits) g -= 0.5f * __ldg(p.gLogits + ((size_t)b * C + k) * p.sLogits) * p.scale_logits;
+        p.G[(size_t)b * C + k] = g;
+        p.Glw[(size_t)b * C + k] = -glx * pk * invD;
+    }
+    if (tid == 0) p.g_jac[b] = -(glx + glc) * invD;
+}
+
+// per chunk of latent dims: g_z = 2 (z rowsum(G) - G mu), g_mu = -2 (G^T z - mu colsum(G)); block 0 also g_phi
+__global__ void __launch_bounds__(IBINN_THREADS) head_bwd_zmu_kernel(const HeadBwdP p) {
+    IBINN_DYN_SMEM(float, smem);
+    const int B = p.B, C = p.C, D = p.D, DC = p.dchunk;
+    const int d0 = blockIdx.x * DC, nd = min(DC, D - d0);
+    float* s_G = smem;                 // [B][C]
+    float* s_z = s_G + (size_t)B * C;  // [B][DC]
+    float* s_mu = s_z + (size_t)B * DC;  // [C][DC]
+    float* s_rs = s_mu + (size_t)C * DC; // [B] row sums
+    float* s_cs = s_rs + B;              // [C] col sums
+    const int tid = threadIdx.x;
+    for (int e = tid; e < B * C; e += IBINN_THREADS) s_G[e] = __ldg(p.G + e);
+    for (int e = tid; e < B * DC; e += IBINN_THREADS) {
+        const int bb = e / DC, d = e - bb * DC;
+        s_z[e] = d < nd ? __ldg(p.z + (size_t)bb * D + d0 + d) : 0.f;
+    }
+    for (int e = tid; e < C * DC; e += IBINN_THREADS) {
+        const int k = e / DC, d = e - k * DC;
+        s_mu[e] = d < nd ? __ldg(p.mu + (size_t)k * D + d0 + d) : 0.f;
+    }
+    __syncthreads();
+    for (int bb = tid; bb < B; bb += IBINN_THREADS) {
+        float s = 0.f;
+        for (int k = 0; k < C; ++k) s += s_G[bb * C + k];
+        s_rs[bb] = s;
+    }
+    for (int k = tid; k < C; k += IBINN_THREADS) {
+        float s = 0.f;
+        for (int bb = 0; bb < B; ++bb) s += s_G[bb * C + k];
+        s_cs[k] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < B * DC; e += IBINN_THREADS) {
+        const int bb = e / DC, d = e - bb * DC;
+        if (d >= nd) continue;
+        float acc = 0.f;
+        for (int k = 0; k < C; ++k) acc = fmaf(s_G[bb * C + k], s_mu[k * DC + d], acc);
+        p.g_z[(size_t)bb * D + d0 + d] = 2.f * (s_z[e] * s_rs[bb] - acc);
+    }
+    if (p.g_mu) {
+        for (int e = tid; e < C * DC; e += IBINN_THREADS) {
+            const int k = e / DC, d = e - k * DC;
+            if (d >= nd) continue;
+            float acc = 0.f;
+            for (int bb = 0; bb < B; ++bb) acc = fmaf(s_G[bb * C + k], s_z[bb * DC + d], acc);
+            const float v = -2.f * (acc - s_mu[e] * s_cs[k]);
+            float* dst = p.g_mu + (size_t)k * D + d0 + d;
+            if (p.acc_mu) *dst += v; else *dst = v;
+        }
+    }
+    if (blockIdx.x == 0 && p.g_phi) {
+        // g_logw_k = sum_b Glw[b][k];  g_phi = g_logw - softmax(phi) * sum_k g_logw
+        __shared__ float s_lw[1024];
+        __shared__ float s_gl[1024];
+        __shared__ float s_scr[40];
+        log_softmax_phi(p.phi, C, s_lw);
+        float part = 0.f;
+        for (int k = tid; k < C; k += IBINN_THREADS) {
+            float s = 0.f;
+            for (int bb = 0; bb < B; ++bb) s += __ldg(p.Glw + (size_t)bb * C + k);
+            s_gl[k] = s;
+            part += s;
+        }
+        const float tot = block_sum(part, s_scr);
+        for (int k = tid; k < C; k += IBINN_THREADS) {
+            const float v = s_gl[k] - expf(s_lw[k]) * tot;
+            if (p.acc_phi) p.g_phi[k] += v; else p.g_phi[k] = v;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int64_t ibinn_gmm_head_partials_floats(int B) { return (int64_t)B * 5; }
+
+extern "C" int ibinn_gmm_head_forward(const float* z, const float* jac, const float* mu, const float* phi, const float* y,
+                                      float* L_x, float* logits, float* L_cNLL, float* L_y, float* correct, float* lse,
+                                      float* means, float* partials, uint32_t* counter, int B, int C, int D,
+                                      ibinn_stream_t stream) {
+    int e = ibinn_check_device();
+    if (e) return e;
+    if (!z || !jac || !mu || !phi || !L_x || !logits || !lse || !means || !partials || !counter) return IBINN_ENULL;
+    if (y && (!L_cNLL || !L_y || !correct)) return IBINN_ENULL;
+    if (B <= 0 || C <= 0 || D <= 0 || C > 1024) return IBINN_EINVAL;
+    HeadP p{};
+    p.z = z; p.jac = jac; p.mu = mu; p.phi = phi; p.y = y; p.Lx = L_x; p.logits = logits; p.Lc = L_cNLL; p.Ly = L_y;
+    p.correct = correct; p.lse = lse; p.means = means; p.partials = partials; p.counter = counter; p.B = B; p.C = C; p.D = D;
+    size_t sm = ((size_t)D + 2 * C + 8) * sizeof(float);
+    e = ibinn_set_smem(head_fwd_kernel, sm);
+    if (e) return e;
+    IBINN_LAUNCH(head_fwd_kernel, dim3(B), dim3(IBINN_THREADS), sm, (cudaStream_t)stream, p);
+    return ibinn_launch_status();
+}
+
+extern "C" int ibinn_gmm_head_backward(const float* z, const float* mu, const float* phi, const float* y, const float* logits,
+                                       const float* lse, const float* g_Lx, int s_Lx, const float* g_LcNLL, int s_Lc,
+                                       const float* g_Ly, int s_Ly, const float* g_logits, int s_logits, float scale_vec,
+                                       float scale_logits, float* G_ws, float* Glw_ws, float* g_z, float* g_jac, float* g_mu,
+                                       int accumulate_mu, float* g_phi, int accumulate_phi, int B, int C, int D,
+                                       ibinn_stream_t stream) {
+    int e = ibinn_check_device();
+    if (e) return e;
+    if (!z || !mu || !phi || !logits || !lse || !G_ws || !Glw_ws || !g_z || !g_jac) return IBINN_ENULL;
+    if (B <= 0 || C <= 0 || D <= 0 || C > 1024) return IBINN_EINVAL;
+    HeadBwdP p{};
+    p.z = z; p.mu = mu; p.phi = phi; p.y = y; p.logits = logits; p.lse = lse;
+    p.gLx = g_Lx; p.gLc = g_LcNLL; p.gLy = g_Ly; p.gLogits = g_logits;
+    p.sLx = s_Lx; p.sLc = s_Lc; p.sLy = s_Ly; p.sLogits = s_logits; p.scale_vec = scale_vec; p.scale_logits = scale_logits;
+    p.G = G_ws; p.Glw = Glw_ws; p.g_jac = g_jac; p.g_z = g_z; p.g_mu = g_mu; p.g_phi = g_phi;
+    p.acc_mu = accumulate_mu; p.acc_phi = accumulate_phi; p.B = B; p.C = C; p.D = D;
+    cudaStream_t st = (cudaStream_t)stream;
+    IBINN_LAUNCH(head_bwd_g_kernel, dim3(B), dim3(IBINN_THREADS), 0, st, p);
+    e = ibinn_launch_status();
+    if (e) return e;
+    int dc = 32;
+    size_t sm;
+    for (;;) {
+        sm = ((size_t)B * C + (size_t)B * dc + (size_t)C * dc + B + C + 8) * sizeof(float);
+        if (sm <= 200 * 1024 || dc == 4) break;
+        dc /= 2;
+    }
+    if (sm > 200 * 1024) return IBINN_EINVAL;
+    p.dchunk = dc;
+    e = ibinn_set_smem(head_bwd_zmu_kernel, sm);
+    if (e) return e;
+    IBINN_LAUNCH(head_bwd_zmu_kernel, dim3((D + dc - 1) / dc), dim3(IBINN_THREADS), sm, st, p);
+    return ibinn_launch_status();
+}

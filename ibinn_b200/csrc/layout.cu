@@ -1,0 +1,171 @@
+// Data-movement nodes of the IB-INN graph (HBM-bound, no parameters to learn):
+//   * DCTPooling2d        reference dct_transform.py:64-104 (separable NxN transform + channel-fastest flatten)
+//   * HaarDownsampling    FrEIA v0.2, used at reference inn_architecture.py:127
+//   * PermuteRandom       FrEIA v0.2, used at reference inn_architecture.py:160
+#include "common.cuh"
+
+namespace {
+
+// out[b, (kw*N + kh)*C + c] = scale * sum_{h,w} M[kh][h] M[kw][w] x[b,c,h,w]
+__global__ void __launch_bounds__(IBINN_THREADS) dct_fwd_kernel(const float* __restrict__ x, const float* __restrict__ M,
+                                                                float* __restrict__ out, int C, int N, float scale) {
+    IBINN_DYN_SMEM(float, smem);
+    const int D = C * N * N, NN = N * N;
+    float* s_x = smem;
+    float* s_t = s_x + D;
+    float* s_M = s_t + D;
+    const int tid = threadIdx.x;
+    const size_t base = (size_t)blockIdx.x * D;
+    for (int e = tid; e < D; e += IBINN_THREADS) s_x[e] = __ldg(x + base + e);
+    for (int e = tid; e < NN; e += IBINN_THREADS) s_M[e] = __ldg(M + e);
+    __syncthreads();
+    // t[c][h][kw] = sum_w M[kw][w] x[c][h][w]
+    for (int e = tid; e < D; e += IBINN_THREADS) {
+        const int kw = e % N, ch = e / N;
+        float acc = 0.f;
+        for (int w = 0; w < N; ++w) acc = fmaf(s_M[kw * N + w], s_x[ch * N + w], acc);
+        s_t[e] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < D; e += IBINN_THREADS) {
+        const int c = e % C, kk = e / C;
+        const int kh = kk % N, kw = kk / N;
+        float acc = 0.f;
+        for (int h = 0; h < N; ++h) acc = fmaf(s_M[kh * N + h], s_t[(c * N + h) * N + kw], acc);
+        out[base + e] = acc * scale;
+    }
+}
+
+// x[b,c,h,w] = scale * sum_{kh,kw} A(h,kh) A(w,kw) t[b, (kw*N + kh)*C + c],  A(r,k) = tr ? M[k][r] : M[r][k]
+__global__ void __launch_bounds__(IBINN_THREADS) dct_inv_kernel(const float* __restrict__ t, const float* __restrict__ M,
+                                                                float* __restrict__ x, int C, int N, float scale, int tr) {
+    IBINN_DYN_SMEM(float, smem);
+    const int D = C * N * N, NN = N * N;
+    float* s_t = smem;       // [c][kh][kw]
+    float* s_u = s_t + D;    // [c][kh][w]
+    float* s_A = s_u + D;    // A(r,k) row-major
+    const int tid = threadIdx.x;
+    const size_t base = (size_t)blockIdx.x * D;
+    for (int e = tid; e < D; e += IBINN_THREADS) {
+        const int c = e % C, kk = e / C;
+        const int kh = kk % N, kw = kk / N;
+        s_t[(c * N + kh) * N + kw] = __ldg(t + base + e);
+    }
+    for (int e = tid; e < NN; e += IBINN_THREADS) {
+        const int r = e / N, k = e % N;
+        s_A[e] = tr ? __ldg(M + k * N + r) : __ldg(M + e);
+    }
+    __syncthreads();
+    for (int e = tid; e < D; e += IBINN_THREADS) {
+        const int w = e % N, ck = e / N;
+        float acc = 0.f;
+        for (int kw = 0; kw < N; ++kw) acc = fmaf(s_A[w * N + kw], s_t[ck * N + kw], acc);
+        s_u[e] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < D; e += IBINN_THREADS) {
+        const int w = e % N, h = (e / N) % N, c = e / NN;
+        float acc = 0.f;
+        for (int kh = 0; kh < N; ++kh) acc = fmaf(s_A[h * N + kh], s_u[(c * N + kh) * N + w], acc);
+        x[base + e] = acc * scale;
+    }
+}
+
+// MODE 0: y[b,4c+j,h,w] = fac * sum_{dy,dx} sgn_j(dy,dx) x[b,c,2h+dy,2w+dx]
+// MODE 1: x[b,c,2h+dy,2w+dx] = fac * sum_j sgn_j(dy,dx) y[b,4c+j,h,w]      (transpose == inverse up to fac)
+template <int MODE>
+__global__ void __launch_bounds__(IBINN_THREADS) haar_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                             long long nblk, int C, int H, int W, float fac) {
+    const int Ho = H / 2, Wo = W / 2;
+    for (long long e = (long long)blockIdx.x * IBINN_THREADS + threadIdx.x; e < nblk; e += (long long)gridDim.x * IBINN_THREADS) {
+        const int w = (int)(e % Wo);
+        const int h = (int)((e / Wo) % Ho);
+        const long long bc = e / ((long long)Wo * Ho);   // b*C + c
+        const size_t hi = ((size_t)bc * H + 2 * h) * W + 2 * w;                 // full-res 2x2 block origin
+        const size_t lo = ((size_t)bc * 4 * Ho + h) * Wo + w;                   // channel 4c+0 at (h,w)
+        const size_t cs = (size_t)Ho * Wo;
+        float v0, v1, v2, v3;
+        if (MODE == 0) { v0 = __ldg(in + hi); v1 = __ldg(in + hi + 1); v2 = __ldg(in + hi + W); v3 = __ldg(in + hi + W + 1); }
+        else { v0 = __ldg(in + lo); v1 = __ldg(in + lo + cs); v2 = __ldg(in + lo + 2 * cs); v3 = __ldg(in + lo + 3 * cs); }
+        // the 4x4 sign matrix is symmetric: row j / column (dy,dx): [++++], [+-+-], [++--], [+--+]
+        const float r0 = (v0 + v1 + v2 + v3) * fac;
+        const float r1 = (v0 - v1 + v2 - v3) * fac;
+        const float r2 = (v0 + v1 - v2 - v3) * fac;
+        const float r3 = (v0 - v1 - v2 + v3) * fac;
+        if (MODE == 0) { out[lo] = r0; out[lo + cs] = r1; out[lo + 2 * cs] = r2; out[lo + 3 * cs] = r3; }
+        else { out[hi] = r0; out[hi + 1] = r1; out[hi + W] = r2; out[hi + W + 1] = r3; }
+    }
+}
+
+__global__ void __launch_bounds__(IBINN_THREADS) gather_kernel(const float* __restrict__ x, const int* __restrict__ idx,
+                                                               float* __restrict__ out, long long n, int D) {
+    for (long long e = (long long)blockIdx.x * IBINN_THREADS + threadIdx.x; e < n; e += (long long)gridDim.x * IBINN_THREADS) {
+        const long long b = e / D;
+        const int i = (int)(e - b * D);
+        out[e] = __ldg(x + b * D + __ldg(idx + i));
+    }
+}
+
+static inline unsigned grid_for(long long n) {
+    long long g = (n + IBINN_THREADS - 1) / IBINN_THREADS;
+    const long long cap = 148LL * 16;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" int ibinn_dct2d_forward(const float* x, const float* M, float* out, int B, int C, int N, float scale,
+                                   ibinn_stream_t stream) {
+    int e = ibinn_check_device();
+    if (e) return e;
+    if (!x || !M || !out) return IBINN_ENULL;
+    if (B <= 0 || C <= 0 || N <= 0 || N > 64) return IBINN_EINVAL;
+    size_t sm = ((size_t)2 * C * N * N + (size_t)N * N) * sizeof(float);
+    e = ibinn_set_smem(dct_fwd_kernel, sm);
+    if (e) return e;
+    IBINN_LAUNCH(dct_fwd_kernel, dim3(B), dim3(IBINN_THREADS), sm, (cudaStream_t)stream, x, M, out, C, N, scale);
+    return ibinn_launch_status();
+}
+
+extern "C" int ibinn_dct2d_inverse(const float* t, const float* M, float* x, int B, int C, int N, float scale,
+                                   int transpose_M, ibinn_stream_t stream) {
+    int e = ibinn_check_device();
+    if (e) return e;
+    if (!x || !M || !t) return IBINN_ENULL;
+    if (B <= 0 || C <= 0 || N <= 0 || N > 64) return IBINN_EINVAL;
+    size_t sm = ((size_t)2 * C * N * N + (size_t)N * N) * sizeof(float);
+    e = ibinn_set_smem(dct_inv_kernel, sm);
+    if (e) return e;
+    IBINN_LAUNCH(dct_inv_kernel, dim3(B), dim3(IBINN_THREADS), sm, (cudaStream_t)stream, t, M, x, C, N, scale, transpose_M);
+    return ibinn_launch_status();
+}
+
+extern "C" int ibinn_haar_forward(const float* x, float* y, int B, int C, int H, int W, float fac, ibinn_stream_t stream) {
+    int e = ibinn_check_device();
+    if (e) return e;
+    if (!x || !y) return IBINN_ENULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return IBINN_EINVAL;
+    const long long n = (long long)B * C * (H / 2) * (W / 2);
+    IBINN_LAUNCH(haar_kernel<0>, dim3(grid_for(n)), dim3(IBINN_THREADS), 0, (cudaStream_t)stream, x, y, n, C, H, W, fac);
+    return ibinn_launch_status();
+}
+
+extern "C" int ibinn_haar_inverse(const float* y, float* x, int B, int C, int H, int W, float fac, ibinn_stream_t stream) {
+    int e = ibinn_check_device();
+    if (e) return e;
+    if (!x || !y) return IBINN_ENULL;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return IBINN_EINVAL;
+    const long long n = (long long)B * C * (H / 2) * (W / 2);
+    IBINN_LAUNCH(haar_kernel<1>, dim3(grid_for(n)), dim3(IBINN_THREADS), 0, (cudaStream_t)stream, y, x, n, C, H, W, fac);
+    return ibinn_launch_status();
+}
+
+extern "C" int ibinn_permute_features(const float* x, const int32_t* index, float* out, int B, int D, ibinn_stream_t stream) {
+    int e = ibinn_check_device();
+    if (e) return e;
+    if (!x || !index || !out) return IBINN_ENULL;
+    if (B <= 0 || D <= 0) return IBINN_EINVAL;
+    const long long n = (long long)B * D;
+    IBINN_LAUNCH(gather_kernel, dim3(grid_for(n)), dim3(IBINN_THREADS), 0, (cudaStream_t)stream, x, (const int*)index, out, n, D);
+    return ibinn_launch_status();
+}

@@ -1,0 +1,24 @@
+// Device gate: the library serves sm_100 (B200) only and has no other path.
+#include "common.cuh"
+
+extern "C" int ibinn_abi_version(void) { return 1; }
+
+extern "C" int ibinn_check_device(void) {
+#ifdef IBINN_EMU
+    return 0;
+#else
+    static int cached[64] = {0};   // 0 unknown, 1 ok, 2 wrong arch
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    if (dev >= 0 && dev < 64 && cached[dev]) return cached[dev] == 1 ? 0 : IBINN_EARCH;
+    int major = 0, minor = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    if (e != cudaSuccess) return (int)e;
+    const bool ok = (major == 10 && minor == 0);
+    if (dev >= 0 && dev < 64) cached[dev] = ok ? 1 : 2;
+    return ok ? 0 : IBINN_EARCH;
+#endif
+}

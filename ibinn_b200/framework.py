@@ -1,0 +1,97 @@
+"""Graph container with the FrEIA-v0.2 API surface the reference uses (FrEIA itself is an
+un-vendored dependency, requirements.txt:2; call sites reference inn_architecture.py:122-164,
+model.py:141-142,235, train.py:161-163).  Every graph the reference builds is a chain, so the
+container is a sequential interpreter; node modules keep the FrEIA protocol
+`__init__(dims_in, **kw)`, `forward([x], rev) -> [y]`, `jacobian([x], rev)`, `output_dims(dims)`.
+"""
+import torch
+import torch.nn as nn
+
+
+class Node:
+    def __init__(self, inputs, module_type, module_args, conditions=None, name=None):
+        if isinstance(inputs, Node):
+            inputs = [(inputs, 0)]
+        elif isinstance(inputs, tuple) and len(inputs) == 2 and isinstance(inputs[0], Node):
+            inputs = [inputs]
+        if conditions:
+            raise ValueError('conditional nodes are not used by IB-INN and not supported')
+        self.inputs = list(inputs)
+        self.module_type, self.module_args, self.name = module_type, module_args, name
+        self.module, self.output_dims = None, None
+
+    @property
+    def out0(self):
+        return (self, 0)
+
+    def build(self):
+        dims_in = [src.output_dims[idx] for src, idx in self.inputs]
+        self.module = self.module_type(dims_in, **self.module_args)
+        self.output_dims = [tuple(d) for d in self.module.output_dims(dims_in)]
+
+
+class InputNode(Node):
+    def __init__(self, *dims, name='node'):
+        self.inputs, self.name, self.module = [], name, None
+        self.output_dims = [tuple(dims)]
+
+    def build(self):
+        pass
+
+
+class OutputNode(Node):
+    def __init__(self, inputs, name='node'):
+        if isinstance(inputs, Node):
+            inputs = [(inputs, 0)]
+        elif isinstance(inputs, tuple) and len(inputs) == 2 and isinstance(inputs[0], Node):
+            inputs = [inputs]
+        self.inputs, self.name, self.module, self.output_dims = list(inputs), name, None, None
+
+    def build(self):
+        self.output_dims = [src.output_dims[idx] for src, idx in self.inputs]
+
+
+class ReversibleGraphNet(nn.Module):
+    """`inn(x)`, `inn(z, rev=True)`, `inn.log_jacobian(run_forward=False)`; `module_list[i]` follows
+    `node_list[i]` (None for the input / output nodes), `tmp_var_<i>` buffers as in FrEIA so that
+    reference checkpoints and train.py:161-163 keep working."""
+
+    def __init__(self, node_list, ind_in=None, ind_out=None, verbose=True):
+        super().__init__()
+        for k, n in enumerate(node_list):
+            if k > 0 and not isinstance(n, InputNode) and [src for src, _ in n.inputs] != [node_list[k - 1]]:
+                raise ValueError('ibinn_b200 supports chain graphs only (every IB-INN graph is one)')
+            n.build()
+        self.node_list = node_list
+        self.module_list = nn.ModuleList([n.module for n in node_list])
+        for k in range(len(node_list)):
+            self.register_buffer('tmp_var_%d' % k, torch.zeros(1))
+        self._jacs, self._rev = [], False
+        if verbose:
+            for n in node_list:
+                print(n.name, n.output_dims)
+
+    def forward(self, x, c=None, rev=False, intermediate_outputs=False):
+        order = range(len(self.node_list))
+        if rev:
+            order = reversed(order)
+        self._node_inputs, self._jacs, self._rev = {}, [], rev
+        h = x
+        for k in order:
+            m = self.module_list[k]
+            if m is None:
+                continue
+            self._node_inputs[k] = h
+            h = m([h], rev=rev)[0]
+            self._jacs.append((k, h))
+        return h
+
+    def log_jacobian(self, x=None, c=None, rev=False, run_forward=True, intermediate_outputs=False):
+        if run_forward:
+            self.forward(x, rev=rev)
+        total = 0.
+        for k, h in self._node_inputs.items():
+            total = total + self.module_list[k].jacobian([h], rev=rev)
+        return total
+
+    jacobian = log_jacobian

@@ -1,0 +1,394 @@
+"""torch.autograd.Function layer: one Function per graph node (forward = our CUDA kernels,
+backward = the hand-derived CUDA backward), so autograd sees ~60 nodes per step instead of the
+~3500 of the reference.  Parameter gradients are either returned to autograd, or -- when
+engine.FlatParams has attached a flat gradient view to each parameter (`p._ibinn_grad`) --
+accumulated straight into that buffer by the kernels (no per-tensor add kernels).
+"""
+import torch
+
+from . import ops
+from .ops import BN, EPI_BNSTATS, EPI_MASKSTATS, EPI_RELUMASK, EPI_STORE, PRE_BN_RELU, PRE_BNBWD, PRE_NONE, PRE_RELU
+
+
+# ------------------------------------------------------------------------------------ helpers
+
+class GradSink:
+    """Where the kernels of one node accumulate parameter gradients."""
+
+    def __init__(self, params):
+        self.params = list(params)
+        self.direct = all(getattr(p, '_ibinn_grad', None) is not None for p in self.params)
+        if self.direct:
+            self.targets = [p._ibinn_grad for p in self.params]
+        else:
+            total = sum(p.numel() for p in self.params)
+            flat = torch.zeros(total, dtype=torch.float32, device=self.params[0].device)
+            self.targets, o = [], 0
+            for p in self.params:
+                self.targets.append(flat[o:o + p.numel()].view(p.shape))
+                o += p.numel()
+
+    def __getitem__(self, i):
+        return self.targets[i]
+
+    def returns(self):
+        return [None] * len(self.params) if self.direct else list(self.targets)
+
+
+def dropout_mask(shape, p, ref):
+    """Bernoulli(1-p)/(1-p) mask as a float tensor (torch's Philox stream; parity tests inject masks)."""
+    if p <= 0.:
+        return None
+    return (torch.rand(shape, device=ref.device) >= p).to(torch.float32) / (1. - p)
+
+
+# ------------------------------------------------------------------------------------ conv subnet
+
+def conv_subnet_forward(net, x, training, mask=None):
+    """basic_residual_block / strided_residual_block (reference inn_architecture.py:68-110).
+    x: (B,cin,H,W) possibly a channel slice.  Returns a and the tensors the backward needs."""
+    bn1, bn2 = net.bn1, net.bn2
+    dev = x.device
+    width = net.conv1.weight.shape[0]
+    stride2 = 2 if net.strided else 1
+    pre0 = PRE_RELU if net.relu_first else PRE_NONE
+    if training:
+        sv = torch.empty(4, width, dtype=torch.float32, device=dev)
+
+        def stats(bn, k):
+            return dict(save_mean=sv[2 * k], save_invstd=sv[2 * k + 1], running_mean=bn.running_mean,
+                        running_var=bn.running_var, nbt=bn.num_batches_tracked, momentum=bn.momentum, eps=bn.eps)
+        h1 = ops.conv_forward(x, net.conv1.weight, 3, 1, pre=pre0, epi=EPI_BNSTATS, stats=stats(bn1, 0))
+        r1 = BN(sv[0], sv[1], bn1.weight, bn1.bias, bn1.eps, False)
+        h2 = ops.conv_forward(h1, net.conv2.weight, 3, stride2, pre=PRE_BN_RELU, pre_bn=r1, epi=EPI_BNSTATS, stats=stats(bn2, 1))
+        r2 = BN(sv[2], sv[3], bn2.weight, bn2.bias, bn2.eps, False)
+        if mask is None and net.p_drop > 0.:
+            mask = dropout_mask((x.shape[0], width), net.p_drop, x)
+    else:
+        h1 = ops.conv_forward(x, net.conv1.weight, 3, 1, pre=pre0)
+        r1 = BN(bn1.running_mean, bn1.running_var, bn1.weight, bn1.bias, bn1.eps, True)
+        h2 = ops.conv_forward(h1, net.conv2.weight, 3, stride2, pre=PRE_BN_RELU, pre_bn=r1)
+        r2 = BN(bn2.running_mean, bn2.running_var, bn2.weight, bn2.bias, bn2.eps, True)
+        mask = None
+    a = ops.conv_forward(h2, net.conv3.weight, 1, 1, pre=PRE_BN_RELU, pre_bn=r2, pre_mask=mask, bias=net.conv3.bias)
+    return a, (h1, h2, r1, r2, mask, training)
+
+
+CONV_SUBNET_PARAMS = ('conv1.weight', 'bn1.weight', 'bn1.bias', 'conv2.weight', 'bn2.weight', 'bn2.bias', 'conv3.weight', 'conv3.bias')
+
+
+def conv_subnet_params(net):
+    return [net.conv1.weight, net.bn1.weight, net.bn1.bias, net.conv2.weight, net.bn2.weight, net.bn2.bias,
+            net.conv3.weight, net.conv3.bias]
+
+
+def conv_subnet_backward(net, saved, x, g_a, sink, s0, g_in_out, addend):
+    """Backward of conv_subnet_forward.  sink[s0:s0+8] receive the parameter gradients in
+    CONV_SUBNET_PARAMS order; the input gradient (+ addend, may alias) is written to g_in_out."""
+    h1, h2, r1, r2, mask, training = saved
+    dev = x.device
+    width = net.conv1.weight.shape[0]
+    cin = net.conv1.weight.shape[1]
+    stride2 = 2 if net.strided else 1
+    dw1, dg1, db1, dw2, dg2, db2, dw3, dbias3 = [sink[s0 + i] for i in range(8)]
+    sums = torch.empty(2, 2, width, dtype=torch.float32, device=dev)
+    zero_sums = None if training else torch.zeros(2, width, dtype=torch.float32, device=dev)
+    g_a = g_a.contiguous()
+    # 1x1 head
+    ops.conv_wgrad(g_a, h2, dw3, 1, 1, x_pre=PRE_BN_RELU, x_bn=r2, x_mask=mask, dbias=dbias3)
+    g2 = ops.conv_forward(g_a, net.conv3.weight, 1, 1, cout=width, w_transposed=True, epi=EPI_MASKSTATS,
+                          mask=dict(h=h2, bn=r2, drop=mask, sums_out=sums[1], dgamma=dg2, dbeta=db2))
+    s2 = sums[1] if training else zero_sums
+    # middle 3x3 (stride 1 or 2)
+    ops.conv_wgrad(g2, h1, dw2, 3, stride2, g_pre=PRE_BNBWD, gh=h2, g_bn=r2, g_sums=s2, x_pre=PRE_BN_RELU, x_bn=r1)
+    g1 = ops.conv_forward(g2, net.conv2.weight, 3, 1, cout=width, w_transposed=True, pre=PRE_BNBWD, x2=h2, pre_bn=r2, pre_sums=s2,
+                          upsample_to=(h1.shape[2], h1.shape[3]) if net.strided else None, epi=EPI_MASKSTATS,
+                          mask=dict(h=h1, bn=r1, sums_out=sums[0], dgamma=dg1, dbeta=db1))
+    s1 = sums[0] if training else zero_sums
+    # first 3x3
+    ops.conv_wgrad(g1, x, dw1, 3, 1, g_pre=PRE_BNBWD, gh=h1, g_bn=r1, g_sums=s1, x_pre=PRE_RELU if net.relu_first else PRE_NONE)
+    ops.conv_forward(g1, net.conv1.weight, 3, 1, cout=cin, w_transposed=True, pre=PRE_BNBWD, x2=h1, pre_bn=r1, pre_sums=s1,
+                     epi=EPI_RELUMASK if net.relu_first else EPI_STORE, mask=dict(h=x) if net.relu_first else None,
+                     addend=addend, out=g_in_out)
+
+
+class ConvSubnetFn(torch.autograd.Function):
+    """Stand-alone subnet call (`net(x)`), used by the reverse pass and by tests."""
+
+    @staticmethod
+    def forward(ctx, x, net, mask, *params):
+        x = x if x.dim() == 4 else x
+        a, saved = conv_subnet_forward(net, x, net.training, mask)
+        ctx.net, ctx.saved = net, saved
+        ctx.save_for_backward(x)
+        return a
+
+    @staticmethod
+    def backward(ctx, g_a):
+        (x,) = ctx.saved_tensors
+        net = ctx.net
+        sink = GradSink(conv_subnet_params(net))
+        g_x = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+        conv_subnet_backward(net, ctx.saved, x, g_a, sink, 0, g_x, None)
+        return (g_x, None, None) + tuple(sink.returns())
+
+
+# ------------------------------------------------------------------------------------ AIO block
+
+class AIOBlockFn(torch.autograd.Function):
+    """AIO_Block.forward, rev=False (reference all_in_one_block.py:83-114)."""
+
+    @staticmethod
+    def forward(ctx, x, blk, mask, *params):
+        x = x.contiguous()
+        c1 = blk.split_len1
+        a, saved = conv_subnet_forward(blk.s, x[:, :c1], blk.training, mask)
+        out, jac = ops.aio_coupling_forward(x, a, blk.w, blk.act_norm, blk.act_offset, blk.clamp, 0.1)
+        ctx.blk, ctx.saved = blk, saved
+        ctx.save_for_backward(x, a, out)
+        return out, jac
+
+    @staticmethod
+    def backward(ctx, g_out, g_jac):
+        x, a, out = ctx.saved_tensors
+        blk = ctx.blk
+        c1 = blk.split_len1
+        sink = GradSink(conv_subnet_params(blk.s) + [blk.act_norm, blk.act_offset])
+        if g_out is None:
+            g_out = torch.zeros_like(out)
+        g_jac = None if g_jac is None else g_jac.contiguous()
+        g_x, g_a = ops.aio_coupling_backward(g_out, g_jac, x, a, out, blk.w, blk.act_norm, blk.act_offset, blk.clamp, 0.1,
+                                             sink[8], sink[9])
+        conv_subnet_backward(blk.s, ctx.saved, x[:, :c1], g_a, sink, 0, g_x[:, :c1], g_x[:, :c1])
+        return (g_x, None, None) + tuple(sink.returns())
+
+
+def aio_block_reverse(blk, y):
+    """AIO_Block.forward, rev=True (reference all_in_one_block.py:93-103).  No autograd."""
+    u = ops.aio_unpermute(y, blk.w_inv, blk.act_norm, blk.act_offset)
+    a, _ = conv_subnet_forward(blk.s, u[:, :blk.split_len1], blk.training)
+    jac = ops.aio_affine_inverse_(u, a, blk.act_norm, blk.clamp, 0.1)
+    return u, jac
+
+
+# ------------------------------------------------------------------------------------ downsampling block
+
+class DownBlockFn(torch.autograd.Function):
+    """DownsampleCouplingBlock.forward, rev=False (reference downsampling_coupling_block.py:68-94)."""
+
+    @staticmethod
+    def forward(ctx, x, blk, mask, *params):
+        x = x.contiguous()
+        B, C, H, W = x.shape
+        c1 = blk.split_len1
+        out = torch.empty((B, 4 * C, H // 2, W // 2), dtype=torch.float32, device=x.device)
+        jac = torch.empty(B, dtype=torch.float32, device=x.device)
+        a1, sv1 = conv_subnet_forward(blk.s_hi, x[:, :c1], blk.training)
+        ops.s2d_coupling_forward(x[:, c1:], a1, out[:, 4 * c1:], jac, False, blk.clamp, 0.2)
+        a2, sv2 = conv_subnet_forward(blk.s_lo, out[:, 4 * c1:], blk.training, mask)
+        ops.s2d_coupling_forward(x[:, :c1], a2, out[:, :4 * c1], jac, True, blk.clamp, 0.2)
+        ctx.blk, ctx.sv1, ctx.sv2 = blk, sv1, sv2
+        ctx.save_for_backward(x, a1, a2, out)
+        return out, jac
+
+    @staticmethod
+    def backward(ctx, g_out, g_jac):
+        x, a1, a2, out = ctx.saved_tensors
+        blk = ctx.blk
+        c1 = blk.split_len1
+        sink = GradSink(conv_subnet_params(blk.s_hi) + conv_subnet_params(blk.s_lo))
+        if g_out is None:
+            g_out = torch.zeros_like(out)
+        g_out = g_out.contiguous()
+        g_jac = None if g_jac is None else g_jac.contiguous()
+        g_x = torch.empty_like(x)
+        g_a2 = ops.s2d_coupling_backward(g_out[:, :4 * c1], g_jac, x[:, :c1], a2, g_x[:, :c1], blk.clamp, 0.2)
+        g_y2 = torch.empty(out[:, 4 * c1:].shape, dtype=torch.float32, device=x.device)
+        conv_subnet_backward(blk.s_lo, ctx.sv2, out[:, 4 * c1:], g_a2, sink, 8, g_y2, g_out[:, 4 * c1:])
+        g_a1 = ops.s2d_coupling_backward(g_y2, g_jac, x[:, c1:], a1, g_x[:, c1:], blk.clamp, 0.2)
+        conv_subnet_backward(blk.s_hi, ctx.sv1, x[:, :c1], g_a1, sink, 0, g_x[:, :c1], g_x[:, :c1])
+        return (g_x, None, None) + tuple(sink.returns())
+
+
+def down_block_reverse(blk, y):
+    """DownsampleCouplingBlock.forward, rev=True (reference downsampling_coupling_block.py:84-91)."""
+    y = y.contiguous()
+    B, C4, Ho, Wo = y.shape
+    C = C4 // 4
+    c1 = blk.split_len1
+    x = torch.empty((B, C, 2 * Ho, 2 * Wo), dtype=torch.float32, device=y.device)
+    jac = torch.empty(B, dtype=torch.float32, device=y.device)
+    a2, _ = conv_subnet_forward(blk.s_lo, y[:, 4 * c1:], blk.training)
+    ops.s2d_coupling_inverse(y[:, :4 * c1], a2, x[:, :c1], jac, False, blk.clamp, 0.2)
+    a1, _ = conv_subnet_forward(blk.s_hi, x[:, :c1], blk.training)
+    ops.s2d_coupling_inverse(y[:, 4 * c1:], a1, x[:, c1:], jac, True, blk.clamp, 0.2)
+    return x, jac
+
+
+# ------------------------------------------------------------------------------------ FC subnet / GLOW block
+
+def fc_subnet_params(net):
+    return [net.lin1.weight, net.lin1.bias, net.lin2.weight, net.lin2.bias]
+
+
+def fc_subnet_forward(net, x, training, mask=None):
+    """fc_constr (reference inn_architecture.py:112-120): Linear -> ReLU -> Dropout -> Linear."""
+    h = ops.linear_forward(x, net.lin1.weight, net.lin1.bias)
+    if training and mask is None and net.p_drop > 0.:
+        mask = dropout_mask(h.shape, net.p_drop, h)
+    if not training:
+        mask = None
+    r = ops.linear_forward(h, net.lin2.weight, net.lin2.bias, x_pre=1, x_mask=mask)
+    return r, (h, mask)
+
+
+def fc_subnet_backward(net, saved, x, g_r, sink, s0, g_in_out, accumulate):
+    h, mask = saved
+    dW1, db1, dW2, db2 = [sink[s0 + i] for i in range(4)]
+    g_r = g_r.contiguous()
+    ops.linear_wgrad(g_r, h, dW2, db2, x_pre=1, x_mask=mask)
+    g_h = torch.empty_like(h)
+    ops.linear_dgrad(g_r, net.lin2.weight, g_h, accumulate=False)
+    ops.linear_wgrad(g_h, x, dW1, db1, g_pre=2, h=h, g_mask=mask)
+    ops.linear_dgrad(g_h, net.lin1.weight, g_in_out, accumulate=accumulate, g_pre=2, h=h, g_mask=mask)
+
+
+class FCSubnetFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, net, mask, *params):
+        r, saved = fc_subnet_forward(net, x, net.training, mask)
+        ctx.net, ctx.saved = net, saved
+        ctx.save_for_backward(x)
+        return r
+
+    @staticmethod
+    def backward(ctx, g_r):
+        (x,) = ctx.saved_tensors
+        sink = GradSink(fc_subnet_params(ctx.net))
+        g_x = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+        fc_subnet_backward(ctx.net, ctx.saved, x, g_r, sink, 0, g_x, False)
+        return (g_x, None, None) + tuple(sink.returns())
+
+
+class GlowBlockFn(torch.autograd.Function):
+    """FrEIA v0.2 GLOWCouplingBlock forward (reference call site inn_architecture.py:161); s2 acts first."""
+
+    @staticmethod
+    def forward(ctx, x, blk, masks, *params):
+        x = x.contiguous()
+        B, D = x.shape
+        l1 = blk.split_len1
+        m1, m2 = masks if masks is not None else (None, None)
+        out = torch.empty_like(x)
+        jac = torch.empty(B, dtype=torch.float32, device=x.device)
+        r2, sv2 = fc_subnet_forward(blk.s2, x[:, l1:], blk.training, m2)
+        ops.glow_affine_forward(x[:, :l1], r2, out[:, :l1], jac, False, blk.clamp)
+        r1, sv1 = fc_subnet_forward(blk.s1, out[:, :l1], blk.training, m1)
+        ops.glow_affine_forward(x[:, l1:], r1, out[:, l1:], jac, True, blk.clamp)
+        ctx.blk, ctx.sv1, ctx.sv2 = blk, sv1, sv2
+        ctx.save_for_backward(x, r1, r2, out)
+        return out, jac
+
+    @staticmethod
+    def backward(ctx, g_out, g_jac):
+        x, r1, r2, out = ctx.saved_tensors
+        blk = ctx.blk
+        l1 = blk.split_len1
+        sink = GradSink(fc_subnet_params(blk.s1) + fc_subnet_params(blk.s2))
+        if g_out is None:
+            g_out = torch.zeros_like(out)
+        g_out = g_out.contiguous()
+        g_jac = None if g_jac is None else g_jac.contiguous()
+        g_x = torch.empty_like(x)
+        g_r1 = ops.glow_affine_backward(g_out[:, l1:], g_jac, x[:, l1:], r1, g_x[:, l1:], blk.clamp)
+        g_y1 = g_out[:, :l1].contiguous().clone() if g_out[:, :l1].is_contiguous() else g_out[:, :l1].contiguous()
+        fc_subnet_backward(blk.s1, ctx.sv1, out[:, :l1], g_r1, sink, 0, g_y1, True)
+        g_r2 = ops.glow_affine_backward(g_y1, g_jac, x[:, :l1], r2, g_x[:, :l1], blk.clamp)
+        fc_subnet_backward(blk.s2, ctx.sv2, x[:, l1:], g_r2, sink, 4, g_x[:, l1:], True)
+        return (g_x, None, None) + tuple(sink.returns())
+
+
+def glow_block_reverse(blk, y):
+    y = y.contiguous()
+    B, D = y.shape
+    l1 = blk.split_len1
+    x = torch.empty_like(y)
+    jac = torch.empty(B, dtype=torch.float32, device=y.device)
+    r1, _ = fc_subnet_forward(blk.s1, y[:, :l1], blk.training)
+    ops.glow_affine_inverse(y[:, l1:], r1, x[:, l1:], jac, False, blk.clamp)
+    r2, _ = fc_subnet_forward(blk.s2, x[:, l1:], blk.training)
+    ops.glow_affine_inverse(y[:, :l1], r2, x[:, :l1], jac, True, blk.clamp)
+    return x, jac
+
+
+# ------------------------------------------------------------------------------------ data movement nodes
+
+class DCTFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, scale):
+        ctx.weight, ctx.scale, ctx.shape = weight, scale, x.shape
+        return ops.dct2d_forward(x, weight, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        _, C, N, _ = ctx.shape
+        return ops.dct2d_inverse(g, ctx.weight, C, N, ctx.scale, True), None, None
+
+
+class HaarFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, fac):
+        ctx.fac = fac
+        return ops.haar_forward(x, fac)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.haar_inverse(g, ctx.fac), None
+
+
+class PermuteFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, perm, perm_inv):
+        ctx.perm_inv = perm_inv
+        return ops.permute_features(x, perm)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.permute_features(g, ctx.perm_inv), None, None
+
+
+# ------------------------------------------------------------------------------------ GMM / IB head
+
+class GMMHeadFn(torch.autograd.Function):
+    """GenerativeClassifier.forward after the INN (reference model.py:144-163)."""
+
+    @staticmethod
+    def forward(ctx, z, jac, mu, phi, y, loss_mean):
+        mu2 = mu.reshape(-1, mu.shape[-1])
+        o = ops.gmm_head_forward(z, jac, mu2, phi, y)
+        ctx.save_for_backward(z, mu2, phi, o['logits'], o['lse'])
+        ctx.y, ctx.loss_mean, ctx.mu_shape, ctx.mu_param, ctx.phi_param = y, loss_mean, mu.shape, mu, phi
+        has_y = y is not None
+        if loss_mean:
+            m = o['means']
+            outs = (m[0], m[1], m[2] if has_y else None, m[3] if has_y else None, m[4] if has_y else None)
+        else:
+            outs = (o['L_x'], o['logits'], o.get('L_cNLL'), o.get('L_y'), m_acc(o) if has_y else None)
+        ctx.mark_non_differentiable(*[t for t in outs[4:] if t is not None])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_lx, g_logits, g_lc, g_ly, g_acc):
+        z, mu2, phi, logits, lse = ctx.saved_tensors
+        B, C = logits.shape
+        grads = {'L_x': g_lx, 'logits': g_logits, 'L_cNLL': g_lc, 'L_y': g_ly}
+        sv, sl = (1. / B, 1. / (B * C)) if ctx.loss_mean else (1., 1.)
+        tm = getattr(ctx.mu_param, '_ibinn_grad', None)
+        tp = getattr(ctx.phi_param, '_ibinn_grad', None)
+        g_z, g_jac, g_mu, g_phi = ops.gmm_head_backward(z, mu2, phi, ctx.y, logits, lse, grads, sv, sl,
+                                                        None if tm is None else tm.view(C, -1), tp)
+        return g_z, g_jac, (None if tm is not None else g_mu.view(ctx.mu_shape)), (None if tp is not None else g_phi), None, None
+
+
+def m_acc(o):
+    return o['means'][4]

@@ -1,0 +1,373 @@
+"""Thin Python wrappers (tensor -> pointer/shape marshalling) over the C ABI.  No autograd here;
+`functions.py` builds the torch.autograd.Function layer on top.  Everything raises if the CUDA
+library is missing or a tensor is not on the B200 (see _lib.py)."""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import BnRef, ConvArgs, WgradArgs, check, ptr, stream
+
+PRE_NONE, PRE_RELU, PRE_BN_RELU, PRE_BNBWD = 0, 1, 2, 3
+EPI_STORE, EPI_BNSTATS, EPI_MASKSTATS, EPI_RELUMASK = 0, 1, 2, 3
+
+_COUNTERS = {}
+_N_COUNTERS = 4096
+
+
+def counter_ptr(ref):
+    """A zero-initialised uint32 slot on ref's device.  Kernels return their slot to zero, so the
+    slots are handed out round-robin (kernels on one stream never overlap on a slot)."""
+    key = (ref.device.type, ref.device.index)
+    ent = _COUNTERS.get(key)
+    if ent is None:
+        ent = [torch.zeros(_N_COUNTERS, dtype=torch.int32, device=ref.device), 0]
+        _COUNTERS[key] = ent
+    ent[1] = (ent[1] + 1) % _N_COUNTERS
+    return ent[0].data_ptr() + 4 * ent[1]
+
+
+def _nchw(t):
+    """(pointer, batch stride) of a (B,C,H,W) tensor that is contiguous within each image."""
+    if t is None:
+        return None, 0
+    B, C, H, W = t.shape
+    st = t.stride()
+    if not (st[3] == 1 and (H == 1 or st[2] == W) and (C == 1 or st[1] == H * W)):
+        raise ValueError('ibinn_b200: tensor must be NCHW-contiguous within an image, got strides %s for shape %s' % (st, tuple(t.shape)))
+    return ptr(t, strided=True), (st[0] if B > 1 else C * H * W)
+
+
+def _rows(t):
+    """(pointer, row stride) of a (B,L) tensor with unit inner stride."""
+    B, L_ = t.shape
+    if t.stride(1) != 1 and L_ > 1:
+        raise ValueError('ibinn_b200: inner stride must be 1')
+    return ptr(t, strided=True), (t.stride(0) if B > 1 else L_)
+
+
+def bn_ref(mean, scale, gamma, beta, eps, scale_is_variance):
+    return BnRef(ptr(mean), ptr(scale), ptr(gamma), ptr(beta), float(eps), int(bool(scale_is_variance)))
+
+
+class BN:
+    """What a kernel needs to know about one BatchNorm2d layer at one call."""
+    __slots__ = ('mean', 'scale', 'gamma', 'beta', 'eps', 'is_var')
+
+    def __init__(self, mean, scale, gamma, beta, eps, is_var):
+        self.mean, self.scale, self.gamma, self.beta, self.eps, self.is_var = mean, scale, gamma, beta, eps, is_var
+
+    def ref(self):
+        return bn_ref(self.mean, self.scale, self.gamma, self.beta, self.eps, self.is_var)
+
+
+def conv_forward(x, w, ksize, stride=1, *, cout=None, pre=PRE_NONE, pre_bn=None, pre_mask=None, x2=None, pre_sums=None,
+                 epi=EPI_STORE, bias=None, addend=None, out=None, w_transposed=False, upsample_to=None,
+                 stats=None, mask=None):
+    """One launch of the subnet convolution kernel (see include/ibinn_b200.h, ibinn_conv_args).
+
+    stats (EPI_BNSTATS): dict(save_mean, save_invstd, running_mean, running_var, nbt, momentum, eps)
+    mask  (EPI_MASKSTATS / EPI_RELUMASK): dict(h, bn=BN|None, drop, sums_out, dgamma, dbeta)
+    """
+    B, Cin, Hs, Ws = x.shape
+    if cout is None:
+        cout = w.shape[1] if w_transposed else w.shape[0]
+    Hin, Win = (Hs, Ws) if upsample_to is None else upsample_to
+    pad = ksize // 2
+    Hout = (Hin + 2 * pad - ksize) // stride + 1
+    Wout = (Win + 2 * pad - ksize) // stride + 1
+    if out is None:
+        out = torch.empty((B, cout, Hout, Wout), dtype=torch.float32, device=x.device)
+    a = ConvArgs()
+    a.x, a.x_bs = _nchw(x)
+    a.x2, a.x2_bs = _nchw(x2)
+    a.w, a.bias = ptr(w), ptr(bias)
+    a.addend, a.addend_bs = _nchw(addend)
+    a.y, a.y_bs = _nchw(out)
+    a.B, a.Cin, a.Cout, a.Hs, a.Ws, a.Hout, a.Wout = B, Cin, cout, Hs, Ws, Hout, Wout
+    a.ksize, a.stride, a.upsample2, a.Hin, a.Win = ksize, stride, int(upsample_to is not None), Hin, Win
+    a.w_transposed, a.pre, a.epi = int(w_transposed), pre, epi
+    if pre_bn is not None:
+        a.pre_bn = pre_bn.ref()
+    a.pre_mask, a.pre_sums = ptr(pre_mask), ptr(pre_sums)
+    a.pre_inv_count = 1.0 / float(B * Hs * Ws)
+    if stats is not None:
+        a.save_mean, a.save_invstd = ptr(stats['save_mean']), ptr(stats['save_invstd'])
+        a.running_mean, a.running_var = ptr(stats.get('running_mean')), ptr(stats.get('running_var'))
+        a.num_batches_tracked = ptr(stats.get('nbt'), torch.int64)
+        mom = stats.get('momentum')
+        a.momentum = -1.0 if mom is None else float(mom)
+        a.bn_eps = float(stats['eps'])
+    if mask is not None:
+        a.m_h, a.m_bs = _nchw(mask['h'])
+        if mask.get('bn') is not None:
+            a.m_bn = mask['bn'].ref()
+        a.m_drop, a.sums_out = ptr(mask.get('drop')), ptr(mask.get('sums_out'))
+        a.m_dgamma, a.m_dbeta = ptr(mask.get('dgamma')), ptr(mask.get('dbeta'))
+    L = _lib.lib()
+    keep = None
+    if epi in (EPI_BNSTATS, EPI_MASKSTATS):
+        n = L.ibinn_conv_partials_floats(ctypes.byref(a))
+        if n < 0:
+            check(int(n), 'conv_partials_floats')
+        keep = torch.empty(max(int(n), 1), dtype=torch.float32, device=x.device)
+        a.partials = ptr(keep)
+        a.counter = counter_ptr(x)
+    check(L.ibinn_conv_forward(ctypes.byref(a), stream(x)), 'conv_forward')
+    return out
+
+
+def conv_wgrad(g, x, dw, ksize, stride=1, *, g_pre=PRE_NONE, gh=None, g_bn=None, g_sums=None, x_pre=PRE_NONE, x_bn=None,
+               x_mask=None, dbias=None):
+    B, Cout, Hout, Wout = g.shape
+    _, Cin, Hin, Win = x.shape
+    a = WgradArgs()
+    a.g, a.g_bs = _nchw(g)
+    a.gh, a.gh_bs = _nchw(gh)
+    a.g_pre = g_pre
+    if g_bn is not None:
+        a.g_bn = g_bn.ref()
+    a.g_sums = ptr(g_sums)
+    a.g_inv_count = 1.0 / float(B * Hout * Wout)
+    a.x, a.x_bs = _nchw(x)
+    a.x_pre = x_pre
+    if x_bn is not None:
+        a.x_bn = x_bn.ref()
+    a.x_mask = ptr(x_mask)
+    a.dw, a.dbias = ptr(dw), ptr(dbias)
+    a.B, a.Cin, a.Cout, a.Hin, a.Win, a.Hout, a.Wout, a.ksize, a.stride = B, Cin, Cout, Hin, Win, Hout, Wout, ksize, stride
+    check(_lib.lib().ibinn_conv_wgrad(ctypes.byref(a), stream(g)), 'conv_wgrad')
+
+
+# ------------------------------------------------------------------------------------ couplings
+
+def aio_coupling_forward(x, a, w, act_norm, act_offset, clamp, alpha=0.1):
+    B, C, H, W = x.shape
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    jac = torch.empty(B, dtype=torch.float32, device=x.device)
+    check(_lib.lib().ibinn_aio_coupling_forward(ptr(x), ptr(a), ptr(w), ptr(act_norm), ptr(act_offset), ptr(out), ptr(jac),
+                                                B, C, H, W, clamp, alpha, stream(x)), 'aio_coupling_forward')
+    return out, jac
+
+
+def aio_coupling_backward(g_out, g_jac, x, a, out, w, act_norm, act_offset, clamp, alpha, g_act_norm, g_act_offset):
+    """returns g_x, g_a; accumulates into g_act_norm / g_act_offset (C)."""
+    B, C, H, W = x.shape
+    g_out = g_out.contiguous()
+    g_x = torch.empty_like(x)
+    g_a = torch.empty_like(a)
+    part = torch.empty(B * 2 * C, dtype=torch.float32, device=x.device)
+    check(_lib.lib().ibinn_aio_coupling_backward(ptr(g_out), ptr(g_jac), ptr(x), ptr(a), ptr(out), ptr(w), ptr(act_norm),
+                                                 ptr(act_offset), ptr(g_x), ptr(g_a), ptr(g_act_norm), ptr(g_act_offset),
+                                                 ptr(part), counter_ptr(x), B, C, H, W, clamp, alpha, stream(x)),
+          'aio_coupling_backward')
+    return g_x, g_a
+
+
+def aio_unpermute(y, w_inv, act_norm, act_offset):
+    B, C, H, W = y.shape
+    y = y.contiguous()
+    u = torch.empty_like(y)
+    check(_lib.lib().ibinn_aio_unpermute(ptr(y), ptr(w_inv), ptr(act_norm), ptr(act_offset), ptr(u), B, C, H, W, stream(y)),
+          'aio_unpermute')
+    return u
+
+
+def aio_affine_inverse_(u, a, act_norm, clamp, alpha=0.1):
+    B, C, H, W = u.shape
+    jac = torch.empty(B, dtype=torch.float32, device=u.device)
+    check(_lib.lib().ibinn_aio_affine_inverse(ptr(u), ptr(a), ptr(act_norm), ptr(jac), B, C, H, W, clamp, alpha, stream(u)),
+          'aio_affine_inverse')
+    return jac
+
+
+def s2d_coupling_forward(x, a, out, jac, accumulate, clamp, alpha=0.2):
+    B, cp, H, W = x.shape
+    xp, xbs = _nchw(x)
+    op, obs = _nchw(out)
+    check(_lib.lib().ibinn_s2d_coupling_forward(xp, xbs, ptr(a), op, obs, ptr(jac), int(accumulate), B, cp, H, W, clamp, alpha,
+                                                stream(x)), 's2d_coupling_forward')
+
+
+def s2d_coupling_inverse(y, a, x, jac, accumulate, clamp, alpha=0.2):
+    B, cp, H, W = x.shape
+    xp, xbs = _nchw(x)
+    yp, ybs = _nchw(y)
+    check(_lib.lib().ibinn_s2d_coupling_inverse(yp, ybs, ptr(a), xp, xbs, ptr(jac), int(accumulate), B, cp, H, W, clamp, alpha,
+                                                stream(x)), 's2d_coupling_inverse')
+
+
+def s2d_coupling_backward(g_out, g_jac, x, a, g_x, clamp, alpha=0.2):
+    B, cp, H, W = x.shape
+    gp, gbs = _nchw(g_out)
+    xp, xbs = _nchw(x)
+    gxp, gxbs = _nchw(g_x)
+    g_a = torch.empty_like(a)
+    check(_lib.lib().ibinn_s2d_coupling_backward(gp, gbs, ptr(g_jac), xp, xbs, ptr(a), gxp, gxbs, ptr(g_a), B, cp, H, W, clamp,
+                                                 alpha, stream(x)), 's2d_coupling_backward')
+    return g_a
+
+
+def glow_affine_forward(x, r, y, jac, accumulate, clamp):
+    B, L_ = x.shape
+    xp, xrs = _rows(x)
+    yp, yrs = _rows(y)
+    check(_lib.lib().ibinn_glow_affine_forward(xp, xrs, ptr(r), yp, yrs, ptr(jac), int(accumulate), B, L_, clamp, stream(x)),
+          'glow_affine_forward')
+
+
+def glow_affine_inverse(y, r, x, jac, accumulate, clamp):
+    B, L_ = y.shape
+    xp, xrs = _rows(x)
+    yp, yrs = _rows(y)
+    check(_lib.lib().ibinn_glow_affine_inverse(yp, yrs, ptr(r), xp, xrs, ptr(jac), int(accumulate), B, L_, clamp, stream(y)),
+          'glow_affine_inverse')
+
+
+def glow_affine_backward(g_y, g_jac, x, r, g_x, clamp):
+    B, L_ = x.shape
+    gp, grs = _rows(g_y)
+    xp, xrs = _rows(x)
+    gxp, gxrs = _rows(g_x)
+    g_r = torch.empty_like(r)
+    check(_lib.lib().ibinn_glow_affine_backward(gp, grs, ptr(g_jac), xp, xrs, ptr(r), gxp, gxrs, ptr(g_r), B, L_, clamp,
+                                                stream(x)), 'glow_affine_backward')
+    return g_r
+
+
+# ------------------------------------------------------------------------------------ data movement
+
+def dct2d_forward(x, M, scale):
+    B, C, N, _ = x.shape
+    x = x.contiguous()
+    out = torch.empty((B, C * N * N), dtype=torch.float32, device=x.device)
+    check(_lib.lib().ibinn_dct2d_forward(ptr(x), ptr(M), ptr(out), B, C, N, scale, stream(x)), 'dct2d_forward')
+    return out
+
+
+def dct2d_inverse(t, M, C, N, scale, transpose_M):
+    B = t.shape[0]
+    t = t.contiguous()
+    x = torch.empty((B, C, N, N), dtype=torch.float32, device=t.device)
+    check(_lib.lib().ibinn_dct2d_inverse(ptr(t), ptr(M), ptr(x), B, C, N, scale, int(transpose_M), stream(t)), 'dct2d_inverse')
+    return x
+
+
+def haar_forward(x, fac):
+    B, C, H, W = x.shape
+    x = x.contiguous()
+    y = torch.empty((B, 4 * C, H // 2, W // 2), dtype=torch.float32, device=x.device)
+    check(_lib.lib().ibinn_haar_forward(ptr(x), ptr(y), B, C, H, W, fac, stream(x)), 'haar_forward')
+    return y
+
+
+def haar_inverse(y, fac):
+    B, C4, Ho, Wo = y.shape
+    y = y.contiguous()
+    x = torch.empty((B, C4 // 4, 2 * Ho, 2 * Wo), dtype=torch.float32, device=y.device)
+    check(_lib.lib().ibinn_haar_inverse(ptr(y), ptr(x), B, C4 // 4, 2 * Ho, 2 * Wo, fac, stream(y)), 'haar_inverse')
+    return x
+
+
+def permute_features(x, index):
+    B, D = x.shape
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    check(_lib.lib().ibinn_permute_features(ptr(x), ptr(index, torch.int32), ptr(out), B, D, stream(x)), 'permute_features')
+    return out
+
+
+# ------------------------------------------------------------------------------------ linear
+
+def linear_forward(x, w, bias, *, x_pre=0, x_mask=None):
+    B, K = x.shape
+    N = w.shape[0]
+    xp, xrs = _rows(x)
+    y = torch.empty((B, N), dtype=torch.float32, device=x.device)
+    check(_lib.lib().ibinn_linear_forward(xp, xrs, ptr(x_mask), x_pre, ptr(w), ptr(bias), ptr(y), B, K, N, stream(x)),
+          'linear_forward')
+    return y
+
+
+def linear_dgrad(g, w, dx, *, accumulate, g_pre=0, h=None, g_mask=None):
+    B, N = g.shape
+    K = w.shape[1]
+    dp, drs = _rows(dx)
+    check(_lib.lib().ibinn_linear_dgrad(ptr(g), ptr(h), ptr(g_mask), g_pre, ptr(w), dp, drs, int(accumulate), B, K, N, stream(g)),
+          'linear_dgrad')
+
+
+def linear_wgrad(g, x, dw, db, *, g_pre=0, h=None, g_mask=None, x_pre=0, x_mask=None):
+    B, N = g.shape
+    K = x.shape[1]
+    xp, xrs = _rows(x)
+    check(_lib.lib().ibinn_linear_wgrad(ptr(g), ptr(h), ptr(g_mask), g_pre, xp, xrs, ptr(x_mask), x_pre, ptr(dw), ptr(db), B, K, N,
+                                        stream(g)), 'linear_wgrad')
+
+
+# ------------------------------------------------------------------------------------ head / optimiser
+
+def gmm_head_forward(z, jac, mu, phi, y):
+    B, D = z.shape
+    C = phi.shape[0]
+    dev = z.device
+    z = z.contiguous()
+    f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    out = dict(L_x=f(B), logits=f(B, C), lse=f(B), means=f(5))
+    if y is not None:
+        y = y.contiguous()
+        out.update(L_cNLL=f(B), L_y=f(B), correct=f(B))
+    part = f(B * 5)
+    check(_lib.lib().ibinn_gmm_head_forward(ptr(z), ptr(jac.contiguous()), ptr(mu), ptr(phi), ptr(y), ptr(out['L_x']), ptr(out['logits']),
+                                            ptr(out.get('L_cNLL')), ptr(out.get('L_y')), ptr(out.get('correct')), ptr(out['lse']),
+                                            ptr(out['means']), ptr(part), counter_ptr(z), B, C, D, stream(z)), 'gmm_head_forward')
+    return out
+
+
+def gmm_head_backward(z, mu, phi, y, logits, lse, grads, scale_vec, scale_logits, g_mu=None, g_phi=None):
+    """grads: dict with optional 'L_x','L_cNLL','L_y','logits' upstream gradients (per-sample, or 0-dim when the
+    means were returned).  Returns g_z, g_jac, g_mu, g_phi (the latter two accumulated in place if given)."""
+    B, D = z.shape
+    C = phi.shape[0]
+    dev = z.device
+
+    def gs(name):
+        g = grads.get(name)
+        if g is None:
+            return None, 0
+        g = g.contiguous()
+        return ptr(g), (0 if g.numel() == 1 else 1)
+
+    acc_mu, acc_phi = g_mu is not None, g_phi is not None
+    if g_mu is None:
+        g_mu = torch.empty((C, D), dtype=torch.float32, device=dev)
+    if g_phi is None:
+        g_phi = torch.empty(C, dtype=torch.float32, device=dev)
+    G = torch.empty((B, C), dtype=torch.float32, device=dev)
+    Glw = torch.empty((B, C), dtype=torch.float32, device=dev)
+    g_z = torch.empty((B, D), dtype=torch.float32, device=dev)
+    g_jac = torch.empty(B, dtype=torch.float32, device=dev)
+    (p1, s1), (p2, s2), (p3, s3), (p4, s4) = gs('L_x'), gs('L_cNLL'), gs('L_y'), gs('logits')
+    check(_lib.lib().ibinn_gmm_head_backward(ptr(z), ptr(mu), ptr(phi), ptr(y), ptr(logits), ptr(lse), p1, s1, p2, s2, p3, s3, p4, s4,
+                                             scale_vec, scale_logits, ptr(G), ptr(Glw), ptr(g_z), ptr(g_jac), ptr(g_mu), int(acc_mu),
+                                             ptr(g_phi), int(acc_phi), B, C, D, stream(z)), 'gmm_head_backward')
+    return g_z, g_jac, g_mu, g_phi
+
+
+def grad_norm_clip(flat_grad, max_norm, extra_sumsq=None):
+    """-> tensor [norm, clip_coef] on the device (no host sync)."""
+    L = _lib.lib()
+    dev = flat_grad.device
+    part = torch.empty(int(L.ibinn_grad_norm_partials_doubles()), dtype=torch.float64, device=dev)
+    out = torch.empty(2, dtype=torch.float32, device=dev)
+    n_extra = 0 if extra_sumsq is None else extra_sumsq.numel()
+    check(L.ibinn_grad_norm_clip(ptr(flat_grad), flat_grad.numel(), ptr(extra_sumsq), n_extra, float(max_norm),
+                                 ptr(part, torch.float64), counter_ptr(flat_grad), ptr(out), stream(flat_grad)), 'grad_norm_clip')
+    return out
+
+
+def sgd_step_(param, grad, buf, hyper, clip_coef=None, grad_scale=1.0):
+    cp = None if clip_coef is None else ptr(clip_coef)
+    check(_lib.lib().ibinn_sgd_step(ptr(param), ptr(grad), ptr(buf), param.numel(), ptr(hyper), cp, float(grad_scale),
+                                    stream(param)), 'sgd_step')

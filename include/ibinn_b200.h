@@ -1,0 +1,223 @@
+/* ibinn_b200 -- C ABI of the B200-native IB-INN hot path (sm_100a only).
+ *
+ * The reference (vislearn/IB-INN) is pure Python/PyTorch and has no FFI of its own; each entry
+ * point below replaces the stock ATen/cuDNN/cuBLAS calls that the cited reference lines issue.
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer on the current device, fp32 unless noted, contiguous NCHW
+ *     within an image; `*_bs` is the batch stride in floats (lets a kernel address a channel slice
+ *     of a wider tensor without a copy);
+ *   - the caller owns all buffers, including workspaces; kernels never allocate, free or sync;
+ *   - all work is enqueued on `stream` (a cudaStream_t); safe under CUDA-graph capture;
+ *   - return 0 on success, a negative IBINN_E* for a rejected call (checked before launch),
+ *     a positive value = cudaError_t of the launch.  Nothing throws or exits;
+ *   - `counter` arguments point at one zero-initialised uint32 that the kernel returns to zero;
+ *   - there is no CPU fallback: on a device that is not sm_100 every call returns IBINN_EARCH.
+ */
+#ifndef IBINN_B200_H
+#define IBINN_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IBINN_OK 0
+#define IBINN_EINVAL (-1)   /* bad shape / unsupported size */
+#define IBINN_EALIGN (-2)   /* pointer or stride not aligned as required */
+#define IBINN_EARCH (-3)    /* device is not sm_100 (B200) */
+#define IBINN_ENULL (-4)    /* required pointer is NULL */
+
+typedef void* ibinn_stream_t; /* cudaStream_t */
+
+int ibinn_abi_version(void);
+/* 0 if the current device is sm_100, else IBINN_EARCH (or the cudaError_t). */
+int ibinn_check_device(void);
+
+/* ---------------------------------------------------------------- subnet convolutions
+ * Replaces nn.Conv2d / nn.BatchNorm2d / nn.ReLU / nn.Dropout2d of basic_residual_block and
+ * strided_residual_block (reference inn_architecture.py:68-110) and their autograd backward.
+ * One kernel = [pre-op on the input while it is staged] -> KSxKS convolution (pad KS/2,
+ * stride 1|2, no groups) -> [epilogue].  dgrad is the same kernel with `w_transposed`.
+ */
+enum {
+    IBINN_PRE_NONE = 0,
+    IBINN_PRE_RELU = 1,     /* relu(x)                                     inn_architecture.py:72 */
+    IBINN_PRE_BN_RELU = 2,  /* relu(bn(x)) [* dropout mask (B,Cin)]        inn_architecture.py:78-84 */
+    IBINN_PRE_BNBWD = 3     /* batch-norm backward applied to (x=grad, x2=raw fwd activation) */
+};
+enum {
+    IBINN_EPI_STORE = 0,     /* y = conv (+bias) (+addend) */
+    IBINN_EPI_BNSTATS = 1,   /* y = conv; batch mean / inv-std of y -> save_*, running stats updated */
+    IBINN_EPI_MASKSTATS = 2, /* y = conv * [bn(m_h) > 0] (* drop mask); sums_out = (sum y, sum y*xhat) */
+    IBINN_EPI_RELUMASK = 3   /* y = conv * [m_h > 0] (+addend) */
+};
+
+typedef struct ibinn_bn_ref {  /* a batch-norm layer as seen by a kernel */
+    const float* mean;         /* (C) batch or running mean */
+    const float* scale;        /* (C) inv-std, or the variance if var_is_variance */
+    const float* gamma;        /* (C) */
+    const float* beta;         /* (C) */
+    float eps;
+    int32_t scale_is_variance;
+} ibinn_bn_ref;
+
+typedef struct ibinn_conv_args {
+    const float* x;  int64_t x_bs;      /* input  (B, Cin, Hs, Ws)                     */
+    const float* x2; int64_t x2_bs;     /* PRE_BNBWD: raw forward activation, same geometry */
+    const float* w;                     /* (Cout,Cin,KS,KS); w_transposed: (Cin,Cout,KS,KS) read flipped */
+    const float* bias;                  /* (Cout) or NULL */
+    const float* addend; int64_t addend_bs; /* (B,Cout,Hout,Wout) or NULL; may alias y */
+    float* y; int64_t y_bs;             /* output (B, Cout, Hout, Wout) */
+    int32_t B, Cin, Cout, Hs, Ws, Hout, Wout;
+    int32_t ksize, stride;              /* ksize 1|3, stride 1|2 */
+    int32_t upsample2;                  /* input is zero-inserted to (2Hs [-1], 2Ws [-1]) first: dgrad of a stride-2 conv */
+    int32_t Hin, Win;                   /* logical input size (== Hs,Ws unless upsample2) */
+    int32_t w_transposed;
+    int32_t pre, epi;
+    ibinn_bn_ref pre_bn;                /* PRE_BN_RELU, PRE_BNBWD */
+    const float* pre_mask;              /* PRE_BN_RELU: (B,Cin) dropout mask (0 or 1/(1-p)) or NULL */
+    const float* pre_sums;              /* PRE_BNBWD: (2,Cin) = sum g, sum g*xhat */
+    float pre_inv_count;                /* PRE_BNBWD: 1 / (B*Hs*Ws) */
+    /* EPI_BNSTATS */
+    float* save_mean; float* save_invstd;        /* (Cout) outputs */
+    float* running_mean; float* running_var;     /* (Cout) in/out or NULL */
+    int64_t* num_batches_tracked;                /* in/out or NULL */
+    float momentum;                              /* < 0: cumulative average 1/num_batches_tracked */
+    float bn_eps;
+    /* EPI_MASKSTATS / EPI_RELUMASK */
+    const float* m_h; int64_t m_bs;              /* activation that decides the mask (B,Cout,Hout,Wout) */
+    ibinn_bn_ref m_bn;                           /* MASKSTATS: its batch norm */
+    const float* m_drop;                         /* (B,Cout) dropout mask or NULL */
+    float* sums_out;                             /* (2,Cout) */
+    float* m_dgamma; float* m_dbeta;             /* (Cout) accumulated: += sums_out[1], += sums_out[0]; or NULL */
+    /* workspaces */
+    float* partials;                             /* ibinn_conv_partials_floats() floats (BNSTATS, MASKSTATS) */
+    uint32_t* counter;
+} ibinn_conv_args;
+
+size_t ibinn_sizeof_conv_args(void);
+/* number of floats `partials` must hold for this call (0 if the epilogue needs none) */
+int64_t ibinn_conv_partials_floats(const ibinn_conv_args* a);
+int ibinn_conv_forward(const ibinn_conv_args* a, ibinn_stream_t stream);
+
+typedef struct ibinn_wgrad_args {
+    const float* g;  int64_t g_bs;      /* grad w.r.t. conv output (B,Cout,Hout,Wout)        */
+    const float* gh; int64_t gh_bs;     /* g_pre == PRE_BNBWD: raw conv output of the forward */
+    int32_t g_pre;                      /* IBINN_PRE_NONE | IBINN_PRE_BNBWD */
+    ibinn_bn_ref g_bn; const float* g_sums; float g_inv_count;
+    const float* x;  int64_t x_bs;      /* conv input before its pre-op (B,Cin,Hin,Win) */
+    int32_t x_pre;                      /* NONE | RELU | BN_RELU */
+    ibinn_bn_ref x_bn; const float* x_mask;
+    float* dw;                          /* (Cout,Cin,KS,KS), ACCUMULATED into (atomics) */
+    float* dbias;                       /* (Cout) accumulated, or NULL */
+    int32_t B, Cin, Cout, Hin, Win, Hout, Wout, ksize, stride;
+} ibinn_wgrad_args;
+
+size_t ibinn_sizeof_wgrad_args(void);
+int ibinn_conv_wgrad(const ibinn_wgrad_args* a, ibinn_stream_t stream);
+
+/* ---------------------------------------------------------------- AIO_Block coupling
+ * Replaces reference all_in_one_block.py:61-111 (`log_e`, `affine`, `permute`, `forward`):
+ *   x1|x2 = split(x, [C - C/2, C/2]);  sig = clamp*tanh(alpha*a[:, :C/2]);  y2 = x2*exp(sig) + a[:, C/2:]
+ *   out = (w . [x1|y2]) * exp(act_norm) + act_offset ;  jac[b] = sum(sig) + H*W*sum(act_norm)   (:113-114)
+ * all tensors contiguous; x,out (B,C,H,W); a (B,2*(C/2),H,W); w (C,C) as [out][in]; one CTA per sample. */
+int ibinn_aio_coupling_forward(const float* x, const float* a, const float* w, const float* act_norm,
+                               const float* act_offset, float* out, float* jac, int B, int C, int H, int W,
+                               float clamp, float alpha, ibinn_stream_t stream);
+/* hand-derived backward.  `out` is the forward output.  g_act_norm /
+ * g_act_offset (C) are accumulated into; partials: B*2*C floats. */
+int ibinn_aio_coupling_backward(const float* g_out, const float* g_jac, const float* x, const float* a,
+                                const float* out, const float* w, const float* act_norm, const float* act_offset,
+                                float* g_x, float* g_a, float* g_act_norm, float* g_act_offset, float* partials,
+                                uint32_t* counter, int B, int C, int H, int W, float clamp, float alpha,
+                                ibinn_stream_t stream);
+/* inverse direction (all_in_one_block.py:69,93-103): u = w_inv . ((y - act_offset) * exp(-act_norm)),
+ * then, with a = subnet(u[:, :C-C/2]):  u[:, C-C/2:] <- (u2 - t) * exp(-sig) in place; jac = -(...) */
+int ibinn_aio_unpermute(const float* y, const float* w_inv, const float* act_norm, const float* act_offset, float* u,
+                        int B, int C, int H, int W, ibinn_stream_t stream);
+int ibinn_aio_affine_inverse(float* u, const float* a, const float* act_norm, float* jac, int B, int C, int H, int W,
+                             float clamp, float alpha, ibinn_stream_t stream);
+
+/* ---------------------------------------------------------------- DownsampleCouplingBlock halves
+ * Replaces reference downsampling_coupling_block.py:49-66 (`down`/`up` grouped stride-2 convs with one-hot
+ * kernels + `affine`):  out[b,4c+2dy+dx,h,w] = x[b,c,2h+dy,2w+dx] * exp(clamp*tanh(alpha*a[b,4c+2dy+dx,h,w]))
+ *                                              + a[b,4cp+4c+2dy+dx,h,w]
+ * x: (B,cp,H,W) slice with batch stride x_bs; a: (B,8cp,H/2,W/2) contiguous; out: (B,4cp,H/2,W/2) slice, out_bs.
+ * jac[b] (+)= sum of the log-scales. */
+int ibinn_s2d_coupling_forward(const float* x, int64_t x_bs, const float* a, float* out, int64_t out_bs, float* jac,
+                               int jac_accumulate, int B, int cp, int H, int W, float clamp, float alpha,
+                               ibinn_stream_t stream);
+int ibinn_s2d_coupling_inverse(const float* y, int64_t y_bs, const float* a, float* x, int64_t x_bs, float* jac,
+                               int jac_accumulate, int B, int cp, int H, int W, float clamp, float alpha,
+                               ibinn_stream_t stream);
+int ibinn_s2d_coupling_backward(const float* g_out, int64_t g_bs, const float* g_jac, const float* x, int64_t x_bs,
+                                const float* a, float* g_x, int64_t gx_bs, float* g_a, int B, int cp, int H, int W,
+                                float clamp, float alpha, ibinn_stream_t stream);
+
+/* ---------------------------------------------------------------- GLOWCouplingBlock halves (FrEIA v0.2; reference
+ * call site inn_architecture.py:161):  y = exp(le(r[:, :L])) * x + r[:, L:],  le(s) = clamp*0.636*atan(s/clamp)
+ * x,y: (B,L) with row strides; r: (B,2L) contiguous; jac[b] (+)= sum le. */
+int ibinn_glow_affine_forward(const float* x, int64_t x_rs, const float* r, float* y, int64_t y_rs, float* jac,
+                              int jac_accumulate, int B, int L, float clamp, ibinn_stream_t stream);
+int ibinn_glow_affine_inverse(const float* y, int64_t y_rs, const float* r, float* x, int64_t x_rs, float* jac,
+                              int jac_accumulate, int B, int L, float clamp, ibinn_stream_t stream);
+int ibinn_glow_affine_backward(const float* g_y, int64_t gy_rs, const float* g_jac, const float* x, int64_t x_rs,
+                               const float* r, float* g_x, int64_t gx_rs, float* g_r, int B, int L, float clamp,
+                               ibinn_stream_t stream);
+
+/* ---------------------------------------------------------------- data-movement nodes
+ * DCTPooling2d (reference dct_transform.py:81-101): out[b,(kw*N+kh)*C+c] = scale * sum M[kh][h] M[kw][w] x[b,c,h,w].
+ * inverse / backward: x[b,c,h,w] = scale * sum A(h,kh) A(w,kw) t[b,(kw*N+kh)*C+c], A = M (rev, M = inv_weight)
+ * or M^T (autograd backward, M = weight). */
+int ibinn_dct2d_forward(const float* x, const float* M, float* out, int B, int C, int N, float scale, ibinn_stream_t stream);
+int ibinn_dct2d_inverse(const float* t, const float* M, float* x, int B, int C, int N, float scale, int transpose_M,
+                        ibinn_stream_t stream);
+/* HaarDownsampling (FrEIA v0.2; reference call site inn_architecture.py:127): (B,C,H,W) <-> (B,4C,H/2,W/2) */
+int ibinn_haar_forward(const float* x, float* y, int B, int C, int H, int W, float fac, ibinn_stream_t stream);
+int ibinn_haar_inverse(const float* y, float* x, int B, int C, int H, int W, float fac, ibinn_stream_t stream);
+/* PermuteRandom (FrEIA v0.2; reference call site inn_architecture.py:160): out[b][i] = x[b][index[i]] */
+int ibinn_permute_features(const float* x, const int32_t* index, float* out, int B, int D, ibinn_stream_t stream);
+
+/* ---------------------------------------------------------------- fully connected subnets (fc_constr,
+ * reference inn_architecture.py:112-120) and their autograd backward */
+int ibinn_linear_forward(const float* x, int64_t x_rs, const float* x_mask, int x_pre, const float* w, const float* bias,
+                         float* y, int B, int K, int N, ibinn_stream_t stream);
+int ibinn_linear_dgrad(const float* g, const float* h, const float* g_mask, int g_pre, const float* w, float* dx,
+                       int64_t dx_rs, int accumulate, int B, int K, int N, ibinn_stream_t stream);
+int ibinn_linear_wgrad(const float* g, const float* h, const float* g_mask, int g_pre, const float* x, int64_t x_rs,
+                       const float* x_mask, int x_pre, float* dw, float* db, int B, int K, int N, ibinn_stream_t stream);
+
+/* ---------------------------------------------------------------- GMM / Information-Bottleneck head
+ * Replaces reference model.py:113-126 (`cluster_distances`) and model.py:144-163 (loss dict).
+ * z (B,D), jac (B), mu (C,D), phi (C), y (B,C) soft one-hot or NULL.  Per-sample outputs L_x, logits (B,C),
+ * L_cNLL, L_y, correct (0/1), lse; means[5] = mean(L_x), mean(logits), mean(L_cNLL), mean(L_y), acc. */
+int64_t ibinn_gmm_head_partials_floats(int B);
+int ibinn_gmm_head_forward(const float* z, const float* jac, const float* mu, const float* phi, const float* y, float* L_x,
+                           float* logits, float* L_cNLL, float* L_y, float* correct, float* lse, float* means,
+                           float* partials, uint32_t* counter, int B, int C, int D, ibinn_stream_t stream);
+/* upstream grads g_* may be NULL; s_* = element stride (0 broadcasts one scalar); they are multiplied by
+ * scale_vec / scale_logits (1/B and 1/(B*C) when the means were the outputs).  G_ws, Glw_ws: (B,C) workspaces. */
+int ibinn_gmm_head_backward(const float* z, const float* mu, const float* phi, const float* y, const float* logits,
+                            const float* lse, const float* g_Lx, int s_Lx, const float* g_LcNLL, int s_Lc,
+                            const float* g_Ly, int s_Ly, const float* g_logits, int s_logits, float scale_vec,
+                            float scale_logits, float* G_ws, float* Glw_ws, float* g_z, float* g_jac, float* g_mu,
+                            int accumulate_mu, float* g_phi, int accumulate_phi, int B, int C, int D,
+                            ibinn_stream_t stream);
+
+/* ---------------------------------------------------------------- clip_grad_norm_ + SGD (reference train.py:109-110)
+ * out_norm_coef[0] = sqrt(sum grad^2 + sum extra_sumsq), [1] = min(1, max_norm/(norm+1e-6)). */
+int64_t ibinn_grad_norm_partials_doubles(void);
+int ibinn_grad_norm_clip(const float* grad, int64_t n, const float* extra_sumsq, int n_extra, float max_norm,
+                         double* partials, uint32_t* counter, float* out_norm_coef, ibinn_stream_t stream);
+/* hyper = {lr, momentum, weight_decay} in device memory; clip_coef device scalar or NULL.
+ * d = grad*coef*grad_scale + wd*p; buf = momentum*buf + d; p -= lr*buf   (torch.optim.SGD, dampening 0) */
+int ibinn_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, const float* hyper,
+                   const float* clip_coef, float grad_scale, ibinn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

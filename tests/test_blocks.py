@@ -1,0 +1,206 @@
+"""Teacher-forced per-node parity: every ibinn_b200 node (forward, log-det, backward, inverse) against
+the fp64 oracle on the same seeded inputs and weights.  Runs on the SIMT simulator ('emu', CPU) and,
+with -m gpu, on the real sm_100a kernels.  Tolerances: out / grads <= 1e-5 of abs-max, log-det 1e-6
+relative (the reference's own fp32 sits at ~4e-7 / 6e-7)."""
+import math
+from functools import partial
+
+import numpy as np
+import pytest
+import torch
+
+from util import O, randomize_, rel, state_of
+
+from ibinn_b200 import functions as Fn
+from ibinn_b200.all_in_one_block import AIO_Block
+from ibinn_b200.dct_transform import DCTPooling2d
+from ibinn_b200.downsampling_coupling_block import DownsampleCouplingBlock
+from ibinn_b200.inn_architecture import _weights_init
+from ibinn_b200.modules import GLOWCouplingBlock, HaarDownsampling, PermuteRandom
+from ibinn_b200.subnets import ConvSubnet, FCSubnet
+
+BN_ARGS = {'track_running_stats': True, 'momentum': 0.999, 'eps': 1e-4}
+TOL_OUT, TOL_JAC, TOL_GRAD = 1e-5, 2e-6, 3e-5
+
+
+def conv_constr(width, dropout, relu_first, strided, cin, cout):
+    net = ConvSubnet(cin, cout, width, dropout, relu_first, strided, BN_ARGS)
+    net.apply(_weights_init)
+    return net
+
+
+def fc_constr(width, dropout, cin, cout):
+    net = FCSubnet(cin, cout, width, dropout)
+    net.apply(_weights_init)
+    return net
+
+
+def run_node(blk, spec, x, dev, train, masks_ours=None, masks_oracle=None, check_inverse=True, seed=0):
+    """forward+backward of `blk` on `dev` vs the oracle node `spec` in fp64."""
+    g = torch.Generator().manual_seed(100 + seed)
+    P = state_of(blk, spec.key + '.')
+    keys = [k for k in O.trainable_keys(P)]
+    for k in keys:
+        P[k].requires_grad_()
+    x64 = x.double().requires_grad_()
+    st = O._State(train, masks_oracle, False)
+    out64, jac64 = O.node_forward(x64, P, spec, st)
+    gout = torch.randn(out64.shape, generator=g)
+    gjac = torch.randn(x.shape[0], generator=g) * 0.01
+    loss64 = (out64 * gout.double()).sum()
+    if torch.is_tensor(jac64):
+        loss64 = loss64 + (jac64 * gjac.double()).sum()
+    loss64.backward()
+
+    blk = blk.to(dev)
+    blk.train(train)
+    xd = x.to(dev).requires_grad_()
+    kw = {}
+    if masks_ours is not None:
+        kw = masks_ours(dev)
+    out = blk([xd], **kw)[0]
+    jac = blk.jacobian([xd])
+    loss = (out * gout.to(dev)).sum()
+    if torch.is_tensor(jac):
+        loss = loss + (jac * gjac.to(dev)).sum()
+    loss.backward()
+
+    assert rel(out, out64) < TOL_OUT
+    if torch.is_tensor(jac64):
+        assert rel(jac, jac64) < TOL_JAC
+    else:
+        assert abs(float(jac) - float(jac64)) <= 1e-6 * max(1., abs(float(jac64)))
+    assert rel(xd.grad, x64.grad) < TOL_GRAD
+    named = dict(blk.named_parameters())
+    for k in keys:
+        name = k[len(spec.key) + 1:]
+        assert named[name].grad is not None, name
+        assert rel(named[name].grad, P[k].grad) < TOL_GRAD, name
+    if train:
+        for k, v in st.new_stats.items():
+            assert rel(dict(blk.state_dict())[k[len(spec.key) + 1:]], v) < 1e-5, k
+    if check_inverse:
+        blk.eval()
+        with torch.no_grad():
+            y = blk([x.to(dev)])[0]
+            xr = blk([y], rev=True)[0]
+            jr = blk.jacobian([y], rev=True)
+            jf = blk([x.to(dev)])[0] is not None and blk.jacobian([x.to(dev)])
+        assert rel(xr, x) < 2e-5
+        if torch.is_tensor(jr):
+            # log-det of the inverse at y = - log-det of the forward at x
+            blk([x.to(dev)])
+            jf = blk.jacobian([x.to(dev)])
+            assert rel(-jr, jf) < 1e-5
+
+
+AIO_CASES = [  # C, H, width, relu_first, B
+    (3, 32, 16, False, 3), (3, 32, 16, True, 2), (12, 16, 32, True, 3), (48, 8, 64, True, 2),
+    (4, 14, 32, True, 2), (16, 7, 64, True, 3), (8, 32, 16, True, 2),
+]
+
+
+@pytest.mark.parametrize('C,H,width,relu_first,B', AIO_CASES)
+@pytest.mark.parametrize('train', [True, False])
+def test_aio_block(dev, C, H, width, relu_first, B, train):
+    torch.manual_seed(C * 100 + H)
+    np.random.seed(C + H)
+    g = torch.Generator().manual_seed(7)
+    blk = AIO_Block([(C, H, H)], subnet_constructor=partial(conv_constr, width, 0., relu_first, False), clamp=0.7,
+                    act_norm=0.75, permute_soft=True)
+    randomize_(blk, g)
+    spec = O.NodeSpec('aio', 1, 'aio', (C, H, H), (C, H, H), dict(width=width, dropout=0., relu_first=relu_first, clamp=0.7))
+    x = torch.randn(B, C, H, H, generator=g)
+    run_node(blk, spec, x, dev, train)
+
+
+def test_aio_block_dropout_mask(dev):
+    """Dropout2d: injected (b,c) mask, same mask given to the oracle."""
+    torch.manual_seed(3)
+    np.random.seed(3)
+    g = torch.Generator().manual_seed(8)
+    C, H, width, B = 48, 8, 64, 3
+    blk = AIO_Block([(C, H, H)], subnet_constructor=partial(conv_constr, width, 0.25, True, False), clamp=0.7,
+                    act_norm=0.75, permute_soft=True)
+    randomize_(blk, g)
+    spec = O.NodeSpec('aio', 1, 'aio', (C, H, H), (C, H, H), dict(width=width, dropout=0.25, relu_first=True, clamp=0.7))
+    mask = (torch.rand(B, width, generator=g) >= 0.25).float() / 0.75
+    x = torch.randn(B, C, H, H, generator=g)
+    run_node(blk, spec, x, dev, True, masks_ours=lambda d: dict(mask=mask.to(d)), masks_oracle={'module_list.1.s.7': mask.double()},
+             check_inverse=False)
+
+
+DOWN_CASES = [(3, 32, 32, 2), (12, 16, 64, 2), (4, 14, 64, 3), (8, 32, 32, 2)]
+
+
+@pytest.mark.parametrize('C,H,width,B', DOWN_CASES)
+@pytest.mark.parametrize('train', [True, False])
+def test_down_block(dev, C, H, width, B, train):
+    torch.manual_seed(C * 10 + H)
+    g = torch.Generator().manual_seed(9)
+    blk = DownsampleCouplingBlock([(C, H, H)], subnet_constructor_strided=partial(conv_constr, width, 0., False, True),
+                                  subnet_constructor_low_res=partial(conv_constr, width, 0., False, False), clamp=0.7)
+    randomize_(blk, g)
+    spec = O.NodeSpec('down', 1, 'down', (C, H, H), (4 * C, H // 2, H // 2), dict(width=width, dropout=0., clamp=0.7))
+    x = torch.randn(B, C, H, H, generator=g)
+    run_node(blk, spec, x, dev, train)
+
+
+@pytest.mark.parametrize('D,width,B', [(3072, 16, 3), (784, 32, 2), (25, 8, 4)])
+@pytest.mark.parametrize('train', [True, False])
+def test_glow_block(dev, D, width, B, train):
+    torch.manual_seed(D)
+    g = torch.Generator().manual_seed(10)
+    blk = GLOWCouplingBlock([(D,)], subnet_constructor=partial(fc_constr, width, 0.), clamp=2.0)
+    randomize_(blk, g)
+    spec = O.NodeSpec('glow', 1, 'glow', (D,), (D,), dict(clamp=2.0, width=width, dropout=0.))
+    x = torch.randn(B, D, generator=g)
+    run_node(blk, spec, x, dev, train)
+
+
+def test_glow_block_dropout_mask(dev):
+    torch.manual_seed(5)
+    g = torch.Generator().manual_seed(11)
+    D, width, B = 96, 32, 5
+    blk = GLOWCouplingBlock([(D,)], subnet_constructor=partial(fc_constr, width, 0.5), clamp=2.0)
+    randomize_(blk, g)
+    spec = O.NodeSpec('glow', 1, 'glow', (D,), (D,), dict(clamp=2.0, width=width, dropout=0.5))
+    m1 = (torch.rand(B, width, generator=g) >= 0.5).float() * 2
+    m2 = (torch.rand(B, width, generator=g) >= 0.5).float() * 2
+    x = torch.randn(B, D, generator=g)
+    run_node(blk, spec, x, dev, True, masks_ours=lambda d: dict(masks=(m1.to(d), m2.to(d))),
+             masks_oracle={'module_list.1.s1.2': m1.double(), 'module_list.1.s2.2': m2.double()}, check_inverse=False)
+
+
+@pytest.mark.parametrize('C,N,B', [(48, 8, 3), (16, 7, 2), (128, 8, 2)])
+def test_dct(dev, C, N, B):
+    g = torch.Generator().manual_seed(12)
+    blk = DCTPooling2d([(C, N, N)], rebalance=0.5)
+    spec = O.NodeSpec('dct', 1, 'dct', (C, N, N), (C * N * N,), dict(rebalance=0.5))
+    x = torch.randn(B, C, N, N, generator=g)
+    run_node(blk, spec, x, dev, False)
+    # analytic weight == what the reference gets from its FFT-based dct_1d (3e-7), and the declared constant log-det
+    assert abs(blk.jac - N * N * C * math.log(0.5)) < 1e-9
+
+
+@pytest.mark.parametrize('C,H,B', [(1, 28, 3), (3, 8, 2)])
+def test_haar(dev, C, H, B):
+    g = torch.Generator().manual_seed(13)
+    blk = HaarDownsampling([(C, H, H)], rebalance=1.)
+    spec = O.NodeSpec('haar', 1, 'haar', (C, H, H), (4 * C, H // 2, H // 2), dict(rebalance=1.))
+    x = torch.randn(B, C, H, H, generator=g)
+    run_node(blk, spec, x, dev, False)
+
+
+@pytest.mark.parametrize('D', [3072, 784])
+def test_permute(dev, D):
+    g = torch.Generator().manual_seed(14)
+    blk = PermuteRandom([(D,)], seed=0)
+    # known answers of numpy's legacy RandomState
+    assert blk.perm[:8].tolist() == {3072: [1430, 779, 643, 1853, 1907, 1224, 1476, 2497],
+                                     784: [693, 85, 647, 392, 765, 14, 299, 711]}[D]
+    spec = O.NodeSpec('perm', 1, 'perm', (D,), (D,), dict(seed=0))
+    x = torch.randn(3, D, generator=g)
+    run_node(blk, spec, x, dev, False)
+    y = blk([x.to(dev)])[0]
+    assert torch.equal(y.cpu(), x[:, blk.perm])          # bit-exact gather
