@@ -66,7 +66,8 @@ __global__ void __launch_bounds__(IBINN_THREADS) head_fwd_kernel(const HeadP p) 
         float s = 0.f;
         for (int k = lane; k < C; k += 32) s += expf(-0.5f * s_zz[k] + s_lw[k] - m);
         s = warp_sum(s);
-        const float lse = m + logf(s);
+        const float ls = logf(s);
+        const float lse = m + ls;
         float sl = 0.f;
         for (int k = lane; k < C; k += 32) {
             const float lg = -0.5f * s_zz[k];
@@ -81,7 +82,8 @@ __global__ void __launch_bounds__(IBINN_THREADS) head_fwd_kernel(const HeadP p) 
                 const float yk = __ldg(p.y + (size_t)b * C + k);
                 const float lg = -0.5f * s_zz[k];
                 lc = fmaf(s_zz[k], rintf(yk), lc);
-                ly = fmaf(yk, lg - lse, ly);   // log_softmax(l)_k - logw_k with l_k = lg + logw_k
+                // (log_softmax(l)_k - logw_k) evaluated like the reference: shift by the max first
+                ly = fmaf(yk, ((lg + s_lw[k] - m) - ls) - s_lw[k], ly);
                 if (yk > by) { by = yk; iy = k; }
                 if (lg > bl) { bl = lg; il = k; }
             }
@@ -129,34 +131,48 @@ struct HeadBwdP {
     int B, C, D, dchunk;
 };
 
-// per sample: G = dLoss/dzz, Glw = dLoss/dlogw contributions, g_jac
-__global__ void __launch_bounds__(IBINN_THREADS) head_bwd_g_kernel(const HeadBwdP p) {
-    __shared__ float s_lw[1024];
-    const int C = p.C, b = blockIdx.x, tid = threadIdx.x;
-    log_softmax_phi(p.phi, C, s_lw);
-    __syncthreads();
+// per sample: G = dLoss/dzz, Glw = dLoss/dlogw contributions, g_jac.  The class posterior is
+// re-normalised here (p = exp(l - max) / sum) so that sum_k p_k = 1 to rounding: with logits of
+// magnitude 1e3 a saved fp32 log-sum-exp would leave a 1e-4 common factor that the cancelling
+// (-y + p) terms amplify.
+__global__ void __launch_bounds__(32) head_bwd_g_kernel(const HeadBwdP p) {
+    const int C = p.C, b = blockIdx.x, lane = threadIdx.x;
+    // log_softmax(phi)
+    float pm = -INFINITY;
+    for (int k = lane; k < C; k += 32) pm = fmaxf(pm, __ldg(p.phi + k));
+    pm = warp_max(pm);
+    float ps = 0.f;
+    for (int k = lane; k < C; k += 32) ps += expf(__ldg(p.phi + k) - pm);
+    ps = warp_sum(ps);
+    const float plse = pm + logf(ps);
     const float invD = 1.f / (float)p.D;
     const float glx = p.gLx ? __ldg(p.gLx + (size_t)b * p.sLx) * p.scale_vec : 0.f;
     const float glc = p.gLc ? __ldg(p.gLc + (size_t)b * p.sLc) * p.scale_vec : 0.f;
     const float gly = p.gLy ? __ldg(p.gLy + (size_t)b * p.sLy) * p.scale_vec : 0.f;
-    const float lse = __ldg(p.lse + b);
-    __shared__ float s_scr[40];
-    float sy = 0.f;
-    if (p.y) for (int k = tid; k < C; k += IBINN_THREADS) sy += __ldg(p.y + (size_t)b * C + k);
-    sy = block_sum(sy, s_scr);
-    for (int k = tid; k < C; k += IBINN_THREADS) {
-        const float lg = __ldg(p.logits + (size_t)b * C + k);
-        const float pk = expf(lg + s_lw[k] - lse);
+    float m = -INFINITY, sy = 0.f;
+    for (int k = lane; k < C; k += 32) {
+        m = fmaxf(m, __ldg(p.logits + (size_t)b * C + k) + (__ldg(p.phi + k) - plse));
+        if (p.y) sy += __ldg(p.y + (size_t)b * C + k);
+    }
+    m = warp_max(m);
+    sy = warp_sum(sy);
+    float se = 0.f;
+    for (int k = lane; k < C; k += 32) se += expf(__ldg(p.logits + (size_t)b * C + k) + (__ldg(p.phi + k) - plse) - m);
+    se = warp_sum(se);
+    const float inv_se = 1.f / se;
+    for (int k = lane; k < C; k += 32) {
+        const float l = __ldg(p.logits + (size_t)b * C + k) + (__ldg(p.phi + k) - plse);
+        const float pk = expf(l - m) * inv_se;
         float g = glx * pk * 0.5f * invD;
         if (p.y) {
             const float yk = __ldg(p.y + (size_t)b * C + k);
-            g += gly * (-0.5f * yk + 0.5f * pk * sy) + glc * rintf(yk) * 0.5f * invD;
+            g += gly * 0.5f * (pk * sy - yk) + glc * rintf(yk) * 0.5f * invD;
         }
         if (p.gLogits) g -= 0.5f * __ldg(p.gLogits + ((size_t)b * C + k) * p.sLogits) * p.scale_logits;
         p.G[(size_t)b * C + k] = g;
         p.Glw[(size_t)b * C + k] = -glx * pk * invD;
     }
-    if (tid == 0) p.g_jac[b] = -(glx + glc) * invD;
+    if (lane == 0) p.g_jac[b] = -(glx + glc) * invD;
 }
 
 // per chunk of latent dims: g_z = 2 (z rowsum(G) - G mu), g_mu = -2 (G^T z - mu colsum(G)); block 0 also g_phi
@@ -270,7 +286,7 @@ extern "C" int ibinn_gmm_head_backward(const float* z, const float* mu, const fl
     p.G = G_ws; p.Glw = Glw_ws; p.g_jac = g_jac; p.g_z = g_z; p.g_mu = g_mu; p.g_phi = g_phi;
     p.acc_mu = accumulate_mu; p.acc_phi = accumulate_phi; p.B = B; p.C = C; p.D = D;
     cudaStream_t st = (cudaStream_t)stream;
-    IBINN_LAUNCH(head_bwd_g_kernel, dim3(B), dim3(IBINN_THREADS), 0, st, p);
+    IBINN_LAUNCH(head_bwd_g_kernel, dim3(B), dim3(32), 0, st, p);
     e = ibinn_launch_status();
     if (e) return e;
     int dc = 32;
