@@ -50,6 +50,7 @@ class WgradArgs(Structure):
 P, I, F, L = c_void_p, c_int, c_float, c_int64
 _SIGNATURES = {
     'ibinn_abi_version': ([], c_int),
+    'ibinn_launch_count': ([], c_int64),
     'ibinn_check_device': ([], c_int),
     'ibinn_sizeof_conv_args': ([], c_size_t),
     'ibinn_conv_partials_floats': ([POINTER(ConvArgs)], c_int64),
@@ -103,11 +104,57 @@ def load(path=None):
     return _declare(ctypes.CDLL(path))
 
 
+class _Profiler:
+    """Proxy over the library that brackets every entry point with CUDA events on the current stream
+    (bench.py's per-kernel-class device times; eager mode only, never active under graph capture)."""
+
+    def __init__(self, lib):
+        self._lib, self.records = lib, []
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if fn.restype is not c_int or name == 'ibinn_check_device':
+            return fn
+
+        def timed(*args):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = fn(*args)
+            b.record()
+            self.records.append((name + ('[%s]' % _tag if _tag else ''), a, b))
+            return rc
+        return timed
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.records:
+            t, n = out.get(name, (0., 0))
+            out[name] = (t + a.elapsed_time(b), n + 1)
+        return out
+
+
+_profiler = None
+_tag = ''
+
+
+def set_tag(t):
+    global _tag
+    _tag = t
+
+
+def profile(enable):
+    """bench.py: start / stop per-entry-point device timing.  Returns the finished profiler on stop."""
+    global _profiler
+    old, _profiler = _profiler, (_Profiler(lib()) if enable else None)
+    return old
+
+
 def lib():
     global _lib
     if _lib is None:
         _lib = load()
-    return _lib
+    return _profiler if _profiler is not None else _lib
 
 
 def _use_library_for_tests(path, allow_host_pointers):

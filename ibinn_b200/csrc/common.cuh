@@ -3,8 +3,9 @@
 #ifndef IBINN_EMU
 #include <cuda_runtime.h>
 #include <stdint.h>
+extern unsigned long long ibinn_launch_counter;
 #define IBINN_LAUNCH(kernel, grid, block, smem, stream, ...) \
-    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+    (++ibinn_launch_counter, kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__))
 #define IBINN_DYN_SMEM(type, name)                                  \
     extern __shared__ __align__(1024) unsigned char ibinn_dyn_raw[]; \
     type* name = reinterpret_cast<type*>(ibinn_dyn_raw)

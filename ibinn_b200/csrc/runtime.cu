@@ -1,7 +1,20 @@
 // Device gate: the library serves sm_100 (B200) only and has no other path.
 #include "common.cuh"
 
+#ifndef IBINN_EMU
+unsigned long long ibinn_launch_counter = 0;
+#endif
+
 extern "C" int ibinn_abi_version(void) { return 1; }
+
+// number of kernels this library has enqueued in this process (host-side counter; bench.py reports it)
+extern "C" int64_t ibinn_launch_count(void) {
+#ifdef IBINN_EMU
+    return 0;
+#else
+    return (int64_t)ibinn_launch_counter;
+#endif
+}
 
 extern "C" int ibinn_check_device(void) {
 #ifdef IBINN_EMU

@@ -1,0 +1,187 @@
+"""Training-step engine around GenerativeClassifier: flat parameter / gradient buffers, fused
+clip + SGD, whole-step CUDA-graph capture, and batch-sharded data parallelism over NCCL.
+
+Reference semantics reproduced (train.py:88-111): loss = beta_x * L_x - beta_y * L_y with
+beta_x = 2/(1+beta), beta_y = 2 beta/(1+beta); clip_grad_norm_ over *all* trainable tensors
+(INN, mu, phi) at `clip_grad_norm`; torch.optim.SGD per parameter group (model.py:73-100).
+Multi-GPU: every rank runs the reference's single-GPU step on its own batch
+with local BatchNorm statistics; the only exchange is one all-reduce of the flat gradient.
+"""
+import torch
+import torch.distributed as dist
+
+from . import _lib, ops
+
+
+class FlatParams:
+    """Moves every trainable tensor of the model into one flat fp32 buffer (segments per optimiser
+    group, 16-byte aligned) with a matching flat gradient and momentum buffer.  Parameters keep
+    their identity (`p.data` becomes a view), so state_dict / checkpoints / the torch optimiser
+    object are unaffected; `p._ibinn_grad` tells the backward kernels to accumulate in place."""
+
+    def __init__(self, model):
+        self.model = model
+        dev = model.mu.device
+        groups = model.optimizer.param_groups
+        in_group = set()
+        segs = []
+        for gi, g in enumerate(groups):
+            ps = [p for p in g['params'] if p.requires_grad]
+            in_group.update(id(p) for p in ps)
+            segs.append((gi, ps))
+        rest = [p for p in model.trainable_params if id(p) not in in_group and p.requires_grad]
+        if rest:
+            segs.append((None, rest))      # clipped with the others, but no optimiser group updates them
+        total, layout = 0, []
+        for gi, ps in segs:
+            start = total
+            offs = []
+            for p in ps:
+                offs.append(total)
+                total += (p.numel() + 3) // 4 * 4
+            layout.append((gi, ps, offs, start, total))
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.buf = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.segments = []
+        for gi, ps, offs, start, end in layout:
+            for p, o in zip(ps, offs):
+                n = p.numel()
+                self.flat[o:o + n].copy_(p.data.reshape(-1))
+                p.data = self.flat[o:o + n].view(p.shape)
+                p._ibinn_grad = self.grad[o:o + n].view(p.shape)
+                p.grad = p._ibinn_grad
+            hyper = torch.zeros(3, dtype=torch.float32, device=dev) if gi is not None else None
+            self.segments.append(dict(group=gi, start=start, end=end, hyper=hyper, host=None))
+        self.sync_hyper()
+
+    def sync_hyper(self):
+        """Copy lr / momentum / weight_decay of the torch optimiser groups to the device (call after a
+        scheduler step; a captured graph reads them from there)."""
+        for s in self.segments:
+            if s['group'] is None:
+                continue
+            g = self.model.optimizer.param_groups[s['group']]
+            vals = (float(g['lr']), float(g.get('momentum', 0.)), float(g.get('weight_decay', 0.)))
+            if vals != s['host']:
+                s['hyper'].copy_(torch.tensor(vals, dtype=torch.float32))
+                s['host'] = vals
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def clip_and_step(self, max_norm, grad_scale=1.0):
+        """Fused clip_grad_norm_ + SGD.  Returns the device tensor [total_norm, clip_coef]."""
+        # ||grad_scale * g|| <= max_norm  <=>  ||g|| <= max_norm / grad_scale
+        nc = ops.grad_norm_clip(self.grad, max_norm / grad_scale)
+        for s in self.segments:
+            if s['group'] is None:
+                continue
+            sl = slice(s['start'], s['end'])
+            ops.sgd_step_(self.flat[sl], self.grad[sl], self.buf[sl], s['hyper'], nc[1:], grad_scale)
+        return nc
+
+
+def beta_weights(beta, train_nll=True):
+    """reference train.py:88-92"""
+    if not train_nll:
+        return 0., 1.
+    return 2. / (1. + beta), 2. * beta / (1. + beta)
+
+
+class TrainStep:
+    """One optimisation step: zero grads -> forward -> IB loss -> backward -> [all-reduce] -> clip -> SGD.
+
+    `step(x, y)` takes device tensors or pinned host tensors (copied into static device buffers on the
+    step's stream) and returns the dict of device scalars the reference logs (no host sync).  With
+    `use_graph` the whole step is captured once into CUDA graphs and replayed."""
+
+    def __init__(self, model, batch_size, beta=None, clip=None, use_graph=True, process_group=None, class_nll=None):
+        if not isinstance(model.optimizer, torch.optim.SGD):
+            raise NotImplementedError('the fused step implements the reference default (SGD); use the plain torch loop otherwise')
+        t = model.args['training']
+        self.model = model
+        self.beta = float(t['beta_IB']) if beta is None else float(beta)
+        self.clip = float(t['clip_grad_norm']) if clip is None else float(clip)
+        ab = model.args['ablations']
+        self.class_nll = eval(ab['class_NLL']) if class_nll is None else class_nll
+        self.bx, self.by = beta_weights(self.beta, not eval(ab['no_NLL_term']))
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
+        self.flat = FlatParams(model)
+        dev = model.mu.device
+        self.x = torch.zeros((batch_size,) + tuple(model.dims), dtype=torch.float32, device=dev)
+        self.y = torch.zeros((batch_size, model.n_classes), dtype=torch.float32, device=dev)
+        self.use_graph = bool(use_graph) and dev.type == 'cuda'
+        self._g1 = self._g2 = None
+        self.out = None
+        self.launches = None
+
+    # -- pieces ---------------------------------------------------------------------------------
+    def _fwd_bwd(self):
+        self.flat.zero_grad()
+        losses = self.model(self.x, self.y)
+        if self.class_nll:
+            loss = 2. * losses['L_cNLL_tr']
+        else:
+            loss = self.bx * losses['L_x_tr'] - self.by * losses['L_y_tr']
+        loss.backward()
+        self.out = {k: losses[k].detach() for k in ('L_x_tr', 'L_y_tr', 'acc_tr', 'L_cNLL_tr')}
+
+    def _reduce(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
+
+    def _update(self):
+        # the all-reduce sums; the mean gradient is grad / world (folded into the clip and the update)
+        nc = self.flat.clip_and_step(self.clip, grad_scale=1.0 / self.world)
+        self.out['grad_norm'] = nc[0] / self.world if self.world > 1 else nc[0]
+
+    def _eager(self):
+        self._fwd_bwd()
+        self._reduce()
+        self._update()
+
+    def capture(self, warmup=3):
+        """Warm up eagerly (lazy inits, allocator), then capture.  The all-reduce stays outside the
+        graphs (two graphs around one NCCL call) so that capture never depends on the NCCL build."""
+        L = _lib.lib()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._eager()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        n0 = L.ibinn_launch_count() if hasattr(L, 'ibinn_launch_count') else 0
+        self._g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g1):
+            self._fwd_bwd()
+        self._g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._g2, pool=self._g1.pool()):
+            self._update()
+        n1 = L.ibinn_launch_count() if hasattr(L, 'ibinn_launch_count') else 0
+        self.launches = int(n1 - n0)
+        torch.cuda.synchronize()
+
+    # -- public ---------------------------------------------------------------------------------
+    def load(self, x, y):
+        self.x.copy_(x, non_blocking=True)
+        self.y.copy_(y, non_blocking=True)
+
+    def run(self):
+        """one step on whatever is in the static buffers"""
+        self.flat.sync_hyper()
+        if self.use_graph:
+            if self._g1 is None:
+                self.capture()
+            self._g1.replay()
+            self._reduce()
+            self._g2.replay()
+        else:
+            self._eager()
+        return self.out
+
+    def step(self, x, y):
+        self.load(x, y)
+        return self.run()

@@ -113,7 +113,10 @@ def conv_forward(x, w, ksize, stride=1, *, cout=None, pre=PRE_NONE, pre_bn=None,
         keep = torch.empty(max(int(n), 1), dtype=torch.float32, device=x.device)
         a.partials = ptr(keep)
         a.counter = counter_ptr(x)
+    if _lib._profiler is not None:
+        _lib.set_tag('k%d s%d %s %d->%d @%dx%d pre%d epi%d' % (ksize, stride, 'T' if w_transposed else 'N', Cin, cout, Hout, Wout, pre, epi))
     check(L.ibinn_conv_forward(ctypes.byref(a), stream(x)), 'conv_forward')
+    _lib.set_tag('')
     return out
 
 
@@ -136,7 +139,10 @@ def conv_wgrad(g, x, dw, ksize, stride=1, *, g_pre=PRE_NONE, gh=None, g_bn=None,
     a.x_mask = ptr(x_mask)
     a.dw, a.dbias = ptr(dw), ptr(dbias)
     a.B, a.Cin, a.Cout, a.Hin, a.Win, a.Hout, a.Wout, a.ksize, a.stride = B, Cin, Cout, Hin, Win, Hout, Wout, ksize, stride
+    if _lib._profiler is not None:
+        _lib.set_tag('k%d s%d %d->%d @%dx%d' % (ksize, stride, Cin, Cout, Hout, Wout))
     check(_lib.lib().ibinn_conv_wgrad(ctypes.byref(a), stream(g)), 'conv_wgrad')
+    _lib.set_tag('')
 
 
 # ------------------------------------------------------------------------------------ couplings

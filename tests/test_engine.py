@@ -1,0 +1,147 @@
+"""Fused clip + SGD and the whole training step (flat buffers, direct gradient accumulation) against
+torch.optim.SGD / clip_grad_norm_ and the fp64 oracle; data-parallel equivalence on 2 gloo ranks."""
+import copy
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from util import O, ROOT, rel
+
+from ibinn_b200 import config, ops
+from ibinn_b200.engine import FlatParams, TrainStep
+from ibinn_b200.model import GenerativeClassifier
+
+SMALL = {'model': {'n_coupling_blocks_conv': '[1, 1, 1]', 'fc_width': '8', 'dropout_conv': '[0., 0., 0.]', 'dropout_fc': '0.'}}
+
+
+def test_clip_and_sgd_kernels(dev):
+    g = torch.Generator().manual_seed(0)
+    n = 10007
+    p = torch.randn(n, generator=g).to(dev)
+    gr = (torch.randn(n, generator=g) * 3).to(dev)
+    buf = torch.randn(n, generator=g).to(dev)
+    pad = torch.zeros(16 - n % 16 if n % 16 else 0)     # the kernels only need 16-byte aligned starts
+    hyper = torch.tensor([0.07, 0.9, 1e-4]).to(dev)
+    p0, g0, b0 = p.clone(), gr.clone(), buf.clone()
+    nc = ops.grad_norm_clip(gr, 8.0)
+    ops.sgd_step_(p, gr, buf, hyper, nc[1:], 1.0)
+    norm = g0.double().norm()
+    coef = min(1., 8.0 / (norm.item() + 1e-6))
+    assert rel(nc[0:1], norm.view(1)) < 1e-6 and abs(nc[1].item() - coef) < 1e-6
+    d = g0.double() * coef + 1e-4 * p0.double()
+    b1 = 0.9 * b0.double() + d
+    assert rel(buf, b1) < 1e-6
+    assert rel(p, p0.double() - 0.07 * b1) < 1e-6
+
+
+def _model(dev, seed=0, overrides=SMALL):
+    args = config.make_args(overrides=overrides)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    return GenerativeClassifier(args).to(dev)
+
+
+def _batch(B, C, gen):
+    x = torch.randn(B, 3, 32, 32, generator=gen)
+    lab = torch.randint(0, C, (B,), generator=gen)
+    y = torch.zeros(B, C).scatter_(1, lab.view(-1, 1), 1.) * 0.98 + 0.02 / C
+    return x, y
+
+
+def test_train_step_matches_torch_loop(dev):
+    """TrainStep (flat buffers, in-place gradient accumulation, fused clip+SGD) == the reference's loop
+    (loss.backward(); clip_grad_norm_; optimizer.step()) run on the same ibinn_b200 model."""
+    gen = torch.Generator().manual_seed(1)
+    m1 = _model(dev)
+    m2 = copy.deepcopy(m1)
+    step = TrainStep(m2, batch_size=4, beta=1.0, clip=8., use_graph=False)
+    for it in range(3):
+        x, y = _batch(4, 10, gen)
+        x, y = x.to(dev), y.to(dev)
+        out = m1(x, y)
+        loss = 1.0 * out['L_x_tr'] - 1.0 * out['L_y_tr']
+        loss.backward()
+        n1 = torch.nn.utils.clip_grad_norm_(m1.trainable_params, 8.)
+        m1.optimizer.step()
+        m1.optimizer.zero_grad()
+        o2 = step.step(x, y)
+        assert rel(o2['L_x_tr'], out['L_x_tr']) < 1e-6
+        assert rel(o2['grad_norm'], n1) < 1e-4
+    sd1, sd2 = m1.state_dict(), m2.state_dict()
+    for k in sd1:
+        if sd1[k].is_floating_point():
+            assert rel(sd2[k], sd1[k]) < 2e-4, k
+    # the torch optimiser's momentum state and ours agree too
+    p1 = m1.optimizer.param_groups[0]['params'][0]
+    p2 = m2.optimizer.param_groups[0]['params'][0]
+    b2 = step.flat.buf[:p2.numel()].view(p2.shape)
+    assert rel(b2, m1.optimizer.state[p1]['momentum_buffer']) < 2e-4
+
+
+def test_train_step_follows_lr_schedule(dev):
+    m = _model(dev)
+    step = TrainStep(m, batch_size=2, use_graph=False)
+    sched = torch.optim.lr_scheduler.MultiStepLR(m.optimizer, milestones=[1], gamma=0.1)
+    gen = torch.Generator().manual_seed(2)
+    x, y = _batch(2, 10, gen)
+    step.step(x.to(dev), y.to(dev))
+    m.optimizer.step = lambda *a, **k: None      # the scheduler only needs the call order to be sane
+    sched.step()
+    step.step(x.to(dev), y.to(dev))
+    assert step.flat.segments[0]['hyper'][0].item() == pytest.approx(0.007)
+    assert step.flat.segments[1]['hyper'][0].item() == pytest.approx(0.021)
+
+
+def _ddp_worker(rank, world, port, lib_path, tmp):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    sys.path[:0] = [ROOT, os.path.join(ROOT, 'tests')]
+    import torch.distributed as dist
+    from ibinn_b200 import _lib
+    _lib._use_library_for_tests(lib_path, True)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    dev = torch.device('cpu')
+    m = _model(dev)
+    step = TrainStep(m, batch_size=3, beta=1.0, clip=8., use_graph=False)
+    gen = torch.Generator().manual_seed(5)
+    for it in range(2):
+        xs, ys = _batch(3 * world, 10, gen)
+        step.step(xs[rank * 3:(rank + 1) * 3], ys[rank * 3:(rank + 1) * 3])
+    torch.save({k: v for k, v in m.state_dict().items() if 'running' not in k and 'num_batches' not in k}, os.path.join(tmp, 'r%d.pt' % rank))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_equals_gradient_accumulation(tmp_path):
+    """2 gloo ranks (simulator kernels) == 1 process that runs the two micro-batches one after the other with
+    gradient accumulation (BatchNorm statistics local to each micro-batch), SURVEY.md section 8e."""
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, 'tests', 'emu'))
+    import build_emu
+    lib_path = build_emu.build()
+    from ibinn_b200 import _lib
+    _lib._use_library_for_tests(lib_path, True)
+    try:
+        port = 29500 + os.getpid() % 2000
+        mp.spawn(_ddp_worker, args=(2, port, lib_path, str(tmp_path)), nprocs=2, join=True)
+        r0, r1 = torch.load(tmp_path / 'r0.pt'), torch.load(tmp_path / 'r1.pt')
+        for k in r0:
+            assert torch.equal(r0[k], r1[k]), k          # replicas stay bit-identical
+        dev = torch.device('cpu')
+        m = _model(dev)
+        flat = FlatParams(m)
+        gen = torch.Generator().manual_seed(5)
+        for it in range(2):
+            xs, ys = _batch(6, 10, gen)
+            flat.zero_grad()
+            for r in range(2):
+                out = m(xs[r * 3:(r + 1) * 3], ys[r * 3:(r + 1) * 3])
+                (out['L_x_tr'] - out['L_y_tr']).backward()
+            flat.clip_and_step(8., grad_scale=0.5)
+        sd = m.state_dict()
+        for k in r0:
+            if r0[k].is_floating_point():
+                assert rel(r0[k], sd[k]) < 1e-5, k
+    finally:
+        _lib._use_library_for_tests(None, False)
