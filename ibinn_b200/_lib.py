@@ -51,6 +51,7 @@ P, I, F, L = c_void_p, c_int, c_float, c_int64
 _SIGNATURES = {
     'ibinn_abi_version': ([], c_int),
     'ibinn_launch_count': ([], c_int64),
+    'ibinn_last_error': ([], ctypes.c_char_p),
     'ibinn_check_device': ([], c_int),
     'ibinn_sizeof_conv_args': ([], c_size_t),
     'ibinn_conv_partials_floats': ([POINTER(ConvArgs)], c_int64),
@@ -169,7 +170,12 @@ def check(rc, what):
         return
     if rc < 0:
         raise RuntimeError('ibinn_b200.%s rejected the call: %s' % (what, ERRORS.get(rc, rc)))
-    raise RuntimeError('ibinn_b200.%s: CUDA error %d at launch' % (what, rc))
+    msg = ''
+    try:
+        msg = (_lib.ibinn_last_error() or b'').decode()
+    except Exception:
+        pass
+    raise RuntimeError('ibinn_b200.%s: CUDA error %d (%s)' % (what, rc, msg))
 
 
 def ptr(t, dtype=torch.float32, strided=False):

@@ -3,26 +3,46 @@
 #ifndef IBINN_EMU
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 extern unsigned long long ibinn_launch_counter;
 #define IBINN_LAUNCH(kernel, grid, block, smem, stream, ...) \
     (++ibinn_launch_counter, kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__))
 #define IBINN_DYN_SMEM(type, name)                                  \
-    extern __shared__ __align__(1024) unsigned char ibinn_dyn_raw[]; \
+    extern __shared__ __align__(16) unsigned char ibinn_dyn_raw[]; \
     type* name = reinterpret_cast<type*>(ibinn_dyn_raw)
 #endif
 #include "../../include/ibinn_b200.h"
 
 #define IBINN_THREADS 256
 
+// last failure of this library in this process, for the Python wrapper's exception text
+extern char ibinn_errbuf[256];
+#ifdef IBINN_EMU
+#define IBINN_ERRSTR(e) "emulator"
+#else
+#define IBINN_ERRSTR(e) cudaGetErrorString(e)
+#endif
+
 // status of the launch just enqueued: 0 or the (positive) cudaError_t
-static inline int ibinn_launch_status() { return (int)cudaGetLastError(); }
+static inline int ibinn_launch_status_(const char* file, int line) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) snprintf(ibinn_errbuf, sizeof(ibinn_errbuf), "%s:%d launch failed: %s", file, line, IBINN_ERRSTR(e));
+    return (int)e;
+}
+#define ibinn_launch_status() ibinn_launch_status_(__FILE__, __LINE__)
 
 template <class F>
 static inline int ibinn_set_smem(F kernel, size_t bytes) {
-    if (bytes > 227 * 1024) return IBINN_EINVAL;
-    if (bytes > 48 * 1024) {
+    if (bytes > 227 * 1024) {
+        snprintf(ibinn_errbuf, sizeof(ibinn_errbuf), "dynamic shared memory request of %zu bytes exceeds 227 KB", bytes);
+        return IBINN_EINVAL;
+    }
+    if (bytes > 40 * 1024) {   // static shared memory counts against the 48 KB default too
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        if (e != cudaSuccess) return (int)e;
+        if (e != cudaSuccess) {
+            snprintf(ibinn_errbuf, sizeof(ibinn_errbuf), "cudaFuncSetAttribute(max dynamic smem = %zu) failed: %s", bytes, IBINN_ERRSTR(e));
+            return (int)e;
+        }
     }
     return 0;
 }

@@ -5,7 +5,12 @@
 unsigned long long ibinn_launch_counter = 0;
 #endif
 
+char ibinn_errbuf[256] = "";
+
 extern "C" int ibinn_abi_version(void) { return 1; }
+
+// text of the most recent failure reported by this library ("" if none)
+extern "C" const char* ibinn_last_error(void) { return ibinn_errbuf; }
 
 // number of kernels this library has enqueued in this process (host-side counter; bench.py reports it)
 extern "C" int64_t ibinn_launch_count(void) {

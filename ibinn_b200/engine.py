@@ -146,6 +146,12 @@ class TrainStep:
         """Warm up eagerly (lazy inits, allocator), then capture.  The all-reduce stays outside the
         graphs (two graphs around one NCCL call) so that capture never depends on the NCCL build."""
         L = _lib.lib()
+        # Warm up and capture on ONE side stream: autograd remembers the stream on which a parameter's
+        # gradient accumulator was created and syncs it with the backward's stream, which is illegal
+        # across a capture boundary.
+        self.out = None
+        if hasattr(self.model.inn, 'release_graph'):
+            self.model.inn.release_graph()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -153,14 +159,14 @@ class TrainStep:
                 self._eager()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
-        n0 = L.ibinn_launch_count() if hasattr(L, 'ibinn_launch_count') else 0
+        n0 = L.ibinn_launch_count()
         self._g1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._g1):
+        with torch.cuda.graph(self._g1, stream=s):
             self._fwd_bwd()
         self._g2 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._g2, pool=self._g1.pool()):
+        with torch.cuda.graph(self._g2, pool=self._g1.pool(), stream=s):
             self._update()
-        n1 = L.ibinn_launch_count() if hasattr(L, 'ibinn_launch_count') else 0
+        n1 = L.ibinn_launch_count()
         self.launches = int(n1 - n0)
         torch.cuda.synchronize()
 

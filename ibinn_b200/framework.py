@@ -86,6 +86,15 @@ class ReversibleGraphNet(nn.Module):
             self._jacs.append((k, h))
         return h
 
+    def release_graph(self):
+        """Drop every reference to autograd graphs of earlier passes (cached per-node log-dets, node
+        inputs).  engine.TrainStep calls this before CUDA-graph capture: a live old graph keeps the
+        parameters' gradient accumulators -- and the stream they were created on -- alive."""
+        self._node_inputs, self._jacs = {}, []
+        for m in self.module_list:
+            if m is not None and hasattr(m, 'last_jac') and torch.is_tensor(m.last_jac):
+                m.last_jac = None
+
     def log_jacobian(self, x=None, c=None, rev=False, run_forward=True, intermediate_outputs=False):
         if run_forward:
             self.forward(x, rev=rev)

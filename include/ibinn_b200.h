@@ -33,6 +33,8 @@ extern "C" {
 typedef void* ibinn_stream_t; /* cudaStream_t */
 
 int ibinn_abi_version(void);
+/* text of the most recent failure reported by this library ("" if none); not thread-safe, diagnostics only */
+const char* ibinn_last_error(void);
 /* kernels enqueued by this library in this process so far (host-side counter) */
 int64_t ibinn_launch_count(void);
 /* 0 if the current device is sm_100, else IBINN_EARCH (or the cudaError_t). */
