@@ -1,9 +1,13 @@
 // Fully connected subnets of the GLOW coupling block (reference inn_architecture.py:112-120:
-// Linear -> ReLU -> Dropout -> Linear) and their backward: exact-fp32 SGEMM on the CUDA cores.
+// Linear -> ReLU -> Dropout -> Linear) and their backward as tcgen05 tensor-core GEMMs with
+// fp32-accurate 3xTF32 arithmetic (x = hi + lo; D += hi.hi + hi.lo + lo.hi, fp32 accumulate in TMEM).
 // One strided kernel serves y = x W^T + b, dx = g W and dW = g^T x; ReLU / dropout (forward) and
-// their masks (backward) are applied to the A operand while it is staged, so the pre-activation
-// is the only tensor that is stored.  Small-M problems are split along K to fill the 148 SMs.
+// their masks (backward) are applied while an operand is staged, so the pre-activation is the only
+// tensor that is stored.  Small-M problems are split along K to fill the 148 SMs.
+// (The plain CUDA-core kernel below is what the host-side simulator build runs; the product build
+// never launches it.)
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace {
 
@@ -120,6 +124,135 @@ __global__ void __launch_bounds__(IBINN_THREADS) gemm_kernel(const GemmP p) {
     }
 }
 
+
+#ifndef IBINN_EMU
+// ------------------------------------------------------------------------------------ tcgen05 path
+// CTA tile: 128 (M) x 64 (N), K staged 32 at a time (4 MMAs of K = 8 per pass), 2 stages.
+// All 256 threads stage operands (global -> registers -> pre-op -> hi/lo split -> shared, canonical
+// K-major no-swizzle layout); thread 0 issues the MMAs of a stage and commits them to that stage's
+// mbarrier, so the staging of stage s^1 overlaps the tensor-core work of stage s.
+constexpr int TC_M = 128, TC_N = 64, TC_BK = 32, TC_KC = TC_BK / 4;
+constexpr int TC_LBO_A = (TC_M + 1) * 16, TC_LBO_B = (TC_N + 1) * 16;          // +1 row: conflict-free staging stores
+constexpr int TC_A_BYTES = TC_KC * TC_LBO_A, TC_B_BYTES = TC_KC * TC_LBO_B;
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;                 // hi + lo of both operands
+constexpr int TC_SMEM = 2 * TC_STAGE_BYTES + 64;
+
+// stage one operand tile: rows [r0, r0+ROWS) x k [k0, k0+32) -> hi / lo buffers
+template <int ROWS, int LBO, bool IS_A>
+__device__ __forceinline__ void tc_stage(const GemmP& p, unsigned char* hi, unsigned char* lo, int r0, int k0, int kend) {
+    const float* base = IS_A ? p.A : p.Bm;
+    const long long sr = IS_A ? p.sAi : p.sBj, sk = IS_A ? p.sAk : p.sBk;
+    const int nrows = IS_A ? p.M : p.N;
+    const int pre = IS_A ? p.a_pre : p.b_pre;
+    const float* x2 = IS_A ? p.A2 : nullptr;
+    const float* mask = IS_A ? p.Amask : p.Bmask;
+    const bool kcontig = (sk == 1);
+    for (int c = threadIdx.x; c < ROWS * TC_KC; c += IBINN_THREADS) {
+        int r, k4;
+        if (kcontig) { k4 = c % TC_KC; r = c / TC_KC; } else { r = c % ROWS; k4 = c / ROWS; }
+        const int row = r0 + r, k = k0 + k4 * 4;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (row < nrows) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (k + i < kend) {
+                    const size_t off = (size_t)row * sr + (size_t)(k + i) * sk;
+                    float t = __ldg(base + off);
+                    if (pre == 1) { t = fmaxf(t, 0.f); if (mask) t *= __ldg(mask + off); }
+                    else if (pre == 2) { t = __ldg(x2 + off) > 0.f ? t : 0.f; if (mask) t *= __ldg(mask + off); }
+                    v[i] = t;
+                }
+            }
+        }
+        float h[4], l[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tc::split_tf32(v[i], h[i], l[i]);
+        *reinterpret_cast<float4*>(hi + k4 * LBO + r * 16) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(lo + k4 * LBO + r * 16) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+__global__ void __launch_bounds__(IBINN_THREADS) gemm_tc_kernel(const GemmP p) {
+    extern __shared__ __align__(128) unsigned char tc_smem[];
+    __shared__ __align__(8) uint64_t bar_stage[2];
+    __shared__ __align__(8) uint64_t bar_done;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * TC_M, n0 = blockIdx.x * TC_N;
+    const int kbeg = blockIdx.z * p.kchunk, kend = min(p.K, kbeg + p.kchunk);
+
+    if (tid == 0) {
+        tc::mbar_init(&bar_stage[0], 1);
+        tc::mbar_init(&bar_stage[1], 1);
+        tc::mbar_init(&bar_done, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, TC_N);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_d = tmem_base_s;
+    const uint32_t idesc = tc::idesc_tf32(TC_M, TC_N);
+
+    int it = 0;
+    for (int k0 = kbeg; k0 < kend; k0 += TC_BK, ++it) {
+        const int s = it & 1;
+        unsigned char* st = tc_smem + s * TC_STAGE_BYTES;
+        unsigned char *a_hi = st, *a_lo = st + TC_A_BYTES, *b_hi = st + 2 * TC_A_BYTES, *b_lo = b_hi + TC_B_BYTES;
+        if (it >= 2) tc::mbar_wait(&bar_stage[s], ((it >> 1) - 1) & 1);      // MMAs that read this stage are done
+        tc_stage<TC_M, TC_LBO_A, true>(p, a_hi, a_lo, m0, k0, kend);
+        tc_stage<TC_N, TC_LBO_B, false>(p, b_hi, b_lo, n0, k0, kend);
+        tc::fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const uint32_t ah = tc::smem_u32(a_hi), al = tc::smem_u32(a_lo), bh = tc::smem_u32(b_hi), bl = tc::smem_u32(b_lo);
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {
+                const uint32_t aa = pass == 2 ? al : ah, bb = pass == 1 ? bl : bh;       // lo terms first would be nicer; order is immaterial in fp32 TMEM
+#pragma unroll
+                for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                    const uint64_t da = tc::smem_desc(aa + ks * 2 * TC_LBO_A, TC_LBO_A);
+                    const uint64_t db = tc::smem_desc(bb + ks * 2 * TC_LBO_B, TC_LBO_B);
+                    tc::mma_tf32(tmem_d, da, db, idesc, (it | pass | ks) != 0);
+                }
+            }
+            tc::mma_commit(&bar_stage[s]);
+        }
+    }
+    if (tid == 0) tc::mma_commit(&bar_done);
+    tc::mbar_wait(&bar_done, 0);
+    tc::fence_after_sync();
+
+    if (warp < 4) {
+        const int row = m0 + warp * 32 + lane;
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+        for (int c8 = 0; c8 < TC_N / 8; ++c8) {
+            float v[8];
+            tc::tmem_ld8(taddr + c8 * 8, v);
+            tc::tmem_ld_wait();
+            if (row < p.M) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int j = n0 + c8 * 8 + i;
+                    if (j >= p.N) continue;
+                    float o = v[i];
+                    if (p.bias && blockIdx.z == 0) o += __ldg(p.bias + j);
+                    float* dst = p.C + (size_t)row * p.ldc + j;
+                    if (p.splits > 1) atomicAdd(dst, o);
+                    else if (p.accumulate) *dst += o;
+                    else *dst = o;
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_d, TC_N);
+}
+#endif  // !IBINN_EMU
+
 // out[j] (+)= sum_i pre(A)[i][j]   -- bias gradient
 __global__ void __launch_bounds__(IBINN_THREADS) colsum_kernel(const float* __restrict__ A, const float* __restrict__ A2,
                                                                const float* __restrict__ mask, int a_pre, float* __restrict__ out,
@@ -137,14 +270,19 @@ __global__ void __launch_bounds__(IBINN_THREADS) colsum_kernel(const float* __re
 }
 
 static int gemm_run(GemmP p, cudaStream_t st) {
-    const int gx = (p.N + BN - 1) / BN, gy = (p.M + BM - 1) / BM;
+#ifndef IBINN_EMU
+    const int tile_m = TC_M, tile_n = TC_N, tile_k = TC_BK;
+#else
+    const int tile_m = BM, tile_n = BN, tile_k = BK;
+#endif
+    const int gx = (p.N + tile_n - 1) / tile_n, gy = (p.M + tile_m - 1) / tile_m;
     int splits = 1;
     {
         const int ctas = gx * gy;
-        while (ctas * splits < 148 && splits < 16 && p.K / (splits * 2) >= 4 * BK) splits *= 2;
+        while (ctas * splits < 148 && splits < 16 && p.K / (splits * 2) >= 4 * tile_k) splits *= 2;
     }
     int kchunk = (p.K + splits - 1) / splits;
-    kchunk = (kchunk + BK - 1) / BK * BK;
+    kchunk = (kchunk + tile_k - 1) / tile_k * tile_k;
     splits = (p.K + kchunk - 1) / kchunk;
     p.kchunk = kchunk;
     p.splits = splits;
@@ -154,7 +292,13 @@ static int gemm_run(GemmP p, cudaStream_t st) {
         cudaError_t e = cudaMemsetAsync(p.C, 0, (size_t)p.M * p.N * sizeof(float), st);
         if (e != cudaSuccess) return (int)e;
     }
+#ifndef IBINN_EMU
+    int e = ibinn_set_smem(gemm_tc_kernel, TC_SMEM);
+    if (e) return e;
+    IBINN_LAUNCH(gemm_tc_kernel, dim3(gx, gy, splits), dim3(IBINN_THREADS), TC_SMEM, st, p);
+#else
     IBINN_LAUNCH(gemm_kernel, dim3(gx, gy, splits), dim3(IBINN_THREADS), 0, st, p);
+#endif
     return ibinn_launch_status();
 }
 
