@@ -35,7 +35,7 @@ class ConvArgs(Structure):
                 ('save_mean', c_void_p), ('save_invstd', c_void_p), ('running_mean', c_void_p), ('running_var', c_void_p),
                 ('num_batches_tracked', c_void_p), ('momentum', c_float), ('bn_eps', c_float),
                 ('m_h', c_void_p), ('m_bs', c_int64), ('m_bn', BnRef), ('m_drop', c_void_p), ('sums_out', c_void_p),
-                ('m_dgamma', c_void_p), ('m_dbeta', c_void_p), ('partials', c_void_p), ('counter', c_void_p)]
+                ('m_dgamma', c_void_p), ('m_dbeta', c_void_p), ('partials', c_void_p), ('counter', c_void_p), ('wprep', c_void_p)]
 
 
 class WgradArgs(Structure):
@@ -55,6 +55,7 @@ _SIGNATURES = {
     'ibinn_check_device': ([], c_int),
     'ibinn_sizeof_conv_args': ([], c_size_t),
     'ibinn_conv_partials_floats': ([POINTER(ConvArgs)], c_int64),
+    'ibinn_conv_wprep_floats': ([POINTER(ConvArgs)], c_int64),
     'ibinn_conv_forward': ([POINTER(ConvArgs), P], c_int),
     'ibinn_sizeof_wgrad_args': ([], c_size_t),
     'ibinn_conv_wgrad': ([POINTER(WgradArgs), P], c_int),

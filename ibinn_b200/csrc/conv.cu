@@ -8,6 +8,7 @@
 // The input tile (with halo, pre-op applied, zero padded) and the weight slab of CI_T input
 // channels are staged in shared memory; weights are read as broadcast float4.
 #include "common.cuh"
+#include "conv_internal.cuh"
 
 namespace {
 
@@ -426,9 +427,15 @@ static int conv_launch(const ibinn_conv_args& a, const ConvGeom& g, cudaStream_t
 
 extern "C" size_t ibinn_sizeof_conv_args(void) { return sizeof(ibinn_conv_args); }
 
+extern "C" int64_t ibinn_conv_wprep_floats(const ibinn_conv_args* a) {
+    if (!a) return IBINN_ENULL;
+    return conv_tc_supported(*a) ? conv_tc_wprep_floats(*a) : 0;
+}
+
 extern "C" int64_t ibinn_conv_partials_floats(const ibinn_conv_args* a) {
     if (!a) return IBINN_ENULL;
     if (a->epi != IBINN_EPI_BNSTATS && a->epi != IBINN_EPI_MASKSTATS) return 0;
+    if (conv_tc_supported(*a)) return conv_tc_partials_floats(*a);
     ConvGeom g;
     if (!conv_pick(*a, g)) return IBINN_EINVAL;
     return (int64_t)g.n_ytiles * g.n_cotiles * a->B * 2 * a->Cout;
@@ -441,9 +448,10 @@ extern "C" int ibinn_conv_forward(const ibinn_conv_args* ap, ibinn_stream_t stre
     const ibinn_conv_args& a = *ap;
     e = conv_validate(a);
     if (e) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (conv_tc_supported(a)) return conv_tc_launch(a, st);      // tcgen05 implicit GEMM (stride 1)
     ConvGeom g;
     if (!conv_pick(a, g)) return IBINN_EINVAL;
-    cudaStream_t st = (cudaStream_t)stream;
 #define IBINN_CONV_CASE(KS_, PX_, S_) \
     if (a.ksize == KS_ && g.px == PX_ && a.stride == S_) return conv_launch<KS_, PX_, S_>(a, g, st);
     IBINN_CONV_CASE(3, 4, 1) IBINN_CONV_CASE(3, 2, 1) IBINN_CONV_CASE(3, 1, 1)

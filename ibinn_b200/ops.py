@@ -106,6 +106,10 @@ def conv_forward(x, w, ksize, stride=1, *, cout=None, pre=PRE_NONE, pre_bn=None,
         a.m_dgamma, a.m_dbeta = ptr(mask.get('dgamma')), ptr(mask.get('dbeta'))
     L = _lib.lib()
     keep = None
+    nw = L.ibinn_conv_wprep_floats(ctypes.byref(a))
+    if nw > 0:
+        wprep = torch.empty(int(nw), dtype=torch.float32, device=x.device)
+        a.wprep = ptr(wprep)
     if epi in (EPI_BNSTATS, EPI_MASKSTATS):
         n = L.ibinn_conv_partials_floats(ctypes.byref(a))
         if n < 0:

@@ -100,11 +100,14 @@ typedef struct ibinn_conv_args {
     /* workspaces */
     float* partials;                             /* ibinn_conv_partials_floats() floats (BNSTATS, MASKSTATS) */
     uint32_t* counter;
+    float* wprep;                                /* ibinn_conv_wprep_floats() floats, 16-byte aligned: tensor-core operand image of w */
 } ibinn_conv_args;
 
 size_t ibinn_sizeof_conv_args(void);
 /* number of floats `partials` must hold for this call (0 if the epilogue needs none) */
 int64_t ibinn_conv_partials_floats(const ibinn_conv_args* a);
+/* number of floats `wprep` must hold (0: this call runs on the CUDA-core kernel and needs none) */
+int64_t ibinn_conv_wprep_floats(const ibinn_conv_args* a);
 int ibinn_conv_forward(const ibinn_conv_args* a, ibinn_stream_t stream);
 
 typedef struct ibinn_wgrad_args {

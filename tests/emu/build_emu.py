@@ -6,12 +6,12 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, '..', '..', 'ibinn_b200', 'csrc')
-SOURCES = ['runtime.cu', 'conv.cu', 'wgrad.cu', 'coupling.cu', 'layout.cu', 'linear.cu', 'head.cu', 'optim.cu']
+SOURCES = ['runtime.cu', 'conv.cu', 'conv_tc.cu', 'wgrad.cu', 'coupling.cu', 'layout.cu', 'linear.cu', 'head.cu', 'optim.cu']
 OUT = os.path.join(HERE, 'libibinn_emu.so')
 
 
 def build(force=False):
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, 'common.cuh'), os.path.join(HERE, 'cuda_emu.h'),
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'conv_internal.cuh'), os.path.join(HERE, 'cuda_emu.h'),
                                                         os.path.join(HERE, 'cuda_emu.cpp'),
                                                         os.path.join(CSRC, '..', '..', 'include', 'ibinn_b200.h')]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
