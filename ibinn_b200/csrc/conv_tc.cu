@@ -19,14 +19,16 @@
 #include "tc.cuh"
 
 #ifndef IBINN_EMU
+#define DBG(i)
+
 namespace {
 
 constexpr int TM = 128;
-constexpr int NST = 3;          // weight ring depth
+constexpr int NST = 9;          // weight ring depth (as many taps in flight as shared memory allows)
 constexpr int MAXC_TC = 256;
 
 struct TcGeom {
-    int pad, P, S, Qout, ntiles, npos, halo, cin_p, np, kk, tap_bytes, lbo_a, lbo_b, a_bytes, nst, tmem_cols;
+    int pad, P, S, Qout, ntiles, npos, halo, cin_p, np, kk, tap_bytes, lbo_a, lbo_b, a_bytes, nst, tmem_cols, op_bytes;
     size_t smem_bytes;
 };
 
@@ -47,10 +49,23 @@ static bool tc_geometry(const ibinn_conv_args& a, TcGeom& g) {
     g.lbo_b = g.np * 16;
     g.a_bytes = (g.cin_p / 4) * g.lbo_a;              // one of hi / lo
     g.tap_bytes = 2 * (g.cin_p / 4) * g.lbo_b;        // hi + lo of one tap
-    g.nst = g.kk < NST ? g.kk : NST;
+    {   // ring depth: every tap resident if it fits next to the activation tile, else what ~200 KB allows (>= 2)
+        const long long room = 200 * 1024 - 2LL * g.a_bytes - 8 * 1024;
+        long long n = room / g.tap_bytes;
+        if (n > g.kk) n = g.kk;
+        if (n > NST) n = NST;
+        if (n < 2 && g.kk > 1) n = 2;
+        if (n < 1) n = 1;
+        g.nst = (int)n;
+    }
     g.tmem_cols = g.np <= 32 ? 32 : 64;
-    size_t b = 2 * (size_t)g.a_bytes + (size_t)g.nst * g.tap_bytes + (size_t)g.npos * 4 /*pos table*/ +
-               (3 * MAXC_TC + 4 * 64) * 4 /*coef tables*/ + (2 * 4 * 64 + 16) * 4 /*reduction*/ + 256;
+    size_t operands = 2 * (size_t)g.a_bytes + (size_t)g.nst * g.tap_bytes;
+    const size_t stat_tiles = 2 * 64 * (TM + 4) * 4;             // reuse of the operand area by the statistics epilogue
+    if (operands < stat_tiles) {                                 // grow the weight ring region so the tiles fit
+        operands = stat_tiles;
+    }
+    g.op_bytes = (int)operands;
+    size_t b = operands + (size_t)g.npos * 4 /*pos table*/ + (3 * MAXC_TC + 4 * 64) * 4 /*coef tables*/ + TM * 4 + 256;
     g.smem_bytes = b;
     if (g.lbo_a >= (1 << 18) || b > 220 * 1024) return false;
     return true;
@@ -80,6 +95,7 @@ __device__ __forceinline__ float tc_invstd(const ibinn_bn_ref& r, int c) {
     return r.scale_is_variance ? rsqrtf(s + r.eps) : s;
 }
 
+template <int PRE, int EPI>
 __global__ void __launch_bounds__(IBINN_THREADS, 1) conv_tc_kernel(const ibinn_conv_args p, const TcGeom g) {
     extern __shared__ __align__(128) unsigned char tcs[];
     __shared__ __align__(8) uint64_t bar_full[NST];
@@ -87,12 +103,11 @@ __global__ void __launch_bounds__(IBINN_THREADS, 1) conv_tc_kernel(const ibinn_c
     __shared__ __align__(8) uint64_t bar_done;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_flag;
-    __shared__ float s_cnt[4];
 
     unsigned char* a_hi = tcs;
     unsigned char* a_lo = a_hi + g.a_bytes;
     unsigned char* wst = a_lo + g.a_bytes;                                  // nst stages of tap_bytes
-    int* s_pos = reinterpret_cast<int*>(wst + (size_t)g.nst * g.tap_bytes);   // element offset of (b, c=0, y, x) or -1
+    int* s_pos = reinterpret_cast<int*>(tcs + g.op_bytes);                   // element offset of (b, c=0, y, x) or -1
     float* s_pa = reinterpret_cast<float*>(s_pos + g.npos);
     float* s_pb = s_pa + MAXC_TC;
     float* s_pc = s_pb + MAXC_TC;
@@ -100,12 +115,16 @@ __global__ void __launch_bounds__(IBINN_THREADS, 1) conv_tc_kernel(const ibinn_c
     float* s_eb = s_ea + 64;
     float* s_em = s_eb + 64;
     float* s_ei = s_em + 64;
-    float* s_r1 = s_ei + 64;        // [4][64]
-    float* s_r2 = s_r1 + 4 * 64;    // [4][64]
+    float* s_valid = s_ei + 64;     // [128] 1/0 per output row of the tile
+    // after the MMAs the operand area is free: two [64][TP] transposition tiles for the statistics
+    constexpr int TP = TM + 4;
+    float* s_t1 = reinterpret_cast<float*>(tcs);
+    float* s_t2 = s_t1 + 64 * TP;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * TM;
     const int HsWs = p.Hs * p.Ws;
+    DBG(0);
 
     if (tid == 0) {
         for (int i = 0; i < g.nst; ++i) { tc::mbar_init(&bar_full[i], 1); tc::mbar_init(&bar_empty[i], 1); }
@@ -115,13 +134,13 @@ __global__ void __launch_bounds__(IBINN_THREADS, 1) conv_tc_kernel(const ibinn_c
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, g.tmem_cols);
 
     // ---- coefficient tables (same algebra as conv.cu)
-    if (p.pre == IBINN_PRE_BN_RELU) {
+    if (PRE == IBINN_PRE_BN_RELU) {
         for (int c = tid; c < p.Cin; c += IBINN_THREADS) {
             const float is = tc_invstd(p.pre_bn, c), A = p.pre_bn.gamma[c] * is;
             s_pa[c] = A;
             s_pb[c] = p.pre_bn.beta[c] - p.pre_bn.mean[c] * A;
         }
-    } else if (p.pre == IBINN_PRE_BNBWD) {
+    } else if (PRE == IBINN_PRE_BNBWD) {
         for (int c = tid; c < p.Cin; c += IBINN_THREADS) {
             const float is = tc_invstd(p.pre_bn, c), k = p.pre_bn.gamma[c] * is;
             const float m1 = p.pre_sums[c] * p.pre_inv_count, m2 = p.pre_sums[p.Cin + c] * p.pre_inv_count;
@@ -130,7 +149,7 @@ __global__ void __launch_bounds__(IBINN_THREADS, 1) conv_tc_kernel(const ibinn_c
             s_pc[c] = -k * m1 + k * m2 * is * p.pre_bn.mean[c];
         }
     }
-    if (p.epi == IBINN_EPI_MASKSTATS) {
+    if (EPI == IBINN_EPI_MASKSTATS) {
         for (int c = tid; c < 64; c += IBINN_THREADS) {
             float A = 0.f, Bc = 0.f, mean = 0.f, is = 0.f;
             if (c < p.Cout) {
@@ -161,53 +180,86 @@ __global__ void __launch_bounds__(IBINN_THREADS, 1) conv_tc_kernel(const ibinn_c
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_d = tmem_base_s;
+    DBG(1);
 
     // ---- weight producer starts streaming right away (overlaps the activation staging)
+    const bool resident = (g.nst == g.kk);          // every tap fits: one barrier, no ring traffic
     if (warp == 1 && lane == 0) {
-        for (int t = 0; t < g.nst; ++t) {
-            tc::mbar_arrive_expect_tx(&bar_full[t], g.tap_bytes);
-            tc::bulk_g2s(wst + (size_t)t * g.tap_bytes, reinterpret_cast<const unsigned char*>(p.wprep) + (size_t)t * g.tap_bytes, g.tap_bytes,
-                         &bar_full[t]);
+        if (resident) {
+            tc::mbar_arrive_expect_tx(&bar_full[0], (uint32_t)g.kk * g.tap_bytes);
+            for (int t = 0; t < g.kk; ++t)
+                tc::bulk_g2s(wst + (size_t)t * g.tap_bytes, reinterpret_cast<const unsigned char*>(p.wprep) + (size_t)t * g.tap_bytes,
+                             g.tap_bytes, &bar_full[0]);
+        } else {
+            for (int t = 0; t < g.nst; ++t) {
+                tc::mbar_arrive_expect_tx(&bar_full[t], g.tap_bytes);
+                tc::bulk_g2s(wst + (size_t)t * g.tap_bytes, reinterpret_cast<const unsigned char*>(p.wprep) + (size_t)t * g.tap_bytes,
+                             g.tap_bytes, &bar_full[t]);
+            }
         }
     }
 
-    // ---- stage the activation window: 16-byte chunk = 4 channels of one position
+    // ---- stage the activation window: 16-byte chunk = 4 channels of one position.  Tasks are taken
+    // four at a time with all global loads issued before the first use (the shared-memory stores would
+    // otherwise serialise the loads behind them).
     {
         const int nk4 = g.cin_p / 4;
+        const int ntask = g.npos * nk4;
         const int b_x2 = (int)p.x2_bs, b_x = (int)p.x_bs;
-        for (int c = tid; c < g.npos * nk4; c += IBINN_THREADS) {
-            const int i = c % g.npos, k4 = c / g.npos;
-            const int off = s_pos[i];
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            if (off >= 0) {
+        constexpr int U = 4;
+        int i_u = tid, k_u = 0;                      // task (position, chunk) of this thread, advanced by 256 each time
+        while (i_u >= g.npos) { i_u -= g.npos; ++k_u; }
+        for (int c0 = tid; c0 < ntask; c0 += IBINN_THREADS * U) {
+            float v[U][4], w2[U][4];
+            int ti[U], tk[U], toff[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                ti[u] = i_u; tk[u] = k_u;
+                const bool live = (c0 + u * IBINN_THREADS) < ntask;
+                toff[u] = live ? s_pos[i_u] : -2;
+                i_u += IBINN_THREADS;
+                while (i_u >= g.npos) { i_u -= g.npos; ++k_u; }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int ch = k4 * 4 + j;
-                    if (ch < p.Cin) {
-                        const size_t o = (size_t)off + (size_t)ch * HsWs;
-                        float t = __ldg(p.x + o);
-                        if (p.pre == IBINN_PRE_RELU) t = fmaxf(t, 0.f);
-                        else if (p.pre == IBINN_PRE_BN_RELU) {
-                            t = fmaxf(fmaf(t, s_pa[ch], s_pb[ch]), 0.f);
-                            if (p.pre_mask) t *= __ldg(p.pre_mask + (size_t)(off / b_x) * p.Cin + ch);
-                        } else if (p.pre == IBINN_PRE_BNBWD) {
-                            // same (b, y, x) in x2, whose batch stride may differ
-                            const int bb = off / b_x, in_img = off - bb * b_x;
-                            t = fmaf(s_pa[ch], t, fmaf(s_pb[ch], __ldg(p.x2 + (size_t)bb * b_x2 + in_img + (size_t)ch * HsWs), s_pc[ch]));
+                    const int ch = tk[u] * 4 + j;
+                    v[u][j] = 0.f; w2[u][j] = 0.f;
+                    if (toff[u] >= 0 && ch < p.Cin) {
+                        const size_t o = (size_t)toff[u] + (size_t)ch * HsWs;
+                        v[u][j] = __ldg(p.x + o);
+                        if (PRE == IBINN_PRE_BNBWD) {
+                            const int bb = toff[u] / b_x, in_img = toff[u] - bb * b_x;     // same (b, y, x) in x2, own batch stride
+                            w2[u][j] = __ldg(p.x2 + (size_t)bb * b_x2 + in_img + (size_t)ch * HsWs);
+                        } else if (PRE == IBINN_PRE_BN_RELU) {
+                            if (p.pre_mask) w2[u][j] = __ldg(p.pre_mask + (size_t)(toff[u] / b_x) * p.Cin + ch);
                         }
-                        v[j] = t;
                     }
                 }
             }
-            float h[4], l[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) tc::split_tf32(v[j], h[j], l[j]);
-            *reinterpret_cast<float4*>(a_hi + (size_t)k4 * g.lbo_a + i * 16) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4*>(a_lo + (size_t)k4 * g.lbo_a + i * 16) = make_float4(l[0], l[1], l[2], l[3]);
+            for (int u = 0; u < U; ++u) {
+                if (toff[u] == -2) continue;
+                float h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ch = tk[u] * 4 + j;
+                    float t = v[u][j];
+                    if (toff[u] >= 0 && ch < p.Cin) {
+                        if (PRE == IBINN_PRE_RELU) t = fmaxf(t, 0.f);
+                        else if (PRE == IBINN_PRE_BN_RELU) {
+                            t = fmaxf(fmaf(t, s_pa[ch], s_pb[ch]), 0.f);
+                            if (p.pre_mask) t *= w2[u][j];
+                        } else if (PRE == IBINN_PRE_BNBWD) t = fmaf(s_pa[ch], t, fmaf(s_pb[ch], w2[u][j], s_pc[ch]));
+                    }
+                    tc::split_tf32(t, h[j], l[j]);
+                }
+                *reinterpret_cast<float4*>(a_hi + (size_t)tk[u] * g.lbo_a + ti[u] * 16) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(a_lo + (size_t)tk[u] * g.lbo_a + ti[u] * 16) = make_float4(l[0], l[1], l[2], l[3]);
+            }
         }
     }
     tc::fence_async_smem();
     __syncthreads();
+    DBG(2);
 
     // ---- main loop over the filter taps
     if (warp == 1 && lane == 0) {
@@ -221,37 +273,50 @@ __global__ void __launch_bounds__(IBINN_THREADS, 1) conv_tc_kernel(const ibinn_c
     } else if (warp == 0 && lane == 0) {
         tc::fence_after_sync();
         const uint32_t idesc = tc::idesc_tf32(TM, g.np);
-        const uint32_t ah = tc::smem_u32(a_hi), al = tc::smem_u32(a_lo);
+        // descriptors differ only in the 14-bit start-address field: build once, then add (bytes >> 4)
+        const uint64_t da_hi = tc::smem_desc(tc::smem_u32(a_hi), g.lbo_a), da_lo = tc::smem_desc(tc::smem_u32(a_lo), g.lbo_a);
+        const uint64_t db0 = tc::smem_desc(tc::smem_u32(wst), g.lbo_b);
         const int nks = g.cin_p / 8;
-        const uint32_t b_lo_off = (uint32_t)(g.cin_p / 4) * g.lbo_b;
+        const uint32_t b_lo_off = ((uint32_t)(g.cin_p / 4) * g.lbo_b) >> 4;
+        const uint32_t a_step = (uint32_t)(2 * g.lbo_a) >> 4, b_step = (uint32_t)(2 * g.lbo_b) >> 4, st_step = (uint32_t)g.tap_bytes >> 4;
+        bool acc = false;
         for (int t = 0; t < g.kk; ++t) {
             const int s = t % g.nst;
-            tc::mbar_wait(&bar_full[s], (t / g.nst) & 1);
-            tc::fence_after_sync();
+            if (!resident || t == 0) {
+                tc::mbar_wait(&bar_full[s], (t / g.nst) & 1);
+                tc::fence_after_sync();
+            }
             const int dy = g.pad ? t / 3 - 1 : 0, dx = g.pad ? t % 3 - 1 : 0;
-            const uint32_t row_off = (uint32_t)(g.halo + dy * g.P + dx) * 16;
-            const uint32_t bh = tc::smem_u32(wst + (size_t)s * g.tap_bytes), bl = bh + b_lo_off;
+            const uint32_t row_off = (uint32_t)(g.halo + dy * g.P + dx);          // 16-byte rows
+            const uint64_t bh = db0 + (uint64_t)(s * st_step), bl = bh + b_lo_off;
+#pragma unroll 1
             for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t aa = (pass == 2 ? al : ah) + row_off, bb = pass == 1 ? bl : bh;
+                uint64_t da = (pass == 2 ? da_lo : da_hi) + row_off;
+                uint64_t db = pass == 1 ? bl : bh;
+#pragma unroll 2
                 for (int ks = 0; ks < nks; ++ks) {
-                    const uint64_t da = tc::smem_desc(aa + ks * 2 * g.lbo_a, g.lbo_a);
-                    const uint64_t db = tc::smem_desc(bb + ks * 2 * g.lbo_b, g.lbo_b);
-                    tc::mma_tf32(tmem_d, da, db, idesc, (t | pass | ks) != 0);
+                    tc::mma_tf32(tmem_d, da, db, idesc, acc);
+                    acc = true;
+                    da += a_step;
+                    db += b_step;
                 }
             }
-            tc::mma_commit(&bar_empty[s]);
+            if (!resident) tc::mma_commit(&bar_empty[s]);
         }
         tc::mma_commit(&bar_done);
+        DBG(3);
     }
     __syncwarp();
     tc::mbar_wait(&bar_done, 0);
     tc::fence_after_sync();
+    DBG(4);
 
     // ---- epilogue: thread <-> output position q0 + 32*(warp%4) + lane, columns split between warp and warp+4
     const int wq = warp & 3, half = warp >> 2;
     const int ncol = g.np / 2;                       // 8, 16, 24 or 32 columns per thread
     const int col0 = half * ncol;
-    const int q = q0 + wq * 32 + lane;
+    const int row = wq * 32 + lane;
+    const int q = q0 + row;
     bool valid = false;
     size_t obase = 0, mbase = 0, abase = 0;
     int bimg = 0;
@@ -269,85 +334,78 @@ __global__ void __launch_bounds__(IBINN_THREADS, 1) conv_tc_kernel(const ibinn_c
     }
     const size_t HWo = (size_t)p.Hout * p.Wout;
     const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + col0;
-    const bool stats = (p.epi == IBINN_EPI_BNSTATS || p.epi == IBINN_EPI_MASKSTATS);
+    constexpr bool STATS = (EPI == IBINN_EPI_BNSTATS || EPI == IBINN_EPI_MASKSTATS);
+    if (STATS && half == 0) s_valid[row] = valid ? 1.f : 0.f;
 
-    float vals[32];
+#pragma unroll 1
+    for (int c8 = 0; c8 < ncol; c8 += 8) {
+        float v[8];
+        tc::tmem_ld8(taddr + c8, v);
+        tc::tmem_ld_wait();
 #pragma unroll
-    for (int c8 = 0; c8 < 4; ++c8) {
-        if (c8 * 8 < ncol) {
-            float v[8];
-            tc::tmem_ld8(taddr + c8 * 8, v);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 8; ++i) vals[c8 * 8 + i] = v[i];
-        }
-    }
-    // element-wise part + store
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        if (j >= ncol) continue;
-        const int c = col0 + j;
-        float v = vals[j], xh = 0.f;
-        if (valid && c < p.Cout) {
-            if (p.bias) v += __ldg(p.bias + c);
-            if (p.epi == IBINN_EPI_MASKSTATS) {
-                const float h = __ldg(p.m_h + mbase + (size_t)c * HWo);
-                v = fmaf(h, s_ea[c], s_eb[c]) > 0.f ? v : 0.f;
-                if (p.m_drop) v *= __ldg(p.m_drop + (size_t)bimg * p.Cout + c);
-                xh = (h - s_em[c]) * s_ei[c];
-            } else if (p.epi == IBINN_EPI_RELUMASK) {
-                v = __ldg(p.m_h + mbase + (size_t)c * HWo) > 0.f ? v : 0.f;
+        for (int i = 0; i < 8; ++i) {
+            const int c = col0 + c8 + i;
+            float o = 0.f, xh = 0.f;
+            if (valid && c < p.Cout) {
+                o = v[i];
+                if (EPI == IBINN_EPI_STORE || EPI == IBINN_EPI_RELUMASK) { if (p.bias) o += __ldg(p.bias + c); }
+                if (EPI == IBINN_EPI_MASKSTATS) {
+                    const float h = __ldg(p.m_h + mbase + (size_t)c * HWo);
+                    o = fmaf(h, s_ea[c], s_eb[c]) > 0.f ? o : 0.f;
+                    if (p.m_drop) o *= __ldg(p.m_drop + (size_t)bimg * p.Cout + c);
+                    xh = (h - s_em[c]) * s_ei[c];
+                } else if (EPI == IBINN_EPI_RELUMASK) {
+                    o = __ldg(p.m_h + mbase + (size_t)c * HWo) > 0.f ? o : 0.f;
+                }
+                float st = o;
+                if (EPI == IBINN_EPI_STORE || EPI == IBINN_EPI_RELUMASK) { if (p.addend) st += p.addend[abase + (size_t)c * HWo]; }
+                p.y[obase + (size_t)c * HWo] = st;
             }
-            float o = v;
-            if (p.addend) o += p.addend[abase + (size_t)c * HWo];
-            p.y[obase + (size_t)c * HWo] = o;
-        } else v = 0.f;
-        vals[j] = v;
-        if (p.epi == IBINN_EPI_MASKSTATS) {
-            // per-channel sums of v and v*xhat over the tile
-            const float a1 = warp_sum(v), a2 = warp_sum(v * xh);
-            if (lane == 0) { s_r1[wq * 64 + c] = a1; s_r2[wq * 64 + c] = a2; }
-        } else if (p.epi == IBINN_EPI_BNSTATS) {
-            const float a1 = warp_sum(v);
-            if (lane == 0) s_r1[wq * 64 + c] = a1;
+            if (STATS) {
+                s_t1[c * TP + row] = o;
+                if (EPI == IBINN_EPI_MASKSTATS) s_t2[c * TP + row] = o * xh;
+            }
         }
     }
-    if (stats) {
-        const float cw = warp_sum(valid ? 1.f : 0.f);
-        if (half == 0 && lane == 0) s_cnt[wq] = cw;
+    DBG(8);
+    if (STATS) {
         __syncthreads();
-        const float n_tile = s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3];
-        float* rec = p.partials + (size_t)blockIdx.x * (2 * p.Cout + 4);
-        if (p.epi == IBINN_EPI_BNSTATS) {
-            // second pass: centred sum of squares around the tile mean
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if (j >= ncol) continue;
-                const int c = col0 + j;
-                const float mean = n_tile > 0.f ? (s_r1[c] + s_r1[64 + c] + s_r1[128 + c] + s_r1[192 + c]) / n_tile : 0.f;
-                const float d = (valid && c < p.Cout) ? vals[j] - mean : 0.f;
-                const float a2 = warp_sum(d * d);
-                if (lane == 0) s_r2[wq * 64 + c] = a2;
-            }
-            __syncthreads();
-            if (tid < p.Cout) {
-                const float s = s_r1[tid] + s_r1[64 + tid] + s_r1[128 + tid] + s_r1[192 + tid];
-                rec[tid] = n_tile > 0.f ? s / n_tile : 0.f;
-                rec[p.Cout + tid] = s_r2[tid] + s_r2[64 + tid] + s_r2[128 + tid] + s_r2[192 + tid];
-            }
-        } else {
-            if (tid < p.Cout) {
-                rec[tid] = s_r1[tid] + s_r1[64 + tid] + s_r1[128 + tid] + s_r1[192 + tid];
-                rec[p.Cout + tid] = s_r2[tid] + s_r2[64 + tid] + s_r2[128 + tid] + s_r2[192 + tid];
-            }
+        // thread (c = tid/4, part = tid%4) reduces 32 rows of channel c; the 4 parts meet by shuffle
+        const int c = tid >> 2, part = tid & 3;
+        float a1 = 0.f, a2 = 0.f, cnt = 0.f;
+        const float* t1 = s_t1 + c * TP + part * 32;
+        const float* t2 = s_t2 + c * TP + part * 32;
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+            a1 += t1[r];
+            cnt += s_valid[part * 32 + r];
+            if (EPI == IBINN_EPI_MASKSTATS) a2 += t2[r];
         }
-        if (tid == 0) rec[2 * p.Cout] = n_tile;
+        a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, 1); cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+        float* rec = p.partials + (size_t)blockIdx.x * (2 * p.Cout + 4);
+        if (EPI == IBINN_EPI_BNSTATS) {
+            const float mean = cnt > 0.f ? a1 / cnt : 0.f;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+                const float d = t1[r] - mean;
+                a2 = fmaf(s_valid[part * 32 + r] * d, d, a2);
+            }
+            a2 += __shfl_xor_sync(0xffffffffu, a2, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
+            if (part == 0 && c < p.Cout) { rec[c] = mean; rec[p.Cout + c] = a2; }
+        } else {
+            a2 += __shfl_xor_sync(0xffffffffu, a2, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
+            if (part == 0 && c < p.Cout) { rec[c] = a1; rec[p.Cout + c] = a2; }
+        }
+        if (tid == 0) rec[2 * p.Cout] = cnt;
     }
 
+    DBG(5);
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem_d, g.tmem_cols);
-    if (!stats) return;
+    DBG(6);
+    if (!STATS) return;
 
     // ---- last CTA: combine the per-tile records in tile order (deterministic), like conv.cu
     const unsigned nblk = gridDim.x;
@@ -358,7 +416,7 @@ __global__ void __launch_bounds__(IBINN_THREADS, 1) conv_tc_kernel(const ibinn_c
     const int c = tid / tpc, j = tid % tpc;
     const bool cval = (c < p.Cout) && (tid < cpad * tpc);
     const size_t rs = 2 * p.Cout + 4;
-    if (p.epi == IBINN_EPI_BNSTATS) {
+    if (EPI == IBINN_EPI_BNSTATS) {
         double n = 0., mean = 0., m2 = 0.;
         if (cval) {
             for (unsigned bb = j; bb < nblk; bb += tpc) {
@@ -421,6 +479,15 @@ __global__ void __launch_bounds__(IBINN_THREADS, 1) conv_tc_kernel(const ibinn_c
     if (tid == 0) *p.counter = 0u;
 }
 
+template <int PRE, int EPI>
+static int tc_launch_inst(const ibinn_conv_args& a, const TcGeom& g, cudaStream_t st) {
+    auto kfn = conv_tc_kernel<PRE, EPI>;
+    int e = ibinn_set_smem(kfn, g.smem_bytes);
+    if (e) return e;
+    IBINN_LAUNCH(kfn, dim3(g.ntiles), dim3(IBINN_THREADS), g.smem_bytes, st, a, g);
+    return ibinn_launch_status();
+}
+
 }  // namespace
 
 bool conv_tc_supported(const ibinn_conv_args& a) {
@@ -454,10 +521,13 @@ int conv_tc_launch(const ibinn_conv_args& a, cudaStream_t st) {
     IBINN_LAUNCH(wprep_kernel, dim3(nb), dim3(IBINN_THREADS), 0, st, a.w, a.wprep, a.Cin, a.Cout, g.cin_p, g.np, g.kk, a.w_transposed);
     int e = ibinn_launch_status();
     if (e) return e;
-    e = ibinn_set_smem(conv_tc_kernel, g.smem_bytes);
-    if (e) return e;
-    IBINN_LAUNCH(conv_tc_kernel, dim3(g.ntiles), dim3(IBINN_THREADS), g.smem_bytes, st, a, g);
-    return ibinn_launch_status();
+#define TC_CASE(PRE_, EPI_) if (a.pre == PRE_ && a.epi == EPI_) return tc_launch_inst<PRE_, EPI_>(a, g, st);
+    TC_CASE(0, 0) TC_CASE(0, 1) TC_CASE(0, 2) TC_CASE(0, 3)
+    TC_CASE(1, 0) TC_CASE(1, 1) TC_CASE(1, 2) TC_CASE(1, 3)
+    TC_CASE(2, 0) TC_CASE(2, 1) TC_CASE(2, 2) TC_CASE(2, 3)
+    TC_CASE(3, 0) TC_CASE(3, 1) TC_CASE(3, 2) TC_CASE(3, 3)
+#undef TC_CASE
+    return IBINN_EINVAL;
 }
 
 #else  // IBINN_EMU: the simulator build has no tensor cores; conv.cu keeps everything on its CUDA-core kernel
