@@ -19,16 +19,26 @@
 #include "tc.cuh"
 
 #ifndef IBINN_EMU
+#ifdef IBINN_DBG
+__device__ unsigned long long ibinn_dbg[64];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define DBG(i) do { if (blockIdx.x == 0) { ibinn_dbg[i] = gtime(); if ((i) == 10 || (i) == 11) ibinn_dbg[(i) + 40] = clock64(); } } while (0)
+extern "C" int ibinn_debug_read(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, ibinn_dbg, sizeof(unsigned long long) * 64); }
+#else
 #define DBG(i)
-
+#endif
 namespace {
 
 constexpr int TM = 128;
-constexpr int NST = 9;          // weight ring depth (as many taps in flight as shared memory allows)
 constexpr int MAXC_TC = 256;
+constexpr int TP = TM + 4;                  // row pitch of the statistics transposition tiles
+constexpr int NTHREADS_TC = 320;            // warps 0-3 epilogue, 4-7 loaders, 8 MMA issuer, 9 weight producer
+constexpr int MAX_RING = 9;
 
 struct TcGeom {
-    int pad, P, S, Qout, ntiles, npos, halo, cin_p, np, kk, tap_bytes, lbo_a, lbo_b, a_bytes, nst, tmem_cols, op_bytes;
+    int pad, P, S, Qout, ntiles, npos, halo, cin_p, np, kk, tap_bytes, lbo_a, lbo_b, a_bytes;
+    int nbuf, nst, resident, alias_stats, nstat, tmem_cols, grid;
+    int off_w, off_stat, off_tab;           // byte offsets inside dynamic shared memory
     size_t smem_bytes;
 };
 
@@ -49,25 +59,46 @@ static bool tc_geometry(const ibinn_conv_args& a, TcGeom& g) {
     g.lbo_b = g.np * 16;
     g.a_bytes = (g.cin_p / 4) * g.lbo_a;              // one of hi / lo
     g.tap_bytes = 2 * (g.cin_p / 4) * g.lbo_b;        // hi + lo of one tap
-    {   // ring depth: every tap resident if it fits next to the activation tile, else what ~200 KB allows (>= 2)
-        const long long room = 200 * 1024 - 2LL * g.a_bytes - 8 * 1024;
-        long long n = room / g.tap_bytes;
-        if (n > g.kk) n = g.kk;
-        if (n > NST) n = NST;
-        if (n < 2 && g.kk > 1) n = 2;
-        if (n < 1) n = 1;
-        g.nst = (int)n;
+    if (g.lbo_a >= (1 << 18)) return false;
+    g.nstat = a.epi == IBINN_EPI_BNSTATS ? 1 : a.epi == IBINN_EPI_MASKSTATS ? 2 : 0;
+    const int stat_bytes = g.nstat * g.np * TP * 4;
+    const int tab_bytes = (3 * MAXC_TC + 4 * 64 + TM) * 4 + 256;
+    const int budget = 200 * 1024;
+    // candidates, best first: double-buffered activations + resident filters ... single buffer + filter ring
+    bool ok = false;
+    for (int cand = 0; cand < 4 && !ok; ++cand) {
+        g.nbuf = cand == 0 ? 2 : 1;
+        g.resident = cand <= 2;
+        g.alias_stats = cand >= 2;
+        int nst = g.kk;
+        if (!g.resident) {
+            const long long room = (long long)budget - 2LL * g.a_bytes - tab_bytes;
+            nst = (int)(room / g.tap_bytes);
+            if (nst > MAX_RING) nst = MAX_RING;
+            if (nst >= g.kk) nst = g.kk;
+            if (nst < 2) continue;
+        }
+        g.nst = nst;
+        long long op = (long long)g.nbuf * 2 * g.a_bytes + (long long)g.nst * g.tap_bytes;
+        if (g.alias_stats && stat_bytes > g.nbuf * 2 * g.a_bytes) continue;     // borrowed tiles must stay inside the activation buffers
+        const long long tot = op + (g.alias_stats ? 0 : stat_bytes) + tab_bytes;
+        if (tot <= budget) {
+            ok = true;
+            g.off_w = g.nbuf * 2 * g.a_bytes;
+            g.off_stat = g.alias_stats ? 0 : (int)op;
+            g.off_tab = (int)(op + (g.alias_stats ? 0 : stat_bytes));
+            g.off_tab = (g.off_tab + 15) & ~15;
+            g.smem_bytes = (size_t)g.off_tab + tab_bytes;
+        }
     }
-    g.tmem_cols = g.np <= 32 ? 32 : 64;
-    size_t operands = 2 * (size_t)g.a_bytes + (size_t)g.nst * g.tap_bytes;
-    const size_t stat_tiles = 2 * 64 * (TM + 4) * 4;             // reuse of the operand area by the statistics epilogue
-    if (operands < stat_tiles) {                                 // grow the weight ring region so the tiles fit
-        operands = stat_tiles;
-    }
-    g.op_bytes = (int)operands;
-    size_t b = operands + (size_t)g.npos * 4 /*pos table*/ + (3 * MAXC_TC + 4 * 64) * 4 /*coef tables*/ + TM * 4 + 256;
-    g.smem_bytes = b;
-    if (g.lbo_a >= (1 << 18) || b > 220 * 1024) return false;
+    if (!ok) return false;
+    const int cols = g.nbuf * g.np;
+    g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : 128;
+    int per_sm = (int)((220 * 1024) / (g.smem_bytes + 2048));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 512 / g.tmem_cols) per_sm = 512 / g.tmem_cols;
+    if (per_sm > 4) per_sm = 4;
+    g.grid = g.ntiles < 148 * per_sm ? g.ntiles : 148 * per_sm;
     return true;
 }
 
@@ -95,53 +126,117 @@ __device__ __forceinline__ float tc_invstd(const ibinn_bn_ref& r, int c) {
     return r.scale_is_variance ? rsqrtf(s + r.eps) : s;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// Stage the activation window of one tile: global NCHW -> pre-op -> hi/lo split -> K-major rows of 16 bytes.
+// Work item = (position, group of 4 channel-chunks); `lt` of `nlt` cooperating threads.
+template <int PRE>
+__device__ __forceinline__ void tc_stage_tile(const ibinn_conv_args& p, const TcGeom& g, int q0, unsigned char* a_hi, unsigned char* a_lo,
+                                              const float* s_pa, const float* s_pb, const float* s_pc, int lt, int nlt) {
+    const int nk4 = g.cin_p / 4, ngrp = (nk4 + 3) / 4;
+    const int ntask = g.npos * ngrp;
+    const int b_x2 = (int)p.x2_bs, b_x = (int)p.x_bs;
+    const int HsWs = p.Hs * p.Ws;
+    int i = lt, grp = 0;
+    while (i >= g.npos) { i -= g.npos; ++grp; }
+    for (int t = lt; t < ntask; t += nlt) {
+        const int q = q0 - g.halo + i;
+        int off = -1, bb = 0, in_img = 0;
+        if (q >= 0 && q < g.Qout) {
+            const int b = q / g.S, rem = q - b * g.S;
+            const int yy = rem / g.P - g.pad, xx = rem % g.P;
+            if (yy >= 0 && yy < p.Hin && xx < p.Win) {
+                bb = b;
+                if (p.upsample2) {
+                    if (!((yy | xx) & 1) && (yy >> 1) < p.Hs && (xx >> 1) < p.Ws) { in_img = (yy >> 1) * p.Ws + (xx >> 1); off = b * b_x + in_img; }
+                } else { in_img = yy * p.Ws + xx; off = b * b_x + in_img; }
+            }
+        }
+        const int k0 = grp * 4;
+        float v[4][4], w2[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int ch = (k0 + u) * 4 + jj;
+                v[u][jj] = 0.f; w2[u][jj] = 0.f;
+                if (off >= 0 && ch < p.Cin) {
+                    v[u][jj] = __ldg(p.x + (size_t)off + (size_t)ch * HsWs);
+                    if (PRE == IBINN_PRE_BNBWD) w2[u][jj] = __ldg(p.x2 + (size_t)bb * b_x2 + in_img + (size_t)ch * HsWs);
+                    else if (PRE == IBINN_PRE_BN_RELU) { if (p.pre_mask) w2[u][jj] = __ldg(p.pre_mask + (size_t)bb * p.Cin + ch); }
+                }
+            }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (k0 + u >= nk4) continue;
+            float h[4], l[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int ch = (k0 + u) * 4 + jj;
+                float tv = v[u][jj];
+                if (off >= 0 && ch < p.Cin) {
+                    if (PRE == IBINN_PRE_RELU) tv = fmaxf(tv, 0.f);
+                    else if (PRE == IBINN_PRE_BN_RELU) {
+                        tv = fmaxf(fmaf(tv, s_pa[ch], s_pb[ch]), 0.f);
+                        if (p.pre_mask) tv *= w2[u][jj];
+                    } else if (PRE == IBINN_PRE_BNBWD) tv = fmaf(s_pa[ch], tv, fmaf(s_pb[ch], w2[u][jj], s_pc[ch]));
+                }
+                tc::split_tf32(tv, h[jj], l[jj]);
+            }
+            *reinterpret_cast<float4*>(a_hi + (size_t)(k0 + u) * g.lbo_a + i * 16) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(a_lo + (size_t)(k0 + u) * g.lbo_a + i * 16) = make_float4(l[0], l[1], l[2], l[3]);
+        }
+        i += nlt;
+        while (i >= g.npos) { i -= g.npos; ++grp; }
+    }
+}
+
+// Persistent, warp-specialised implicit-GEMM convolution.  Each CTA walks tiles blockIdx.x, +gridDim.x, ...
 template <int PRE, int EPI>
-__global__ void __launch_bounds__(IBINN_THREADS, 1) conv_tc_kernel(const ibinn_conv_args p, const TcGeom g) {
+__global__ void __launch_bounds__(NTHREADS_TC, 1) conv_tc_kernel(const ibinn_conv_args p, const TcGeom g) {
     extern __shared__ __align__(128) unsigned char tcs[];
-    __shared__ __align__(8) uint64_t bar_full[NST];
-    __shared__ __align__(8) uint64_t bar_empty[NST];
-    __shared__ __align__(8) uint64_t bar_done;
+    __shared__ __align__(8) uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], w_full[MAX_RING], w_empty[MAX_RING], a_help;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_flag;
+    constexpr bool STATS = (EPI == IBINN_EPI_BNSTATS || EPI == IBINN_EPI_MASKSTATS);
 
-    unsigned char* a_hi = tcs;
-    unsigned char* a_lo = a_hi + g.a_bytes;
-    unsigned char* wst = a_lo + g.a_bytes;                                  // nst stages of tap_bytes
-    int* s_pos = reinterpret_cast<int*>(tcs + g.op_bytes);                   // element offset of (b, c=0, y, x) or -1
-    float* s_pa = reinterpret_cast<float*>(s_pos + g.npos);
+    unsigned char* wst = tcs + g.off_w;
+    float* s_t1 = reinterpret_cast<float*>(tcs + g.off_stat);
+    float* s_t2 = s_t1 + g.np * TP;
+    float* s_pa = reinterpret_cast<float*>(tcs + g.off_tab);
     float* s_pb = s_pa + MAXC_TC;
     float* s_pc = s_pb + MAXC_TC;
     float* s_ea = s_pc + MAXC_TC;
     float* s_eb = s_ea + 64;
     float* s_em = s_eb + 64;
     float* s_ei = s_em + 64;
-    float* s_valid = s_ei + 64;     // [128] 1/0 per output row of the tile
-    // after the MMAs the operand area is free: two [64][TP] transposition tiles for the statistics
-    constexpr int TP = TM + 4;
-    float* s_t1 = reinterpret_cast<float*>(tcs);
-    float* s_t2 = s_t1 + 64 * TP;
+    float* s_valid = s_ei + 64;     // [128]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q0 = blockIdx.x * TM;
     const int HsWs = p.Hs * p.Ws;
-    DBG(0);
+    if (tid == 0) DBG(0);
 
     if (tid == 0) {
-        for (int i = 0; i < g.nst; ++i) { tc::mbar_init(&bar_full[i], 1); tc::mbar_init(&bar_empty[i], 1); }
-        tc::mbar_init(&bar_done, 1);
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1);
+            tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 128);
+        }
+        for (int i = 0; i < MAX_RING; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
+        tc::mbar_init(&a_help, 128);
         tc::mbar_fence_init();
     }
-    if (warp == 0) tc::tmem_alloc(&tmem_base_s, g.tmem_cols);
-
-    // ---- coefficient tables (same algebra as conv.cu)
+    if (warp == 8) tc::tmem_alloc(&tmem_base_s, g.tmem_cols);
     if (PRE == IBINN_PRE_BN_RELU) {
-        for (int c = tid; c < p.Cin; c += IBINN_THREADS) {
+        for (int c = tid; c < p.Cin; c += NTHREADS_TC) {
             const float is = tc_invstd(p.pre_bn, c), A = p.pre_bn.gamma[c] * is;
             s_pa[c] = A;
             s_pb[c] = p.pre_bn.beta[c] - p.pre_bn.mean[c] * A;
         }
     } else if (PRE == IBINN_PRE_BNBWD) {
-        for (int c = tid; c < p.Cin; c += IBINN_THREADS) {
+        for (int c = tid; c < p.Cin; c += NTHREADS_TC) {
             const float is = tc_invstd(p.pre_bn, c), k = p.pre_bn.gamma[c] * is;
             const float m1 = p.pre_sums[c] * p.pre_inv_count, m2 = p.pre_sums[p.Cin + c] * p.pre_inv_count;
             s_pa[c] = k;
@@ -150,7 +245,7 @@ __global__ void __launch_bounds__(IBINN_THREADS, 1) conv_tc_kernel(const ibinn_c
         }
     }
     if (EPI == IBINN_EPI_MASKSTATS) {
-        for (int c = tid; c < 64; c += IBINN_THREADS) {
+        for (int c = tid; c < 64; c += NTHREADS_TC) {
             float A = 0.f, Bc = 0.f, mean = 0.f, is = 0.f;
             if (c < p.Cout) {
                 is = tc_invstd(p.m_bn, c);
@@ -161,260 +256,235 @@ __global__ void __launch_bounds__(IBINN_THREADS, 1) conv_tc_kernel(const ibinn_c
             s_ea[c] = A; s_eb[c] = Bc; s_em[c] = mean; s_ei[c] = is;
         }
     }
-    // ---- position table of the staged window
-    for (int i = tid; i < g.npos; i += IBINN_THREADS) {
-        const int q = q0 - g.halo + i;
-        int off = -1;
-        if (q >= 0 && q < g.Qout) {
-            const int b = q / g.S, rem = q - b * g.S;
-            const int yy = rem / g.P - g.pad, xx = rem % g.P;
-            if (yy >= 0 && yy < p.Hin && xx < p.Win) {
-                if (p.upsample2) {
-                    if (!((yy | xx) & 1) && (yy >> 1) < p.Hs && (xx >> 1) < p.Ws) off = b * (int)p.x_bs + (yy >> 1) * p.Ws + (xx >> 1);
-                } else off = b * (int)p.x_bs + yy * p.Ws + xx;
-            }
-        }
-        s_pos[i] = off;
-    }
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_d = tmem_base_s;
-    DBG(1);
+    if (tid == 0) DBG(1);
+    const int ntl = (g.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles of this CTA
 
-    // ---- weight producer starts streaming right away (overlaps the activation staging)
-    const bool resident = (g.nst == g.kk);          // every tap fits: one barrier, no ring traffic
-    if (warp == 1 && lane == 0) {
-        if (resident) {
-            tc::mbar_arrive_expect_tx(&bar_full[0], (uint32_t)g.kk * g.tap_bytes);
-            for (int t = 0; t < g.kk; ++t)
-                tc::bulk_g2s(wst + (size_t)t * g.tap_bytes, reinterpret_cast<const unsigned char*>(p.wprep) + (size_t)t * g.tap_bytes,
-                             g.tap_bytes, &bar_full[0]);
-        } else {
-            for (int t = 0; t < g.nst; ++t) {
-                tc::mbar_arrive_expect_tx(&bar_full[t], g.tap_bytes);
-                tc::bulk_g2s(wst + (size_t)t * g.tap_bytes, reinterpret_cast<const unsigned char*>(p.wprep) + (size_t)t * g.tap_bytes,
-                             g.tap_bytes, &bar_full[t]);
+    if (warp == 9) {
+        // ================= weight producer =================
+        if (lane == 0) {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wprep);
+            if (g.resident) {
+                tc::mbar_arrive_expect_tx(&w_full[0], (uint32_t)g.kk * g.tap_bytes);
+                for (int t = 0; t < g.kk; ++t) tc::bulk_g2s(wst + (size_t)t * g.tap_bytes, src + (size_t)t * g.tap_bytes, g.tap_bytes, &w_full[0]);
+            } else {
+                const int total = ntl * g.kk;
+                for (int gi = 0; gi < total; ++gi) {
+                    const int s = gi % g.nst, t = gi % g.kk;
+                    if (gi >= g.nst) tc::mbar_wait(&w_empty[s], ((gi / g.nst) - 1) & 1);
+                    tc::mbar_arrive_expect_tx(&w_full[s], g.tap_bytes);
+                    tc::bulk_g2s(wst + (size_t)s * g.tap_bytes, src + (size_t)t * g.tap_bytes, g.tap_bytes, &w_full[s]);
+                }
             }
         }
-    }
-
-    // ---- stage the activation window: 16-byte chunk = 4 channels of one position.  Tasks are taken
-    // four at a time with all global loads issued before the first use (the shared-memory stores would
-    // otherwise serialise the loads behind them).
-    {
-        const int nk4 = g.cin_p / 4;
-        const int ntask = g.npos * nk4;
-        const int b_x2 = (int)p.x2_bs, b_x = (int)p.x_bs;
-        constexpr int U = 4;
-        int i_u = tid, k_u = 0;                      // task (position, chunk) of this thread, advanced by 256 each time
-        while (i_u >= g.npos) { i_u -= g.npos; ++k_u; }
-        for (int c0 = tid; c0 < ntask; c0 += IBINN_THREADS * U) {
-            float v[U][4], w2[U][4];
-            int ti[U], tk[U], toff[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                ti[u] = i_u; tk[u] = k_u;
-                const bool live = (c0 + u * IBINN_THREADS) < ntask;
-                toff[u] = live ? s_pos[i_u] : -2;
-                i_u += IBINN_THREADS;
-                while (i_u >= g.npos) { i_u -= g.npos; ++k_u; }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int ch = tk[u] * 4 + j;
-                    v[u][j] = 0.f; w2[u][j] = 0.f;
-                    if (toff[u] >= 0 && ch < p.Cin) {
-                        const size_t o = (size_t)toff[u] + (size_t)ch * HsWs;
-                        v[u][j] = __ldg(p.x + o);
-                        if (PRE == IBINN_PRE_BNBWD) {
-                            const int bb = toff[u] / b_x, in_img = toff[u] - bb * b_x;     // same (b, y, x) in x2, own batch stride
-                            w2[u][j] = __ldg(p.x2 + (size_t)bb * b_x2 + in_img + (size_t)ch * HsWs);
-                        } else if (PRE == IBINN_PRE_BN_RELU) {
-                            if (p.pre_mask) w2[u][j] = __ldg(p.pre_mask + (size_t)(toff[u] / b_x) * p.Cin + ch);
+        __syncwarp();        // the warp reaches the closing __syncthreads as one
+    } else if (warp == 8) {
+        // ================= MMA issuer =================
+        // The whole warp walks the loop (descriptor arithmetic stays on the uniform datapath); one
+        // elected lane issues the tcgen05 instructions.
+        {
+            const uint32_t idesc = tc::idesc_tf32(TM, g.np);
+            const uint64_t db0 = tc::smem_desc(tc::smem_u32(wst), g.lbo_b);
+            const int nks = g.cin_p / 8;
+            const uint32_t b_lo_off = ((uint32_t)(g.cin_p / 4) * g.lbo_b) >> 4;
+            const uint32_t a_step = (uint32_t)(2 * g.lbo_a) >> 4, b_step = (uint32_t)(2 * g.lbo_b) >> 4, st_step = (uint32_t)g.tap_bytes >> 4;
+            int gi = 0;
+            for (int j = 0; j < ntl; ++j) {
+                const int buf = j % g.nbuf, n = j / g.nbuf;
+                const uint32_t a_base = tc::smem_u32(tcs + (size_t)buf * 2 * g.a_bytes);
+                const uint64_t da_hi = tc::smem_desc(a_base, g.lbo_a), da_lo = tc::smem_desc(a_base + g.a_bytes, g.lbo_a);
+                const uint32_t acc_addr = tmem_d + buf * g.np;
+                if (n >= 1) tc::mbar_wait(&acc_empty[buf], (n - 1) & 1);      // epilogue has drained this accumulator
+                tc::mbar_wait(&a_full[buf], n & 1);                          // activation tile staged
+                if (j == 0) tc::mbar_wait(&a_help, 0);
+                if (g.resident && j == 0) tc::mbar_wait(&w_full[0], 0);
+                tc::fence_after_sync();
+                if (lane == 0 && j < 4) DBG(10 + 2 * j);
+                uint32_t acc = 0;
+                for (int t = 0; t < g.kk; ++t, ++gi) {
+                    int s = t;
+                    if (!g.resident) {
+                        s = gi % g.nst;
+                        tc::mbar_wait(&w_full[s], (gi / g.nst) & 1);
+                        tc::fence_after_sync();
+                    }
+                    const int dy = g.pad ? t / 3 - 1 : 0, dx = g.pad ? t % 3 - 1 : 0;
+                    const uint32_t row_off = (uint32_t)(g.halo + dy * g.P + dx);          // 16-byte rows
+                    const uint64_t bh = db0 + (uint64_t)(s * st_step), bl = bh + b_lo_off;
+#pragma unroll 1
+                    for (int pass = 0; pass < 3; ++pass) {
+                        uint64_t da = (pass == 2 ? da_lo : da_hi) + row_off;
+                        uint64_t db = pass == 1 ? bl : bh;
+#pragma unroll 4
+                        for (int ks = 0; ks < nks; ++ks) {
+                            if (tc::elect_one()) tc::mma_tf32(acc_addr, da, db, idesc, acc != 0);
+                            acc = 1;
+                            da += a_step;
+                            db += b_step;
                         }
                     }
+                    if (!g.resident) { if (tc::elect_one()) tc::mma_commit(&w_empty[s]); }
+                }
+                if (tc::elect_one()) { tc::mma_commit(&a_empty[buf]); tc::mma_commit(&acc_full[buf]); }
+                if (lane == 0 && j < 4) DBG(11 + 2 * j);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ================= loaders: stage the activation window of each tile =================
+        // (the first tile is staged together with the still idle epilogue warps: 256 threads)
+        const int lt = tid - 128;
+        for (int j = 0; j < ntl; ++j) {
+            const int buf = j % g.nbuf, n = j / g.nbuf;
+            const int q0 = ((int)blockIdx.x + j * (int)gridDim.x) * TM;
+            unsigned char* a_hi = tcs + (size_t)buf * 2 * g.a_bytes;
+            if (n >= 1) {
+                tc::mbar_wait(&a_empty[buf], (n - 1) & 1);                     // MMAs that read this buffer are done
+                if (STATS && g.alias_stats) tc::mbar_wait(&acc_empty[buf], (n - 1) & 1);   // ... and so is the epilogue that borrowed it
+            }
+            if (lt == 0 && j < 4) DBG(20 + 2 * j);
+            if (j == 0) tc_stage_tile<PRE>(p, g, q0, a_hi, a_hi + g.a_bytes, s_pa, s_pb, s_pc, lt + 128, 256);
+            else tc_stage_tile<PRE>(p, g, q0, a_hi, a_hi + g.a_bytes, s_pa, s_pb, s_pc, lt, 128);
+            tc::fence_async_smem();
+            mbar_arrive(&a_full[buf]);
+            if (lt == 0 && j < 4) DBG(21 + 2 * j);
+        }
+    } else {
+        // ================= epilogue: thread <-> output row of the tile =================
+        const int row = tid;                      // 0..127, TMEM lane
+        const size_t HWo = (size_t)p.Hout * p.Wout;
+        const int sc = tid >> 1, part = tid & 1;  // statistics: thread reduces 64 rows of channel sc
+        float run_n = 0.f, run_mean = 0.f, run_m2 = 0.f, run_a1 = 0.f, run_a2 = 0.f;
+        {   // help staging the first tile, then signal on the helper barrier
+            tc_stage_tile<PRE>(p, g, (int)blockIdx.x * TM, tcs, tcs + g.a_bytes, s_pa, s_pb, s_pc, tid, 256);
+            tc::fence_async_smem();
+            mbar_arrive(&a_help);
+        }
+        for (int j = 0; j < ntl; ++j) {
+            const int buf = j % g.nbuf, n = j / g.nbuf;
+            const int q = ((int)blockIdx.x + j * (int)gridDim.x) * TM + row;
+            bool valid = false;
+            size_t obase = 0, mbase = 0, abase = 0;
+            int bimg = 0;
+            if (q < g.Qout) {
+                const int b = q / g.S, rem = q - b * g.S;
+                const int yy = rem / g.P - g.pad, xx = rem % g.P;
+                if (yy >= 0 && yy < p.Hout && xx < p.Wout) {
+                    valid = true;
+                    bimg = b;
+                    const size_t in_img = (size_t)yy * p.Wout + xx;
+                    obase = (size_t)b * p.y_bs + in_img;
+                    mbase = (size_t)b * p.m_bs + in_img;
+                    abase = (size_t)b * p.addend_bs + in_img;
                 }
             }
+            tc::mbar_wait(&acc_full[buf], n & 1);
+            tc::fence_after_sync();
+            if (tid == 0 && j < 4) DBG(30 + 2 * j);
+            if (STATS) s_valid[row] = valid ? 1.f : 0.f;
+            const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + buf * g.np;
+#pragma unroll 1
+            for (int c8 = 0; c8 < g.np; c8 += 8) {
+                float v[8];
+                tc::tmem_ld8(taddr + c8, v);
+                tc::tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (toff[u] == -2) continue;
-                float h[4], l[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int ch = tk[u] * 4 + j;
-                    float t = v[u][j];
-                    if (toff[u] >= 0 && ch < p.Cin) {
-                        if (PRE == IBINN_PRE_RELU) t = fmaxf(t, 0.f);
-                        else if (PRE == IBINN_PRE_BN_RELU) {
-                            t = fmaxf(fmaf(t, s_pa[ch], s_pb[ch]), 0.f);
-                            if (p.pre_mask) t *= w2[u][j];
-                        } else if (PRE == IBINN_PRE_BNBWD) t = fmaf(s_pa[ch], t, fmaf(s_pb[ch], w2[u][j], s_pc[ch]));
+                for (int i = 0; i < 8; ++i) {
+                    const int c = c8 + i;
+                    float o = 0.f, xh = 0.f;
+                    if (valid && c < p.Cout) {
+                        o = v[i];
+                        if (EPI == IBINN_EPI_STORE || EPI == IBINN_EPI_RELUMASK) { if (p.bias) o += __ldg(p.bias + c); }
+                        if (EPI == IBINN_EPI_MASKSTATS) {
+                            const float h = __ldg(p.m_h + mbase + (size_t)c * HWo);
+                            o = fmaf(h, s_ea[c], s_eb[c]) > 0.f ? o : 0.f;
+                            if (p.m_drop) o *= __ldg(p.m_drop + (size_t)bimg * p.Cout + c);
+                            xh = (h - s_em[c]) * s_ei[c];
+                        } else if (EPI == IBINN_EPI_RELUMASK) {
+                            o = __ldg(p.m_h + mbase + (size_t)c * HWo) > 0.f ? o : 0.f;
+                        }
+                        float st = o;
+                        if (EPI == IBINN_EPI_STORE || EPI == IBINN_EPI_RELUMASK) { if (p.addend) st += p.addend[abase + (size_t)c * HWo]; }
+                        p.y[obase + (size_t)c * HWo] = st;
                     }
-                    tc::split_tf32(t, h[j], l[j]);
-                }
-                *reinterpret_cast<float4*>(a_hi + (size_t)tk[u] * g.lbo_a + ti[u] * 16) = make_float4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<float4*>(a_lo + (size_t)tk[u] * g.lbo_a + ti[u] * 16) = make_float4(l[0], l[1], l[2], l[3]);
-            }
-        }
-    }
-    tc::fence_async_smem();
-    __syncthreads();
-    DBG(2);
-
-    // ---- main loop over the filter taps
-    if (warp == 1 && lane == 0) {
-        for (int t = g.nst; t < g.kk; ++t) {
-            const int s = t % g.nst;
-            tc::mbar_wait(&bar_empty[s], ((t / g.nst) - 1) & 1);
-            tc::mbar_arrive_expect_tx(&bar_full[s], g.tap_bytes);
-            tc::bulk_g2s(wst + (size_t)s * g.tap_bytes, reinterpret_cast<const unsigned char*>(p.wprep) + (size_t)t * g.tap_bytes, g.tap_bytes,
-                         &bar_full[s]);
-        }
-    } else if (warp == 0 && lane == 0) {
-        tc::fence_after_sync();
-        const uint32_t idesc = tc::idesc_tf32(TM, g.np);
-        // descriptors differ only in the 14-bit start-address field: build once, then add (bytes >> 4)
-        const uint64_t da_hi = tc::smem_desc(tc::smem_u32(a_hi), g.lbo_a), da_lo = tc::smem_desc(tc::smem_u32(a_lo), g.lbo_a);
-        const uint64_t db0 = tc::smem_desc(tc::smem_u32(wst), g.lbo_b);
-        const int nks = g.cin_p / 8;
-        const uint32_t b_lo_off = ((uint32_t)(g.cin_p / 4) * g.lbo_b) >> 4;
-        const uint32_t a_step = (uint32_t)(2 * g.lbo_a) >> 4, b_step = (uint32_t)(2 * g.lbo_b) >> 4, st_step = (uint32_t)g.tap_bytes >> 4;
-        bool acc = false;
-        for (int t = 0; t < g.kk; ++t) {
-            const int s = t % g.nst;
-            if (!resident || t == 0) {
-                tc::mbar_wait(&bar_full[s], (t / g.nst) & 1);
-                tc::fence_after_sync();
-            }
-            const int dy = g.pad ? t / 3 - 1 : 0, dx = g.pad ? t % 3 - 1 : 0;
-            const uint32_t row_off = (uint32_t)(g.halo + dy * g.P + dx);          // 16-byte rows
-            const uint64_t bh = db0 + (uint64_t)(s * st_step), bl = bh + b_lo_off;
-#pragma unroll 1
-            for (int pass = 0; pass < 3; ++pass) {
-                uint64_t da = (pass == 2 ? da_lo : da_hi) + row_off;
-                uint64_t db = pass == 1 ? bl : bh;
-#pragma unroll 2
-                for (int ks = 0; ks < nks; ++ks) {
-                    tc::mma_tf32(tmem_d, da, db, idesc, acc);
-                    acc = true;
-                    da += a_step;
-                    db += b_step;
+                    if (STATS) {
+                        s_t1[c * TP + row] = o;
+                        if (EPI == IBINN_EPI_MASKSTATS) s_t2[c * TP + row] = o * xh;
+                    }
                 }
             }
-            if (!resident) tc::mma_commit(&bar_empty[s]);
-        }
-        tc::mma_commit(&bar_done);
-        DBG(3);
-    }
-    __syncwarp();
-    tc::mbar_wait(&bar_done, 0);
-    tc::fence_after_sync();
-    DBG(4);
-
-    // ---- epilogue: thread <-> output position q0 + 32*(warp%4) + lane, columns split between warp and warp+4
-    const int wq = warp & 3, half = warp >> 2;
-    const int ncol = g.np / 2;                       // 8, 16, 24 or 32 columns per thread
-    const int col0 = half * ncol;
-    const int row = wq * 32 + lane;
-    const int q = q0 + row;
-    bool valid = false;
-    size_t obase = 0, mbase = 0, abase = 0;
-    int bimg = 0;
-    if (q < g.Qout) {
-        const int b = q / g.S, rem = q - b * g.S;
-        const int yy = rem / g.P - g.pad, xx = rem % g.P;
-        if (yy >= 0 && yy < p.Hout && xx < p.Wout) {
-            valid = true;
-            bimg = b;
-            const size_t in_img = (size_t)yy * p.Wout + xx;
-            obase = (size_t)b * p.y_bs + in_img;
-            mbase = (size_t)b * p.m_bs + in_img;
-            abase = (size_t)b * p.addend_bs + in_img;
-        }
-    }
-    const size_t HWo = (size_t)p.Hout * p.Wout;
-    const uint32_t taddr = tmem_d + ((uint32_t)(wq * 32) << 16) + col0;
-    constexpr bool STATS = (EPI == IBINN_EPI_BNSTATS || EPI == IBINN_EPI_MASKSTATS);
-    if (STATS && half == 0) s_valid[row] = valid ? 1.f : 0.f;
-
-#pragma unroll 1
-    for (int c8 = 0; c8 < ncol; c8 += 8) {
-        float v[8];
-        tc::tmem_ld8(taddr + c8, v);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int c = col0 + c8 + i;
-            float o = 0.f, xh = 0.f;
-            if (valid && c < p.Cout) {
-                o = v[i];
-                if (EPI == IBINN_EPI_STORE || EPI == IBINN_EPI_RELUMASK) { if (p.bias) o += __ldg(p.bias + c); }
-                if (EPI == IBINN_EPI_MASKSTATS) {
-                    const float h = __ldg(p.m_h + mbase + (size_t)c * HWo);
-                    o = fmaf(h, s_ea[c], s_eb[c]) > 0.f ? o : 0.f;
-                    if (p.m_drop) o *= __ldg(p.m_drop + (size_t)bimg * p.Cout + c);
-                    xh = (h - s_em[c]) * s_ei[c];
-                } else if (EPI == IBINN_EPI_RELUMASK) {
-                    o = __ldg(p.m_h + mbase + (size_t)c * HWo) > 0.f ? o : 0.f;
-                }
-                float st = o;
-                if (EPI == IBINN_EPI_STORE || EPI == IBINN_EPI_RELUMASK) { if (p.addend) st += p.addend[abase + (size_t)c * HWo]; }
-                p.y[obase + (size_t)c * HWo] = st;
-            }
+            tc::fence_before_sync();
+            if (!(STATS && g.alias_stats)) mbar_arrive(&acc_empty[buf]);       // accumulator (TMEM) is free again
             if (STATS) {
-                s_t1[c * TP + row] = o;
-                if (EPI == IBINN_EPI_MASKSTATS) s_t2[c * TP + row] = o * xh;
-            }
-        }
-    }
-    DBG(8);
-    if (STATS) {
-        __syncthreads();
-        // thread (c = tid/4, part = tid%4) reduces 32 rows of channel c; the 4 parts meet by shuffle
-        const int c = tid >> 2, part = tid & 3;
-        float a1 = 0.f, a2 = 0.f, cnt = 0.f;
-        const float* t1 = s_t1 + c * TP + part * 32;
-        const float* t2 = s_t2 + c * TP + part * 32;
+                epi_sync();
+                float a1 = 0.f, a2 = 0.f, cnt = 0.f;
+                if (sc < g.np) {
+                    const float* t1 = s_t1 + sc * TP + part * 64;
+                    const float* t2 = s_t2 + sc * TP + part * 64;
 #pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-            a1 += t1[r];
-            cnt += s_valid[part * 32 + r];
-            if (EPI == IBINN_EPI_MASKSTATS) a2 += t2[r];
-        }
-        a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, 1); cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
-        float* rec = p.partials + (size_t)blockIdx.x * (2 * p.Cout + 4);
-        if (EPI == IBINN_EPI_BNSTATS) {
-            const float mean = cnt > 0.f ? a1 / cnt : 0.f;
+                    for (int r = 0; r < 64; ++r) {
+                        a1 += t1[r];
+                        cnt += s_valid[part * 64 + r];
+                        if (EPI == IBINN_EPI_MASKSTATS) a2 += t2[r];
+                    }
+                }
+                a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+                cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+                if (EPI == IBINN_EPI_BNSTATS) {
+                    const float mean = cnt > 0.f ? a1 / cnt : 0.f;
+                    if (sc < g.np) {
+                        const float* t1 = s_t1 + sc * TP + part * 64;
 #pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-                const float d = t1[r] - mean;
-                a2 = fmaf(s_valid[part * 32 + r] * d, d, a2);
+                        for (int r = 0; r < 64; ++r) {
+                            const float d = t1[r] - mean;
+                            a2 = fmaf(s_valid[part * 64 + r] * d, d, a2);
+                        }
+                    }
+                    a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+                    if (cnt > 0.f) {       // Chan: fold the tile (cnt, mean, a2) into the running (n, mean, M2)
+                        const float nn = run_n + cnt, dlt = mean - run_mean;
+                        run_mean += dlt * cnt / nn;
+                        run_m2 += a2 + dlt * dlt * run_n * cnt / nn;
+                        run_n = nn;
+                    }
+                } else {
+                    a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+                    run_a1 += a1;
+                    run_a2 += a2;
+                    run_n += cnt;
+                }
+                epi_sync();                                                  // tiles may be overwritten by the next pass
+                if (g.alias_stats) mbar_arrive(&acc_empty[buf]);             // borrowed operand area is free again
             }
-            a2 += __shfl_xor_sync(0xffffffffu, a2, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
-            if (part == 0 && c < p.Cout) { rec[c] = mean; rec[p.Cout + c] = a2; }
-        } else {
-            a2 += __shfl_xor_sync(0xffffffffu, a2, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
-            if (part == 0 && c < p.Cout) { rec[c] = a1; rec[p.Cout + c] = a2; }
+            if (tid == 0 && j < 4) DBG(31 + 2 * j);
         }
-        if (tid == 0) rec[2 * p.Cout] = cnt;
+        if (STATS) {
+            float* rec = p.partials + (size_t)blockIdx.x * (2 * p.Cout + 4);
+            if (part == 0 && sc < p.Cout) {
+                if (EPI == IBINN_EPI_BNSTATS) { rec[sc] = run_mean; rec[p.Cout + sc] = run_m2; }
+                else { rec[sc] = run_a1; rec[p.Cout + sc] = run_a2; }
+            }
+            if (tid == 0) rec[2 * p.Cout] = run_n;
+        }
     }
 
-    DBG(5);
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_d, g.tmem_cols);
-    DBG(6);
+    if (warp == 8) tc::tmem_dealloc(tmem_d, g.tmem_cols);
+    if (tid == 0) DBG(2);
     if (!STATS) return;
 
-    // ---- last CTA: combine the per-tile records in tile order (deterministic), like conv.cu
+    // ---- last CTA: combine the per-CTA records in CTA order (deterministic for a given grid)
     const unsigned nblk = gridDim.x;
     if (!last_block_ticket(p.counter, nblk, &s_flag)) return;
     int cpad = 8;
     while (cpad < p.Cout) cpad <<= 1;
-    const int tpc = IBINN_THREADS / cpad > 32 ? 32 : IBINN_THREADS / cpad;
+    const int tpc = 256 / cpad > 32 ? 32 : 256 / cpad;
     const int c = tid / tpc, j = tid % tpc;
-    const bool cval = (c < p.Cout) && (tid < cpad * tpc);
+    const bool cval = (tid < 256) && (c < p.Cout) && (tid < cpad * tpc);
     const size_t rs = 2 * p.Cout + 4;
     if (EPI == IBINN_EPI_BNSTATS) {
         double n = 0., mean = 0., m2 = 0.;
@@ -477,6 +547,7 @@ __global__ void __launch_bounds__(IBINN_THREADS, 1) conv_tc_kernel(const ibinn_c
         }
     }
     if (tid == 0) *p.counter = 0u;
+    if (tid == 0) DBG(3);
 }
 
 template <int PRE, int EPI>
@@ -484,7 +555,7 @@ static int tc_launch_inst(const ibinn_conv_args& a, const TcGeom& g, cudaStream_
     auto kfn = conv_tc_kernel<PRE, EPI>;
     int e = ibinn_set_smem(kfn, g.smem_bytes);
     if (e) return e;
-    IBINN_LAUNCH(kfn, dim3(g.ntiles), dim3(IBINN_THREADS), g.smem_bytes, st, a, g);
+    IBINN_LAUNCH(kfn, dim3(g.grid), dim3(NTHREADS_TC), g.smem_bytes, st, a, g);
     return ibinn_launch_status();
 }
 
@@ -501,7 +572,7 @@ bool conv_tc_supported(const ibinn_conv_args& a) {
 int64_t conv_tc_partials_floats(const ibinn_conv_args& a) {
     TcGeom g;
     if (!tc_geometry(a, g)) return IBINN_EINVAL;
-    return (int64_t)g.ntiles * (2 * a.Cout + 4);
+    return (int64_t)g.grid * (2 * a.Cout + 4);
 }
 
 int64_t conv_tc_wprep_floats(const ibinn_conv_args& a) {
