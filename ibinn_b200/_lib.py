@@ -44,7 +44,7 @@ class WgradArgs(Structure):
                 ('x', c_void_p), ('x_bs', c_int64), ('x_pre', c_int32), ('x_bn', BnRef), ('x_mask', c_void_p),
                 ('dw', c_void_p), ('dbias', c_void_p),
                 ('B', c_int32), ('Cin', c_int32), ('Cout', c_int32), ('Hin', c_int32), ('Win', c_int32), ('Hout', c_int32),
-                ('Wout', c_int32), ('ksize', c_int32), ('stride', c_int32)]
+                ('Wout', c_int32), ('ksize', c_int32), ('stride', c_int32), ('workspace', c_void_p)]
 
 
 P, I, F, L = c_void_p, c_int, c_float, c_int64
@@ -58,6 +58,7 @@ _SIGNATURES = {
     'ibinn_conv_wprep_floats': ([POINTER(ConvArgs)], c_int64),
     'ibinn_conv_forward': ([POINTER(ConvArgs), P], c_int),
     'ibinn_sizeof_wgrad_args': ([], c_size_t),
+    'ibinn_conv_wgrad_workspace_floats': ([POINTER(WgradArgs)], c_int64),
     'ibinn_conv_wgrad': ([POINTER(WgradArgs), P], c_int),
     'ibinn_aio_coupling_forward': ([P, P, P, P, P, P, P, I, I, I, I, F, F, P], c_int),
     'ibinn_aio_coupling_backward': ([P] * 14 + [I, I, I, I, F, F, P], c_int),

@@ -11,6 +11,7 @@
 // loop is three LDS.128 per 32 FMA.  Partial tiles are reduced across partitions in shared memory
 // and accumulated to dW with one fp32 atomic per element per CTA.
 #include "common.cuh"
+#include "conv_internal.cuh"
 
 namespace {
 
@@ -239,6 +240,11 @@ __global__ void __launch_bounds__(IBINN_THREADS) wgrad_kernel(const ibinn_wgrad_
 
 extern "C" size_t ibinn_sizeof_wgrad_args(void) { return sizeof(ibinn_wgrad_args); }
 
+extern "C" int64_t ibinn_conv_wgrad_workspace_floats(const ibinn_wgrad_args* a) {
+    if (!a) return IBINN_ENULL;
+    return wgrad_tc_supported(*a) ? wgrad_tc_workspace_floats(*a) : 0;
+}
+
 extern "C" int ibinn_conv_wgrad(const ibinn_wgrad_args* ap, ibinn_stream_t stream) {
     if (!ap) return IBINN_ENULL;
     int e = ibinn_check_device();
@@ -255,6 +261,7 @@ extern "C" int ibinn_conv_wgrad(const ibinn_wgrad_args* ap, ibinn_stream_t strea
     if (a.x_pre == IBINN_PRE_BN_RELU) {
         if (!a.x_bn.mean || !a.x_bn.scale || !a.x_bn.gamma || !a.x_bn.beta) return IBINN_ENULL;
     } else if (a.x_pre != IBINN_PRE_NONE && a.x_pre != IBINN_PRE_RELU) return IBINN_EINVAL;
+    if (wgrad_tc_supported(a)) return wgrad_tc_launch(a, a.workspace, (cudaStream_t)stream);     // tcgen05 path (stride 1)
     WgGeom g;
     if (!wgrad_geometry(a, g)) return IBINN_EINVAL;
     if (g.npixgroups > 65535) return IBINN_EINVAL;

@@ -1,0 +1,497 @@
+// Weight / bias gradients of the stride-1 subnet convolutions on tcgen05 (3xTF32).
+//
+//   dW[co][ci][ky][kx] = sum_q G[q][co] * X[q + (ky-1) P + (kx-1)][ci]        (q = padded pixel position)
+//
+// GEMM view: the reduction dimension K is the PIXEL axis.  NCHW keeps the pixels of one channel
+// contiguous, so both operands are already K-major in global memory: a 16-byte chunk = 4 consecutive
+// pixels of one channel.  The batch is one padded 1-D sequence with pitch P4 (multiple of 4 >= W + pad)
+// and one shared zero row between images, so a row shift (dy) moves whole chunks and only the column
+// shift (dx) needs its own staged copy.  One tcgen05.mma then covers several filter taps at once:
+//   A rows (M = 128) = (dy copy, co):  G shifted by -dy rows        (2 copies for Cout <= 64, 3 for <= 40)
+//   B rows (N <= 256) = (dx copy, ci): X shifted by dx in {-1,0,+1} (+ one row of ones -> dbias for free)
+// i.e. N = 3 Cin >= 128 for the wide layers, which is where the tensor pipe reaches its full rate.
+// CTAs split the pixel axis; each keeps its [128 x N] accumulators in TMEM for its whole range and
+// writes ONE partial record; a second tiny kernel sums the records in CTA order (deterministic, no
+// atomics) and accumulates into dW / dbias.
+#include "common.cuh"
+#include "conv_internal.cuh"
+#include "tc.cuh"
+
+#ifndef IBINN_EMU
+#ifdef IBINN_DBG
+__device__ unsigned long long ibinn_wdbg[64];
+__device__ __forceinline__ unsigned long long wgtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define WDBG(i) do { if (blockIdx.x == 1) ibinn_wdbg[i] = wgtime(); } while (0)
+extern "C" int ibinn_wdebug_read(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, ibinn_wdbg, sizeof(unsigned long long) * 64); }
+#else
+#define WDBG(i)
+#endif
+namespace {
+
+constexpr int WT_STAGERS = 512;     // warps 0-15 stage operands in two groups of 256 (warps 0-3 also run the epilogue)
+constexpr int WT_THREADS = WT_STAGERS + 32;   // + warp 16: MMA issuer
+constexpr int WT_MMA_WARP = WT_STAGERS / 32;
+constexpr int KC_MAX = 16;          // K chunks per stage: 4, 8 or 16 (16 / 32 / 64 pixels), chosen per layer
+constexpr int WT_MAXC = 128;
+
+struct WgTcGeom {
+    int pad, kk, P4, rows_img, S4, Q, nblocks, ncta, bpc;     // bpc = K blocks per CTA
+    int coutp, cinp, na, ntile, nd, np, ones_row, nstage, tmem_cols;
+    int a_tile_bytes, b_bytes, stage_bytes, lbo_a, lbo_b, rec_floats;
+    int vec_g, vec_x, kc;
+    size_t smem_bytes;
+};
+
+static inline int rup(int v, int m) { return (v + m - 1) / m * m; }
+
+static bool wg_geometry(const ibinn_wgrad_args& a, WgTcGeom& g) {
+    if (a.stride != 1 || a.Hout != a.Hin || a.Wout != a.Win) return false;
+    if (a.Cout > 64 || a.Cin > 80 || a.Cout > WT_MAXC || a.Cin > WT_MAXC) return false;
+    g.pad = a.ksize / 2;
+    g.kk = a.ksize * a.ksize;
+    g.P4 = rup(a.Win + g.pad, 4);
+    g.rows_img = a.Hin + g.pad;
+    g.S4 = g.rows_img * g.P4;
+    g.Q = a.B * g.S4 + g.pad * g.P4;
+    g.coutp = rup(a.Cout, 8);
+    g.cinp = rup(a.Cin, 8);
+    g.nd = a.ksize;                                   // dx copies
+    g.na = 128 / g.coutp < a.ksize ? 128 / g.coutp : a.ksize;   // dy copies stacked in one A tile
+    g.ntile = (a.ksize + g.na - 1) / g.na;
+    g.ones_row = a.dbias ? g.nd * g.cinp : -1;
+    g.np = rup(g.nd * g.cinp + (a.dbias ? 8 : 0), 16);
+    if (g.np > 256 || g.ntile * g.np > 512) return false;
+    int cols = g.ntile * g.np;
+    g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+    g.lbo_a = 128 * 16;
+    g.lbo_b = g.np * 16;
+    // enough staging work per K block to hide the load latency (>= ~4 chunk tasks per staging thread),
+    // but at least 3 stages in shared memory
+    const int tasks_per_chunk = g.ntile * g.na * a.Cout + a.Cin;
+    g.kc = tasks_per_chunk * 4 >= 1200 ? 4 : tasks_per_chunk * 8 >= 1200 ? 8 : KC_MAX;
+    for (;;) {
+        g.a_tile_bytes = g.kc * g.lbo_a;                  // one of hi / lo of one A tile
+        g.b_bytes = g.kc * g.lbo_b;
+        g.stage_bytes = 2 * (g.ntile * g.a_tile_bytes + g.b_bytes);
+        g.nstage = (200 * 1024) / g.stage_bytes;
+        if (g.nstage >= 3 || g.kc == 4) break;
+        g.kc /= 2;
+    }
+    if (g.nstage > 4) g.nstage = 4;
+    if (g.nstage < 2) return false;
+    g.nblocks = (g.Q + 4 * g.kc - 1) / (4 * g.kc);
+    g.smem_bytes = (size_t)g.nstage * g.stage_bytes + (5 * WT_MAXC) * 4 + 256;
+    g.ncta = g.nblocks < 148 ? g.nblocks : 148;
+    g.bpc = (g.nblocks + g.ncta - 1) / g.ncta;
+    g.ncta = (g.nblocks + g.bpc - 1) / g.bpc;
+    g.rec_floats = rup(g.kk * a.Cout * a.Cin + (a.dbias ? a.Cout : 0), 4);      // records stay 16-byte aligned
+    if (a.g_pre == IBINN_PRE_BNBWD && a.gh_bs != a.g_bs) return false;      // the staging code addresses g and gh with one offset
+    g.vec_g = (a.Win % 4 == 0) && (a.g_bs % 4 == 0) && (((uintptr_t)a.g & 15) == 0) &&
+              (a.g_pre != IBINN_PRE_BNBWD || ((a.gh_bs % 4 == 0) && (((uintptr_t)a.gh & 15) == 0)));
+    g.vec_x = (a.Win % 4 == 0) && (a.x_bs % 4 == 0) && (((uintptr_t)a.x & 15) == 0);
+    return true;
+}
+
+__device__ __forceinline__ float wt_invstd(const ibinn_bn_ref& r, int c) {
+    const float s = r.scale[c];
+    return r.scale_is_variance ? rsqrtf(s + r.eps) : s;
+}
+__device__ __forceinline__ void wt_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void wt_store_split(unsigned char* hi, unsigned char* lo, const float (&v)[4]) {
+    float h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tc::split_tf32(v[i], h[i], l[i]);
+    *reinterpret_cast<float4*>(hi) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(lo) = make_float4(l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgrad_args p, const WgTcGeom g, float* __restrict__ partials) {
+    extern __shared__ __align__(128) unsigned char wts[];
+    __shared__ __align__(8) uint64_t full[4], empty[4], done;
+    __shared__ uint32_t tmem_base_s;
+    float* s_ga = reinterpret_cast<float*>(wts + (size_t)g.nstage * g.stage_bytes);
+    float* s_gb = s_ga + WT_MAXC;
+    float* s_gc = s_gb + WT_MAXC;
+    float* s_xa = s_gc + WT_MAXC;
+    float* s_xb = s_xa + WT_MAXC;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int HW = p.Hin * p.Win;
+    if (tid == 0) WDBG(0);
+    if (tid == 0) {
+        for (int i = 0; i < 4; ++i) { tc::mbar_init(&full[i], WT_STAGERS / 2); tc::mbar_init(&empty[i], 1); }
+        tc::mbar_init(&done, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == WT_MMA_WARP) tc::tmem_alloc(&tmem_base_s, g.tmem_cols);
+    if (p.g_pre == IBINN_PRE_BNBWD) {
+        for (int c = tid; c < p.Cout; c += WT_THREADS) {
+            const float is = wt_invstd(p.g_bn, c), k = p.g_bn.gamma[c] * is;
+            const float m1 = p.g_sums[c] * p.g_inv_count, m2 = p.g_sums[p.Cout + c] * p.g_inv_count;
+            s_ga[c] = k;
+            s_gb[c] = -k * m2 * is;
+            s_gc[c] = -k * m1 + k * m2 * is * p.g_bn.mean[c];
+        }
+    }
+    if (p.x_pre == IBINN_PRE_BN_RELU) {
+        for (int c = tid; c < p.Cin; c += WT_THREADS) {
+            const float is = wt_invstd(p.x_bn, c), A = p.x_bn.gamma[c] * is;
+            s_xa[c] = A;
+            s_xb[c] = p.x_bn.beta[c] - p.x_bn.mean[c] * A;
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_d = tmem_base_s;
+    if (tid == 0) WDBG(1);
+    const int blk0 = blockIdx.x * g.bpc;
+    const int nblk = min(g.bpc, g.nblocks - blk0);
+    const int nrows_total = p.B * g.rows_img + g.pad;        // padded rows of the whole sequence
+
+    const int KC = g.kc;
+    if (warp == WT_MMA_WARP) {
+        // ================= MMA issuer (whole warp walks the loop, one elected lane issues) =================
+        const uint32_t idesc = tc::idesc_tf32(128, g.np);
+        const uint32_t a_step = (uint32_t)(2 * g.lbo_a) >> 4, b_step = (uint32_t)(2 * g.lbo_b) >> 4;
+        for (int i = 0; i < nblk; ++i) {
+            const int s = i % g.nstage;
+            tc::mbar_wait(&full[s], (i / g.nstage) & 1);
+            tc::fence_after_sync();
+            if (lane == 0 && i < 6) WDBG(10 + i);
+            const uint32_t st = tc::smem_u32(wts + (size_t)s * g.stage_bytes);
+            const uint32_t b_hi = st + 2 * g.ntile * g.a_tile_bytes, b_lo = b_hi + g.b_bytes;
+            for (int t = 0; t < g.ntile; ++t) {
+                const uint32_t a_hi = st + t * 2 * g.a_tile_bytes, a_lo = a_hi + g.a_tile_bytes;
+                const uint32_t acc = tmem_d + t * g.np;
+#pragma unroll 1
+                for (int pass = 0; pass < 3; ++pass) {
+                    uint64_t da = tc::smem_desc(pass == 2 ? a_lo : a_hi, g.lbo_a);
+                    uint64_t db = tc::smem_desc(pass == 1 ? b_lo : b_hi, g.lbo_b);
+#pragma unroll 2
+                    for (int ks = 0; ks < KC / 2; ++ks) {
+                        if (tc::elect_one()) tc::mma_tf32(acc, da, db, idesc, (i | pass | ks) != 0);
+                        da += a_step;
+                        db += b_step;
+                    }
+                }
+            }
+            if (tc::elect_one()) tc::mma_commit(&empty[s]);
+        }
+        if (tc::elect_one()) tc::mma_commit(&done);
+        if (lane == 0) WDBG(2);
+        __syncwarp();
+    } else {
+        // ================= operand staging: two groups of 256 threads take alternate K blocks =================
+        // 256 % KC == 0, so a thread always works on the same chunk column kc of a block: its pixel
+        // coordinates are decoded once per block; what varies over its tasks is the channel / copy.
+        const int grp = tid >> 8, lt = tid & 255;
+        const int kc = lt % KC, lane_t = lt / KC, tstride = 256 / KC;
+        const int n_ar = g.ntile * g.na * p.Cout;              // A rows that carry data: (tile, dy copy, co)
+        const int n_br = p.Cin + (g.ones_row >= 0 ? 1 : 0);    // B source rows: ci (+ the ones row)
+        // per-thread task table (fixed for the whole kernel): the channel / copy of each of its A rows
+        constexpr int UA = 4;
+        int t_row[UA], t_co[UA], t_cp[UA];                     // smem row offset, channel, dy copy (-1: no data)
+#pragma unroll
+        for (int u = 0; u < UA; ++u) {
+            const int r = lane_t + u * tstride;
+            const bool live = r < n_ar;
+            const int co = live ? r % p.Cout : 0, cp = live ? r / p.Cout : 0;
+            const int t = cp / g.na, dyi = cp - t * g.na;
+            t_row[u] = (t * 2 * g.a_tile_bytes) + (dyi * g.coutp + co) * 16;
+            t_co[u] = co;
+            t_cp[u] = live ? ((cp < g.nd || g.kk == 1) ? cp : -1) : -2;      // -2: row does not exist
+        }
+        const bool many_rows = n_ar > UA * tstride;            // shapes with more than 4 rows per thread take the slow loop
+        for (int i = grp; i < nblk; i += 2) {
+            const int s = i % g.nstage;
+            if (i >= g.nstage) tc::mbar_wait(&empty[s], ((i / g.nstage) - 1) & 1);
+            if (lt == 0 && i < 6) WDBG(20 + 2 * i);
+            unsigned char* st = wts + (size_t)s * g.stage_bytes;
+            unsigned char* b_hi = st + 2 * g.ntile * g.a_tile_bytes;
+            const size_t b_lo_off = g.b_bytes;
+            const int q = (blk0 + i) * 4 * KC + 4 * kc;        // first padded position of this thread's chunk
+            const int R0 = q / g.P4, c0 = q % g.P4;
+            // pixel coordinates of the (up to) three row-shifted copies, decoded once per block
+            long long base3[3];
+            bool ok3[3];
+#pragma unroll
+            for (int d3 = 0; d3 < 3; ++d3) {
+                const int R = R0 - (g.pad ? d3 - 1 : 0);
+                ok3[d3] = false; base3[d3] = 0;
+                if (R >= 0 && R < nrows_total && c0 < p.Win && (g.pad || d3 == 0)) {
+                    const int b = R / g.rows_img, y = R - b * g.rows_img - g.pad;
+                    if (y >= 0 && b < p.B) { ok3[d3] = true; base3[d3] = (long long)b * p.g_bs + (long long)y * p.Win + c0; }
+                }
+            }
+            bool rowok = false;
+            int bb = 0, yy = 0;
+            if (R0 >= 0 && R0 < nrows_total) {
+                bb = R0 / g.rows_img; yy = R0 - bb * g.rows_img - g.pad;
+                rowok = (yy >= 0 && bb < p.B);
+            }
+            // ---- issue every global load of this block first, then transform and store
+            constexpr int UB = 2;
+            float w6[UB][6];
+            float mk[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const int ci = lane_t + u * tstride;
+                mk[u] = 1.f;
+#pragma unroll
+                for (int j = 0; j < 6; ++j) w6[u][j] = 0.f;
+                if (ci < p.Cin && rowok) {
+                    const float* xp = p.x + (size_t)bb * p.x_bs + (size_t)ci * HW + (size_t)yy * p.Win;
+                    if (g.vec_x && c0 + 3 < p.Win) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(xp + c0);
+                        w6[u][1] = t4.x; w6[u][2] = t4.y; w6[u][3] = t4.z; w6[u][4] = t4.w;
+                        if (g.nd > 1) {
+                            if (c0 > 0) w6[u][0] = __ldg(xp + c0 - 1);
+                            if (c0 + 4 < p.Win) w6[u][5] = __ldg(xp + c0 + 4);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) {
+                            const int c = c0 - 1 + j;
+                            if (c >= 0 && c < p.Win && (g.nd > 1 || (j >= 1 && j <= 4))) w6[u][j] = __ldg(xp + c);
+                        }
+                    }
+                    if (p.x_pre == IBINN_PRE_BN_RELU && p.x_mask) mk[u] = __ldg(p.x_mask + (size_t)bb * p.Cin + ci);
+                }
+            }
+            if (lt == 0 && i == 0) WDBG(40);
+            {
+                float v[UA][4], h[UA][4];
+                bool ok[UA];
+#pragma unroll
+                for (int u = 0; u < UA; ++u) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { v[u][j] = 0.f; h[u][j] = 0.f; }
+                    const int cp = t_cp[u];
+                    ok[u] = cp >= 0 && (cp == 0 ? ok3[0] : cp == 1 ? ok3[1] : ok3[2]);
+                    if (!ok[u]) continue;
+                    const long long off = (cp == 0 ? base3[0] : cp == 1 ? base3[1] : base3[2]) + (long long)t_co[u] * HW;
+                    const float* gp = p.g + off;
+                    const float* hp = p.gh + off;     // same (b,c,y,x): gh_bs == g_bs is checked on the host
+                    if (g.vec_g) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(gp);
+                        v[u][0] = t4.x; v[u][1] = t4.y; v[u][2] = t4.z; v[u][3] = t4.w;
+                        if (p.g_pre == IBINN_PRE_BNBWD) {
+                            const float4 h4 = *reinterpret_cast<const float4*>(hp);
+                            h[u][0] = h4.x; h[u][1] = h4.y; h[u][2] = h4.z; h[u][3] = h4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (c0 + j < p.Win) {
+                                v[u][j] = __ldg(gp + j);
+                                if (p.g_pre == IBINN_PRE_BNBWD) h[u][j] = __ldg(hp + j);
+                            }
+                        }
+                    }
+                }
+                if (lt == 0 && i == 0) WDBG(41);
+#pragma unroll
+                for (int u = 0; u < UA; ++u) {
+                    if (t_cp[u] == -2) continue;
+                    float o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        o[j] = v[u][j];
+                        // BN backward is affine (a*g + b*h + c): padded positions must stay exactly zero
+                        if (p.g_pre == IBINN_PRE_BNBWD && ok[u] && c0 + j < p.Win) o[j] = fmaf(s_ga[t_co[u]], v[u][j], fmaf(s_gb[t_co[u]], h[u][j], s_gc[t_co[u]]));
+                    }
+                    unsigned char* hi = st + t_row[u] + (size_t)kc * g.lbo_a;
+                    wt_store_split(hi, hi + g.a_tile_bytes, o);
+                }
+            }
+            if (lt == 0 && i == 0) WDBG(42);
+            if (many_rows) {
+                for (int r = lane_t + UA * tstride; r < n_ar; r += tstride) {
+                    const int co = r % p.Cout, cp = r / p.Cout;
+                    const int t = cp / g.na, dyi = cp - t * g.na;
+                    float o[4] = {0.f, 0.f, 0.f, 0.f};
+                    const bool okk = (cp < g.nd || g.kk == 1) && (cp == 0 ? ok3[0] : cp == 1 ? ok3[1] : ok3[2]);
+                    if (okk) {
+                        const long long off = (cp == 0 ? base3[0] : cp == 1 ? base3[1] : base3[2]) + (long long)co * HW;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (c0 + j < p.Win) {
+                                float tv = __ldg(p.g + off + j);
+                                if (p.g_pre == IBINN_PRE_BNBWD) tv = fmaf(s_ga[co], tv, fmaf(s_gb[co], __ldg(p.gh + off + j), s_gc[co]));
+                                o[j] = tv;
+                            }
+                        }
+                    }
+                    unsigned char* hi = st + (t * 2 * g.a_tile_bytes) + (dyi * g.coutp + co) * 16 + (size_t)kc * g.lbo_a;
+                    wt_store_split(hi, hi + g.a_tile_bytes, o);
+                }
+            }
+            // ---- B: activation copies shifted by dx (and the row of ones)
+            for (int u0 = 0; u0 * tstride + lane_t < n_br; ++u0) {
+                const int ci = lane_t + u0 * tstride;
+                if (ci >= p.Cin) {                                   // the ones row: 1 at valid pixels
+                    float o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o[j] = (rowok && c0 + j < p.Win) ? 1.f : 0.f;
+                    unsigned char* hi = b_hi + (size_t)kc * g.lbo_b + (size_t)g.ones_row * 16;
+                    wt_store_split(hi, hi + b_lo_off, o);
+                    continue;
+                }
+                float x6[6];
+                if (u0 < UB) {
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) if (u == u0) {
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) x6[j] = w6[u][j];
+                    }
+                } else {                                             // more than UB channels per thread: load late (rare shapes)
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        const int c = c0 - 1 + j;
+                        x6[j] = (rowok && c >= 0 && c < p.Win) ? __ldg(p.x + (size_t)bb * p.x_bs + (size_t)ci * HW + (size_t)yy * p.Win + c) : 0.f;
+                    }
+                }
+                float mkk = 1.f;
+                if (u0 < UB) {
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) if (u == u0) mkk = mk[u];
+                } else if (rowok && p.x_pre == IBINN_PRE_BN_RELU && p.x_mask) mkk = __ldg(p.x_mask + (size_t)bb * p.Cin + ci);
+#pragma unroll
+                for (int j = 0; j < 6; ++j) {
+                    const int c = c0 - 1 + j;
+                    if (!rowok || c < 0 || c >= p.Win) { x6[j] = 0.f; continue; }
+                    if (p.x_pre == IBINN_PRE_RELU) x6[j] = fmaxf(x6[j], 0.f);
+                    else if (p.x_pre == IBINN_PRE_BN_RELU) x6[j] = fmaxf(fmaf(x6[j], s_xa[ci], s_xb[ci]), 0.f) * mkk;
+                }
+                for (int d = 0; d < g.nd; ++d) {
+                    const int sh = g.nd > 1 ? d : 1;                 // window offset: dx = d - 1 -> x6[sh .. sh+3]
+                    const float o[4] = {x6[sh], x6[sh + 1], x6[sh + 2], x6[sh + 3]};
+                    unsigned char* hi = b_hi + (size_t)kc * g.lbo_b + (size_t)(d * g.cinp + ci) * 16;
+                    wt_store_split(hi, hi + b_lo_off, o);
+                }
+            }
+            if (lt == 0 && i == 0) WDBG(43);
+            tc::fence_async_smem();
+            if (lt == 0 && i == 0) WDBG(44);
+            wt_arrive(&full[s]);
+            if (lt == 0 && i < 6) WDBG(21 + 2 * i);
+        }
+    }
+
+    // ---- epilogue: warps 0-3, thread <-> TMEM lane = A row (dy copy, co)
+    if (warp < 4) {
+        tc::mbar_wait(&done, 0);
+        tc::fence_after_sync();
+        if (tid == 0) WDBG(3);
+        const int row = tid;
+        const int dyi = row / g.coutp, co = row - dyi * g.coutp;
+        float* rec = partials + (size_t)blockIdx.x * g.rec_floats;
+        const bool vec_st = (p.Cin % 4 == 0);
+        for (int t = 0; t < g.ntile; ++t) {
+            const int cp = t * g.na + dyi;                        // dy copy -> ky
+            const bool rowv = (dyi < g.na) && (co < p.Cout) && (cp < g.nd || g.kk == 1);
+            const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + t * g.np;
+            for (int d = 0; d < g.nd; ++d) {
+                const int tap = g.pad ? cp * 3 + d : 0;           // ky = cp, kx = d
+                float* dst = rec + ((size_t)tap * p.Cout + co) * p.Cin;
+#pragma unroll 1
+                for (int c8 = 0; c8 < g.cinp; c8 += 8) {
+                    float v[8];
+                    tc::tmem_ld8(taddr + d * g.cinp + c8, v);
+                    tc::tmem_ld_wait();
+                    if (!rowv) continue;
+                    if (vec_st && c8 + 8 <= p.Cin) {
+                        *reinterpret_cast<float4*>(dst + c8) = make_float4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<float4*>(dst + c8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) if (c8 + j < p.Cin) dst[c8 + j] = v[j];
+                    }
+                }
+            }
+            if (g.ones_row >= 0 && t == 0) {
+                float v[8];
+                tc::tmem_ld8(taddr + g.ones_row, v);
+                tc::tmem_ld_wait();
+                if (rowv) rec[g.kk * p.Cout * p.Cin + co] = v[0];
+            }
+        }
+    }
+    if (tid == 0) WDBG(4);
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == WT_MMA_WARP) tc::tmem_dealloc(tmem_d, g.tmem_cols);
+    if (tid == 0) WDBG(5);
+}
+
+// dw[co][ci][tap] += sum_cta rec[cta][tap][co][ci];  dbias[co] += sum_cta rec[cta][kk*Cout*Cin + co]
+// block = 32 elements x 8 record slices (fixed summation order -> deterministic)
+__global__ void __launch_bounds__(IBINN_THREADS) wgrad_reduce_kernel(const float* __restrict__ partials, int ncta, int rec_floats, float* __restrict__ dw,
+                                                                    float* __restrict__ dbias, int Cout, int Cin, int kk) {
+    __shared__ float s_part[8][33];
+    const int n = kk * Cout * Cin;
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    for (int e0 = blockIdx.x * 32; e0 < rec_floats; e0 += gridDim.x * 32) {
+        const int e = e0 + lane;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        if (e < rec_floats) {
+            int c = slice;
+            for (; c + 24 < ncta; c += 32) {
+                s0 += __ldg(partials + (size_t)c * rec_floats + e);
+                s1 += __ldg(partials + (size_t)(c + 8) * rec_floats + e);
+                s2 += __ldg(partials + (size_t)(c + 16) * rec_floats + e);
+                s3 += __ldg(partials + (size_t)(c + 24) * rec_floats + e);
+            }
+            for (; c < ncta; c += 8) s0 += __ldg(partials + (size_t)c * rec_floats + e);
+        }
+        __syncthreads();
+        s_part[slice][lane] = (s0 + s1) + (s2 + s3);
+        __syncthreads();
+        if (slice == 0 && e < rec_floats) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += s_part[k][lane];
+            if (e < n) {
+                const int ci = e % Cin, co = (e / Cin) % Cout, tap = e / (Cin * Cout);
+                dw[((size_t)co * Cin + ci) * kk + tap] += s;
+            } else if (dbias && e - n < Cout) dbias[e - n] += s;
+        }
+    }
+}
+
+}  // namespace
+
+bool wgrad_tc_supported(const ibinn_wgrad_args& a) {
+    WgTcGeom g;
+    return wg_geometry(a, g);
+}
+
+int64_t wgrad_tc_workspace_floats(const ibinn_wgrad_args& a) {
+    WgTcGeom g;
+    if (!wg_geometry(a, g)) return 0;
+    return (int64_t)g.ncta * g.rec_floats;
+}
+
+int wgrad_tc_launch(const ibinn_wgrad_args& a, float* workspace, cudaStream_t st) {
+    WgTcGeom g;
+    if (!wg_geometry(a, g)) return IBINN_EINVAL;
+    if (!workspace) return IBINN_ENULL;
+    int e = ibinn_set_smem(wgrad_tc_kernel, g.smem_bytes);
+    if (e) return e;
+    IBINN_LAUNCH(wgrad_tc_kernel, dim3(g.ncta), dim3(WT_THREADS), g.smem_bytes, st, a, g, workspace);
+    e = ibinn_launch_status();
+    if (e) return e;
+    int nb = (g.rec_floats + 31) / 32;
+    if (nb > 148 * 8) nb = 148 * 8;
+    IBINN_LAUNCH(wgrad_reduce_kernel, dim3(nb), dim3(IBINN_THREADS), 0, st, workspace, g.ncta, g.rec_floats, a.dw, a.dbias, a.Cout, a.Cin, g.kk);
+    return ibinn_launch_status();
+}
+
+#else
+bool wgrad_tc_supported(const ibinn_wgrad_args&) { return false; }
+int64_t wgrad_tc_workspace_floats(const ibinn_wgrad_args&) { return 0; }
+int wgrad_tc_launch(const ibinn_wgrad_args&, float*, cudaStream_t) { return IBINN_EINVAL; }
+#endif

@@ -143,6 +143,10 @@ def conv_wgrad(g, x, dw, ksize, stride=1, *, g_pre=PRE_NONE, gh=None, g_bn=None,
     a.x_mask = ptr(x_mask)
     a.dw, a.dbias = ptr(dw), ptr(dbias)
     a.B, a.Cin, a.Cout, a.Hin, a.Win, a.Hout, a.Wout, a.ksize, a.stride = B, Cin, Cout, Hin, Win, Hout, Wout, ksize, stride
+    nws = _lib.lib().ibinn_conv_wgrad_workspace_floats(ctypes.byref(a))
+    if nws > 0:
+        ws = torch.empty(int(nws), dtype=torch.float32, device=g.device)
+        a.workspace = ptr(ws)
     if _lib._profiler is not None:
         _lib.set_tag('k%d s%d %d->%d @%dx%d' % (ksize, stride, Cin, Cout, Hout, Wout))
     check(_lib.lib().ibinn_conv_wgrad(ctypes.byref(a), stream(g)), 'conv_wgrad')

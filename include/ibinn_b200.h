@@ -118,12 +118,15 @@ typedef struct ibinn_wgrad_args {
     const float* x;  int64_t x_bs;      /* conv input before its pre-op (B,Cin,Hin,Win) */
     int32_t x_pre;                      /* NONE | RELU | BN_RELU */
     ibinn_bn_ref x_bn; const float* x_mask;
-    float* dw;                          /* (Cout,Cin,KS,KS), ACCUMULATED into (atomics) */
+    float* dw;                          /* (Cout,Cin,KS,KS), ACCUMULATED into */
     float* dbias;                       /* (Cout) accumulated, or NULL */
     int32_t B, Cin, Cout, Hin, Win, Hout, Wout, ksize, stride;
+    float* workspace;                   /* ibinn_conv_wgrad_workspace_floats() floats (per-CTA partial records), or NULL if 0 */
 } ibinn_wgrad_args;
 
 size_t ibinn_sizeof_wgrad_args(void);
+/* floats of `workspace` this call needs (0: CUDA-core kernel, accumulates with atomics) */
+int64_t ibinn_conv_wgrad_workspace_floats(const ibinn_wgrad_args* a);
 int ibinn_conv_wgrad(const ibinn_wgrad_args* a, ibinn_stream_t stream);
 
 /* ---------------------------------------------------------------- AIO_Block coupling
