@@ -35,7 +35,16 @@ class ConvArgs(Structure):
                 ('save_mean', c_void_p), ('save_invstd', c_void_p), ('running_mean', c_void_p), ('running_var', c_void_p),
                 ('num_batches_tracked', c_void_p), ('momentum', c_float), ('bn_eps', c_float),
                 ('m_h', c_void_p), ('m_bs', c_int64), ('m_bn', BnRef), ('m_drop', c_void_p), ('sums_out', c_void_p),
-                ('m_dgamma', c_void_p), ('m_dbeta', c_void_p), ('partials', c_void_p), ('counter', c_void_p), ('wprep', c_void_p)]
+                ('m_dgamma', c_void_p), ('m_dbeta', c_void_p), ('partials', c_void_p), ('counter', c_void_p), ('wprep', c_void_p), ('wprep_ready', c_int32)]
+
+
+class WprepDesc(Structure):
+    _fields_ = [('w', c_void_p), ('out', c_void_p), ('Cin', c_int32), ('Cout', c_int32), ('ksize', c_int32), ('transposed', c_int32)]
+
+
+class WreduceDesc(Structure):
+    _fields_ = [('partials', c_void_p), ('dw', c_void_p), ('dbias', c_void_p), ('ncta', c_int32), ('rec_floats', c_int32),
+                ('Cout', c_int32), ('Cin', c_int32), ('kk', c_int32)]
 
 
 class WgradArgs(Structure):
@@ -44,7 +53,7 @@ class WgradArgs(Structure):
                 ('x', c_void_p), ('x_bs', c_int64), ('x_pre', c_int32), ('x_bn', BnRef), ('x_mask', c_void_p),
                 ('dw', c_void_p), ('dbias', c_void_p),
                 ('B', c_int32), ('Cin', c_int32), ('Cout', c_int32), ('Hin', c_int32), ('Win', c_int32), ('Hout', c_int32),
-                ('Wout', c_int32), ('ksize', c_int32), ('stride', c_int32), ('workspace', c_void_p)]
+                ('Wout', c_int32), ('ksize', c_int32), ('stride', c_int32), ('workspace', c_void_p), ('defer_reduce', c_int32)]
 
 
 P, I, F, L = c_void_p, c_int, c_float, c_int64
@@ -57,9 +66,12 @@ _SIGNATURES = {
     'ibinn_conv_partials_floats': ([POINTER(ConvArgs)], c_int64),
     'ibinn_conv_wprep_floats': ([POINTER(ConvArgs)], c_int64),
     'ibinn_conv_forward': ([POINTER(ConvArgs), P], c_int),
+    'ibinn_wprep_many': ([P, I, P], c_int),
     'ibinn_sizeof_wgrad_args': ([], c_size_t),
     'ibinn_conv_wgrad_workspace_floats': ([POINTER(WgradArgs)], c_int64),
     'ibinn_conv_wgrad': ([POINTER(WgradArgs), P], c_int),
+    'ibinn_conv_wgrad_records': ([POINTER(WgradArgs), POINTER(c_int32), POINTER(c_int32)], c_int),
+    'ibinn_wgrad_reduce_many': ([P, I, P], c_int),
     'ibinn_aio_coupling_forward': ([P, P, P, P, P, P, P, I, I, I, I, F, F, P], c_int),
     'ibinn_aio_coupling_backward': ([P] * 14 + [I, I, I, I, F, F, P], c_int),
     'ibinn_aio_unpermute': ([P, P, P, P, P, I, I, I, I, P], c_int),

@@ -121,6 +121,26 @@ __global__ void __launch_bounds__(IBINN_THREADS) wprep_kernel(const float* __res
     }
 }
 
+// the same for a whole table of layers: blockIdx.y = layer
+__global__ void __launch_bounds__(IBINN_THREADS) wprep_many_kernel(const ibinn_wprep_desc* __restrict__ table) {
+    const ibinn_wprep_desc d = table[blockIdx.y];
+    const int kk = d.ksize * d.ksize, cin_p = (d.Cin + 7) & ~7, np = (d.Cout + 15) & ~15;
+    const int per_tap = (cin_p / 4) * np * 4;
+    const int total = kk * per_tap;
+    for (int e = blockIdx.x * IBINN_THREADS + threadIdx.x; e < total; e += gridDim.x * IBINN_THREADS) {
+        const int i = e & 3, n = (e >> 2) % np, k4 = (e >> 2) / np % (cin_p / 4), tap = e / per_tap;
+        const int ci = k4 * 4 + i;
+        float v = 0.f;
+        if (n < d.Cout && ci < d.Cin)
+            v = d.transposed ? __ldg(d.w + ((size_t)ci * d.Cout + n) * kk + (kk - 1 - tap)) : __ldg(d.w + ((size_t)n * d.Cin + ci) * kk + tap);
+        float hi, lo;
+        tc::split_tf32(v, hi, lo);
+        const size_t o = (size_t)tap * 2 * per_tap + (size_t)(k4 * np + n) * 4 + i;
+        d.out[o] = hi;
+        d.out[o + per_tap] = lo;
+    }
+}
+
 __device__ __forceinline__ float tc_invstd(const ibinn_bn_ref& r, int c) {
     const float s = r.scale[c];
     return r.scale_is_variance ? rsqrtf(s + r.eps) : s;
@@ -586,12 +606,15 @@ int conv_tc_launch(const ibinn_conv_args& a, cudaStream_t st) {
     if (!tc_geometry(a, g)) return IBINN_EINVAL;
     if (!a.wprep) return IBINN_ENULL;
     if (((uintptr_t)a.wprep & 15) != 0) return IBINN_EALIGN;
-    const int total = g.kk * (g.cin_p / 4) * g.np * 4;
-    int nb = (total + IBINN_THREADS - 1) / IBINN_THREADS;
-    if (nb > 148) nb = 148;
-    IBINN_LAUNCH(wprep_kernel, dim3(nb), dim3(IBINN_THREADS), 0, st, a.w, a.wprep, a.Cin, a.Cout, g.cin_p, g.np, g.kk, a.w_transposed);
-    int e = ibinn_launch_status();
-    if (e) return e;
+    int e = 0;
+    if (!a.wprep_ready) {
+        const int total = g.kk * (g.cin_p / 4) * g.np * 4;
+        int nb = (total + IBINN_THREADS - 1) / IBINN_THREADS;
+        if (nb > 148) nb = 148;
+        IBINN_LAUNCH(wprep_kernel, dim3(nb), dim3(IBINN_THREADS), 0, st, a.w, a.wprep, a.Cin, a.Cout, g.cin_p, g.np, g.kk, a.w_transposed);
+        e = ibinn_launch_status();
+        if (e) return e;
+    }
 #define TC_CASE(PRE_, EPI_) if (a.pre == PRE_ && a.epi == EPI_) return tc_launch_inst<PRE_, EPI_>(a, g, st);
     TC_CASE(0, 0) TC_CASE(0, 1) TC_CASE(0, 2) TC_CASE(0, 3)
     TC_CASE(1, 0) TC_CASE(1, 1) TC_CASE(1, 2) TC_CASE(1, 3)
@@ -601,9 +624,19 @@ int conv_tc_launch(const ibinn_conv_args& a, cudaStream_t st) {
     return IBINN_EINVAL;
 }
 
+extern "C" int ibinn_wprep_many(const ibinn_wprep_desc* table, int n, ibinn_stream_t stream) {
+    int e = ibinn_check_device();
+    if (e) return e;
+    if (!table) return IBINN_ENULL;
+    if (n <= 0 || n > 65535) return IBINN_EINVAL;
+    IBINN_LAUNCH(wprep_many_kernel, dim3(8, n), dim3(IBINN_THREADS), 0, (cudaStream_t)stream, table);
+    return ibinn_launch_status();
+}
+
 #else  // IBINN_EMU: the simulator build has no tensor cores; conv.cu keeps everything on its CUDA-core kernel
 bool conv_tc_supported(const ibinn_conv_args&) { return false; }
 int64_t conv_tc_partials_floats(const ibinn_conv_args&) { return 0; }
 int64_t conv_tc_wprep_floats(const ibinn_conv_args&) { return 0; }
 int conv_tc_launch(const ibinn_conv_args&, cudaStream_t) { return IBINN_EINVAL; }
+extern "C" int ibinn_wprep_many(const ibinn_wprep_desc*, int, ibinn_stream_t) { return IBINN_EINVAL; }
 #endif

@@ -462,7 +462,59 @@ __global__ void __launch_bounds__(IBINN_THREADS) wgrad_reduce_kernel(const float
     }
 }
 
+// the same for a table of layers: blockIdx.y = layer
+__global__ void __launch_bounds__(IBINN_THREADS) wgrad_reduce_many_kernel(const ibinn_wreduce_desc* __restrict__ table) {
+    __shared__ float s_part[8][33];
+    const ibinn_wreduce_desc d = table[blockIdx.y];
+    const int n = d.kk * d.Cout * d.Cin;
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    for (int e0 = blockIdx.x * 32; e0 < d.rec_floats; e0 += gridDim.x * 32) {
+        const int e = e0 + lane;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        if (e < d.rec_floats) {
+            int c = slice;
+            for (; c + 24 < d.ncta; c += 32) {
+                s0 += __ldg(d.partials + (size_t)c * d.rec_floats + e);
+                s1 += __ldg(d.partials + (size_t)(c + 8) * d.rec_floats + e);
+                s2 += __ldg(d.partials + (size_t)(c + 16) * d.rec_floats + e);
+                s3 += __ldg(d.partials + (size_t)(c + 24) * d.rec_floats + e);
+            }
+            for (; c < d.ncta; c += 8) s0 += __ldg(d.partials + (size_t)c * d.rec_floats + e);
+        }
+        __syncthreads();
+        s_part[slice][lane] = (s0 + s1) + (s2 + s3);
+        __syncthreads();
+        if (slice == 0 && e < d.rec_floats) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s += s_part[k][lane];
+            if (e < n) {
+                const int ci = e % d.Cin, co = (e / d.Cin) % d.Cout, tap = e / (d.Cin * d.Cout);
+                d.dw[((size_t)co * d.Cin + ci) * d.kk + tap] += s;
+            } else if (d.dbias && e - n < d.Cout) d.dbias[e - n] += s;
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int ibinn_conv_wgrad_records(const ibinn_wgrad_args* a, int32_t* ncta, int32_t* rec_floats) {
+    if (!a || !ncta || !rec_floats) return IBINN_ENULL;
+    WgTcGeom g;
+    if (!wg_geometry(*a, g)) return IBINN_EINVAL;
+    *ncta = g.ncta;
+    *rec_floats = g.rec_floats;
+    return 0;
+}
+
+extern "C" int ibinn_wgrad_reduce_many(const ibinn_wreduce_desc* table, int n, ibinn_stream_t stream) {
+    int e = ibinn_check_device();
+    if (e) return e;
+    if (!table) return IBINN_ENULL;
+    if (n <= 0 || n > 65535) return IBINN_EINVAL;
+    IBINN_LAUNCH(wgrad_reduce_many_kernel, dim3(48, n), dim3(IBINN_THREADS), 0, (cudaStream_t)stream, table);
+    return ibinn_launch_status();
+}
 
 bool wgrad_tc_supported(const ibinn_wgrad_args& a) {
     WgTcGeom g;
@@ -483,7 +535,7 @@ int wgrad_tc_launch(const ibinn_wgrad_args& a, float* workspace, cudaStream_t st
     if (e) return e;
     IBINN_LAUNCH(wgrad_tc_kernel, dim3(g.ncta), dim3(WT_THREADS), g.smem_bytes, st, a, g, workspace);
     e = ibinn_launch_status();
-    if (e) return e;
+    if (e || a.defer_reduce) return e;
     int nb = (g.rec_floats + 31) / 32;
     if (nb > 148 * 8) nb = 148 * 8;
     IBINN_LAUNCH(wgrad_reduce_kernel, dim3(nb), dim3(IBINN_THREADS), 0, st, workspace, g.ncta, g.rec_floats, a.dw, a.dbias, a.Cout, a.Cin, g.kk);
@@ -494,4 +546,6 @@ int wgrad_tc_launch(const ibinn_wgrad_args& a, float* workspace, cudaStream_t st
 bool wgrad_tc_supported(const ibinn_wgrad_args&) { return false; }
 int64_t wgrad_tc_workspace_floats(const ibinn_wgrad_args&) { return 0; }
 int wgrad_tc_launch(const ibinn_wgrad_args&, float*, cudaStream_t) { return IBINN_EINVAL; }
+extern "C" int ibinn_conv_wgrad_records(const ibinn_wgrad_args*, int32_t*, int32_t*) { return IBINN_EINVAL; }
+extern "C" int ibinn_wgrad_reduce_many(const ibinn_wreduce_desc*, int, ibinn_stream_t) { return IBINN_EINVAL; }
 #endif

@@ -82,6 +82,83 @@ class FlatParams:
         return nc
 
 
+class WeightPrep:
+    """Tensor-core operand images (hi/lo tf32 split, per-tap K-major) of every stride-1 subnet filter, in
+    both orientations (forward / dgrad), refreshed by ONE launch per step instead of one per convolution."""
+
+    def __init__(self, model):
+        import ctypes
+        import numpy as np
+        from . import _lib
+        from .subnets import ConvSubnet
+        dev = model.mu.device
+        descs, self.params, self._keep = [], [], []
+        for m in model.inn.modules():
+            if not isinstance(m, ConvSubnet):
+                continue
+            for conv in (m.conv1, m.conv2, m.conv3):
+                if conv.stride[0] != 1:
+                    continue
+                w = conv.weight
+                entry = {'valid': False}
+                for tr in (False, True):
+                    n = ops.conv_wprep_floats(w, tr, 8, 8)
+                    if n <= 0:
+                        continue
+                    buf = torch.empty(n, dtype=torch.float32, device=dev)
+                    entry[tr] = buf
+                    co, ci, ks, _ = w.shape
+                    d = _lib.WprepDesc(w.data_ptr(), buf.data_ptr(), co if tr else ci, ci if tr else co, ks, int(tr))
+                    descs.append(bytes(d))
+                if False in entry and True in entry:
+                    w._ibinn_wprep = entry
+                    self.params.append(w)
+        self.n = len(descs)
+        raw = np.frombuffer(b''.join(descs), dtype=np.uint8).copy() if descs else np.zeros(1, np.uint8)
+        self.table = torch.from_numpy(raw).to(dev)
+
+    def refresh(self):
+        if self.n:
+            ops.wprep_many(self.table, self.n, self.table)
+            for w in self.params:
+                w._ibinn_wprep['valid'] = True
+
+    def invalidate(self):
+        for w in self.params:
+            w._ibinn_wprep['valid'] = False
+
+
+class MaskPool:
+    """All dropout masks of one step (Dropout2d (B,width) per stage-2 subnet, Dropout (B,fc_width) per FC subnet) live
+    in one buffer per drop probability and are redrawn with three in-place launches per probability."""
+
+    def __init__(self, model, batch_size):
+        from .subnets import ConvSubnet, FCSubnet
+        dev = model.mu.device
+        by_p = {}
+        for m in model.inn.modules():
+            if isinstance(m, (ConvSubnet, FCSubnet)) and m.p_drop > 0.:
+                width = m.conv1.weight.shape[0] if isinstance(m, ConvSubnet) else m.lin1.weight.shape[0]
+                by_p.setdefault(m.p_drop, []).append((m, batch_size * width, (batch_size, width)))
+        self.pools = []
+        for p, items in by_p.items():
+            buf = torch.zeros(sum(n for _, n, _ in items), dtype=torch.float32, device=dev)
+            o = 0
+            for m, n, shape in items:
+                m._ibinn_mask = buf[o:o + n].view(shape)
+                o += n
+            self.pools.append((p, buf))
+        self.modules = [m for items in by_p.values() for m, _, _ in items]
+
+    def redraw(self):
+        for p, buf in self.pools:
+            buf.uniform_()
+            buf.ge_(p)
+            buf.mul_(1. / (1. - p))
+        for m in self.modules:
+            m._ibinn_mask_fresh = True
+
+
 def beta_weights(beta, train_nll=True):
     """reference train.py:88-92"""
     if not train_nll:
@@ -110,6 +187,8 @@ class TrainStep:
         self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
         self.flat = FlatParams(model)
         dev = model.mu.device
+        self.wprep = WeightPrep(model) if dev.type == 'cuda' else None      # after FlatParams: the filters have their final addresses
+        self.masks = MaskPool(model, batch_size)
         self.x = torch.zeros((batch_size,) + tuple(model.dims), dtype=torch.float32, device=dev)
         self.y = torch.zeros((batch_size, model.n_classes), dtype=torch.float32, device=dev)
         self.use_graph = bool(use_graph) and dev.type == 'cuda'
@@ -120,12 +199,22 @@ class TrainStep:
     # -- pieces ---------------------------------------------------------------------------------
     def _fwd_bwd(self):
         self.flat.zero_grad()
+        if self.wprep is not None:
+            self.wprep.refresh()
+        if self.model.inn.training:
+            self.masks.redraw()
         losses = self.model(self.x, self.y)
         if self.class_nll:
             loss = 2. * losses['L_cNLL_tr']
         else:
             loss = self.bx * losses['L_x_tr'] - self.by * losses['L_y_tr']
-        loss.backward()
+        ops.DEFERRED_WGRAD = pending = []
+        try:
+            loss.backward()
+        finally:
+            ops.DEFERRED_WGRAD = None
+        self._pinned = ops.flush_deferred_wgrad(pending, self.x, getattr(self, '_pinned', None))
+        self._pending = pending            # keeps the record workspaces alive until the reduction has run
         self.out = {k: losses[k].detach() for k in ('L_x_tr', 'L_y_tr', 'acc_tr', 'L_cNLL_tr')}
 
     def _reduce(self):
@@ -135,6 +224,8 @@ class TrainStep:
     def _update(self):
         # the all-reduce sums; the mean gradient is grad / world (folded into the clip and the update)
         nc = self.flat.clip_and_step(self.clip, grad_scale=1.0 / self.world)
+        if self.wprep is not None:
+            self.wprep.invalidate()         # filters changed: images are stale until the next refresh
         self.out['grad_norm'] = nc[0] / self.world if self.world > 1 else nc[0]
 
     def _eager(self):

@@ -98,9 +98,17 @@ class ReversibleGraphNet(nn.Module):
     def log_jacobian(self, x=None, c=None, rev=False, run_forward=True, intermediate_outputs=False):
         if run_forward:
             self.forward(x, rev=rev)
-        total = 0.
+        const, tens = 0., []
         for k, h in self._node_inputs.items():
-            total = total + self.module_list[k].jacobian([h], rev=rev)
-        return total
+            j = self.module_list[k].jacobian([h], rev=rev)
+            if torch.is_tensor(j):
+                tens.append(j)
+            else:
+                const = const + j
+        if not tens:
+            return const
+        if len(tens) == 1:
+            return tens[0] + const
+        return torch.stack(tens).sum(0) + const          # two kernels instead of one add per node
 
     jacobian = log_jacobian

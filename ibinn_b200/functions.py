@@ -42,6 +42,15 @@ def dropout_mask(shape, p, ref):
     return (torch.rand(shape, device=ref.device) >= p).to(torch.float32) / (1. - p)
 
 
+def pooled_mask(net, shape, p, ref):
+    """engine.MaskPool draws all dropout masks of a step with three launches; without it, one mask per call."""
+    m = getattr(net, '_ibinn_mask', None)
+    if m is not None and getattr(net, '_ibinn_mask_fresh', False) and tuple(m.shape) == tuple(shape) and m.device == ref.device:
+        net._ibinn_mask_fresh = False          # one use per redraw: a forward outside TrainStep draws its own mask
+        return m
+    return dropout_mask(shape, p, ref)
+
+
 # ------------------------------------------------------------------------------------ conv subnet
 
 def conv_subnet_forward(net, x, training, mask=None):
@@ -63,7 +72,7 @@ def conv_subnet_forward(net, x, training, mask=None):
         h2 = ops.conv_forward(h1, net.conv2.weight, 3, stride2, pre=PRE_BN_RELU, pre_bn=r1, epi=EPI_BNSTATS, stats=stats(bn2, 1))
         r2 = BN(sv[2], sv[3], bn2.weight, bn2.bias, bn2.eps, False)
         if mask is None and net.p_drop > 0.:
-            mask = dropout_mask((x.shape[0], width), net.p_drop, x)
+            mask = pooled_mask(net, (x.shape[0], width), net.p_drop, x)
     else:
         h1 = ops.conv_forward(x, net.conv1.weight, 3, 1, pre=pre0)
         r1 = BN(bn1.running_mean, bn1.running_var, bn1.weight, bn1.bias, bn1.eps, True)
@@ -235,7 +244,7 @@ def fc_subnet_forward(net, x, training, mask=None):
     """fc_constr (reference inn_architecture.py:112-120): Linear -> ReLU -> Dropout -> Linear."""
     h = ops.linear_forward(x, net.lin1.weight, net.lin1.bias)
     if training and mask is None and net.p_drop > 0.:
-        mask = dropout_mask(h.shape, net.p_drop, h)
+        mask = pooled_mask(net, h.shape, net.p_drop, h)
     if not training:
         mask = None
     r = ops.linear_forward(h, net.lin2.weight, net.lin2.bias, x_pre=1, x_mask=mask)

@@ -108,8 +108,12 @@ def conv_forward(x, w, ksize, stride=1, *, cout=None, pre=PRE_NONE, pre_bn=None,
     keep = None
     nw = L.ibinn_conv_wprep_floats(ctypes.byref(a))
     if nw > 0:
-        wprep = torch.empty(int(nw), dtype=torch.float32, device=x.device)
-        a.wprep = ptr(wprep)
+        cached = getattr(w, '_ibinn_wprep', None)          # engine.WeightPrep: operand images prepared once per step
+        if cached is not None and cached['valid'] and cached[bool(w_transposed)].numel() == nw:
+            a.wprep, a.wprep_ready = ptr(cached[bool(w_transposed)]), 1
+        else:
+            wprep = torch.empty(int(nw), dtype=torch.float32, device=x.device)
+            a.wprep = ptr(wprep)
     if epi in (EPI_BNSTATS, EPI_MASKSTATS):
         n = L.ibinn_conv_partials_floats(ctypes.byref(a))
         if n < 0:
@@ -122,6 +126,39 @@ def conv_forward(x, w, ksize, stride=1, *, cout=None, pre=PRE_NONE, pre_bn=None,
     check(L.ibinn_conv_forward(ctypes.byref(a), stream(x)), 'conv_forward')
     _lib.set_tag('')
     return out
+
+
+DEFERRED_WGRAD = None       # list while engine.TrainStep collects deferred wgrad reductions, else None
+
+
+def flush_deferred_wgrad(entries, ref, pinned):
+    """one launch for all deferred wgrad record reductions; `pinned` = reusable pinned uint8 staging tensor or None"""
+    import numpy as np
+    if not entries:
+        return pinned
+    raw = b''.join(bytes(d) for _, d in entries)
+    if pinned is None or pinned.numel() < len(raw):
+        pinned = torch.empty(len(raw), dtype=torch.uint8).pin_memory()
+    pinned[:len(raw)].copy_(torch.from_numpy(np.frombuffer(raw, dtype=np.uint8).copy()))
+    table = torch.empty(len(raw), dtype=torch.uint8, device=ref.device)
+    table.copy_(pinned[:len(raw)], non_blocking=True)
+    check(_lib.lib().ibinn_wgrad_reduce_many(ptr(table, torch.uint8), len(entries), stream(ref)), 'wgrad_reduce_many')
+    return pinned
+
+
+def conv_wprep_floats(w, transposed, H, W):
+    """size of the tensor-core operand image of filter tensor `w` (0 if that conv shape runs on the CUDA-core kernel)"""
+    a = ConvArgs()
+    co, ci, ks, _ = w.shape
+    if transposed:
+        co, ci = ci, co
+    a.B, a.Cin, a.Cout, a.Hs, a.Ws, a.Hout, a.Wout, a.Hin, a.Win = 1, ci, co, H, W, H, W, H, W
+    a.ksize, a.stride = ks, 1
+    return int(_lib.lib().ibinn_conv_wprep_floats(ctypes.byref(a)))
+
+
+def wprep_many(table, n, ref):
+    check(_lib.lib().ibinn_wprep_many(ptr(table, torch.uint8), n, stream(ref)), 'wprep_many')
 
 
 def conv_wgrad(g, x, dw, ksize, stride=1, *, g_pre=PRE_NONE, gh=None, g_bn=None, g_sums=None, x_pre=PRE_NONE, x_bn=None,
@@ -147,6 +184,12 @@ def conv_wgrad(g, x, dw, ksize, stride=1, *, g_pre=PRE_NONE, gh=None, g_bn=None,
     if nws > 0:
         ws = torch.empty(int(nws), dtype=torch.float32, device=g.device)
         a.workspace = ptr(ws)
+        if DEFERRED_WGRAD is not None:
+            # engine.TrainStep: leave the per-CTA records in `ws`; one launch sums the records of all layers later
+            ncta, rec = ctypes.c_int32(), ctypes.c_int32()
+            check(_lib.lib().ibinn_conv_wgrad_records(ctypes.byref(a), ctypes.byref(ncta), ctypes.byref(rec)), 'conv_wgrad_records')
+            a.defer_reduce = 1
+            DEFERRED_WGRAD.append((ws, _lib.WreduceDesc(ptr(ws), ptr(dw), ptr(dbias), ncta.value, rec.value, Cout, Cin, ksize * ksize)))
     if _lib._profiler is not None:
         _lib.set_tag('k%d s%d %d->%d @%dx%d' % (ksize, stride, Cin, Cout, Hout, Wout))
     check(_lib.lib().ibinn_conv_wgrad(ctypes.byref(a), stream(g)), 'conv_wgrad')

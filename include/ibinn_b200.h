@@ -101,6 +101,7 @@ typedef struct ibinn_conv_args {
     float* partials;                             /* ibinn_conv_partials_floats() floats (BNSTATS, MASKSTATS) */
     uint32_t* counter;
     float* wprep;                                /* ibinn_conv_wprep_floats() floats, 16-byte aligned: tensor-core operand image of w */
+    int32_t wprep_ready;                         /* 1: `wprep` already holds the image of `w` (ibinn_wprep_many), skip the prep launch */
 } ibinn_conv_args;
 
 size_t ibinn_sizeof_conv_args(void);
@@ -109,6 +110,15 @@ int64_t ibinn_conv_partials_floats(const ibinn_conv_args* a);
 /* number of floats `wprep` must hold (0: this call runs on the CUDA-core kernel and needs none) */
 int64_t ibinn_conv_wprep_floats(const ibinn_conv_args* a);
 int ibinn_conv_forward(const ibinn_conv_args* a, ibinn_stream_t stream);
+
+/* Batched filter preparation for the tensor-core convolutions: one launch turns n raw filter tensors into
+ * their operand images (hi/lo tf32 split, per-tap K-major rows).  `table` is a DEVICE array. */
+typedef struct ibinn_wprep_desc {
+    const float* w;      /* (Cout,Cin,KS,KS), or (Cin,Cout,KS,KS) read flipped when transposed */
+    float* out;          /* ibinn_conv_wprep_floats() floats */
+    int32_t Cin, Cout, ksize, transposed;
+} ibinn_wprep_desc;
+int ibinn_wprep_many(const ibinn_wprep_desc* table, int n, ibinn_stream_t stream);
 
 typedef struct ibinn_wgrad_args {
     const float* g;  int64_t g_bs;      /* grad w.r.t. conv output (B,Cout,Hout,Wout)        */
@@ -122,12 +132,21 @@ typedef struct ibinn_wgrad_args {
     float* dbias;                       /* (Cout) accumulated, or NULL */
     int32_t B, Cin, Cout, Hin, Win, Hout, Wout, ksize, stride;
     float* workspace;                   /* ibinn_conv_wgrad_workspace_floats() floats (per-CTA partial records), or NULL if 0 */
+    int32_t defer_reduce;               /* 1: leave the partial records in `workspace`; the caller sums them later with ibinn_wgrad_reduce_many */
 } ibinn_wgrad_args;
 
 size_t ibinn_sizeof_wgrad_args(void);
 /* floats of `workspace` this call needs (0: CUDA-core kernel, accumulates with atomics) */
 int64_t ibinn_conv_wgrad_workspace_floats(const ibinn_wgrad_args* a);
 int ibinn_conv_wgrad(const ibinn_wgrad_args* a, ibinn_stream_t stream);
+/* Deferred reduction of the tensor-core wgrad records of many layers in ONE launch.  `ibinn_conv_wgrad_records`
+ * tells how the records of a call are laid out; `table` is a DEVICE array. */
+typedef struct ibinn_wreduce_desc {
+    const float* partials; float* dw; float* dbias;
+    int32_t ncta, rec_floats, Cout, Cin, kk;
+} ibinn_wreduce_desc;
+int ibinn_conv_wgrad_records(const ibinn_wgrad_args* a, int32_t* ncta, int32_t* rec_floats);
+int ibinn_wgrad_reduce_many(const ibinn_wreduce_desc* table, int n, ibinn_stream_t stream);
 
 /* ---------------------------------------------------------------- AIO_Block coupling
  * Replaces reference all_in_one_block.py:61-111 (`log_e`, `affine`, `permute`, `forward`):
