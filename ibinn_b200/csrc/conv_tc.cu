@@ -406,9 +406,27 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) conv_tc_kernel(const ibinn_con
             if (tid == 0 && j < 4) DBG(30 + 2 * j);
             if (STATS) s_valid[row] = valid ? 1.f : 0.f;
             const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + buf * g.np;
+            // mask / addend operands of the next 8 columns are fetched while the current 8 are processed
+            constexpr bool NEED_H = (EPI == IBINN_EPI_MASKSTATS || EPI == IBINN_EPI_RELUMASK);
+            float hn[8], an[8];
+            auto prefetch = [&](int c8n) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int c = c8n + i;
+                    hn[i] = 0.f; an[i] = 0.f;
+                    if (valid && c < p.Cout) {
+                        if (NEED_H) hn[i] = __ldg(p.m_h + mbase + (size_t)c * HWo);
+                        if ((EPI == IBINN_EPI_STORE || EPI == IBINN_EPI_RELUMASK) && p.addend) an[i] = p.addend[abase + (size_t)c * HWo];
+                    }
+                }
+            };
+            prefetch(0);
 #pragma unroll 1
             for (int c8 = 0; c8 < g.np; c8 += 8) {
-                float v[8];
+                float v[8], hc[8], ac[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { hc[i] = hn[i]; ac[i] = an[i]; }
+                if (c8 + 8 < g.np) prefetch(c8 + 8);
                 tc::tmem_ld8(taddr + c8, v);
                 tc::tmem_ld_wait();
 #pragma unroll
@@ -419,15 +437,15 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) conv_tc_kernel(const ibinn_con
                         o = v[i];
                         if (EPI == IBINN_EPI_STORE || EPI == IBINN_EPI_RELUMASK) { if (p.bias) o += __ldg(p.bias + c); }
                         if (EPI == IBINN_EPI_MASKSTATS) {
-                            const float h = __ldg(p.m_h + mbase + (size_t)c * HWo);
+                            const float h = hc[i];
                             o = fmaf(h, s_ea[c], s_eb[c]) > 0.f ? o : 0.f;
                             if (p.m_drop) o *= __ldg(p.m_drop + (size_t)bimg * p.Cout + c);
                             xh = (h - s_em[c]) * s_ei[c];
                         } else if (EPI == IBINN_EPI_RELUMASK) {
-                            o = __ldg(p.m_h + mbase + (size_t)c * HWo) > 0.f ? o : 0.f;
+                            o = hc[i] > 0.f ? o : 0.f;
                         }
                         float st = o;
-                        if (EPI == IBINN_EPI_STORE || EPI == IBINN_EPI_RELUMASK) { if (p.addend) st += p.addend[abase + (size_t)c * HWo]; }
+                        if (EPI == IBINN_EPI_STORE || EPI == IBINN_EPI_RELUMASK) st += ac[i];
                         p.y[obase + (size_t)c * HWo] = st;
                     }
                     if (STATS) {
