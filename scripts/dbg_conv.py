@@ -17,8 +17,4 @@ def run(Cin, Cout, H, ks):
     print('   tile 0 mma phase: %d cycles, %.2f us -> %.2f GHz' % (buf[51]-buf[50], r(11)-r(10), (buf[51]-buf[50])/1000./max(r(11)-r(10),1e-9)))
     for j in range(2):
         print('   tile %d: load %.2f-%.2f  mma %.2f-%.2f  epi %.2f-%.2f' % (j, r(20+2*j), r(21+2*j), r(10+2*j), r(11+2*j), r(30+2*j), r(31+2*j)))
-for rep in range(3):
-    run(64,64,8,3); run(32,32,16,3); run(16,16,32,3)
-    x = torch.randn(8192, 8192, device=dev)
-    for _ in range(20): y = x @ x
-    torch.cuda.synchronize()
+run(64,64,8,3); run(32,32,16,3); run(6,32,16,3); run(16,16,32,3)

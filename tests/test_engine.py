@@ -58,7 +58,7 @@ def test_train_step_matches_torch_loop(dev):
     m1 = _model(dev)
     m2 = copy.deepcopy(m1)
     step = TrainStep(m2, batch_size=4, beta=1.0, clip=8., use_graph=False)
-    for it in range(3):
+    for it in range(2):
         x, y = _batch(4, 10, gen)
         x, y = x.to(dev), y.to(dev)
         out = m1(x, y)

@@ -13,6 +13,8 @@ SHAPES = [(128, 1536, 1024), (128, 1024, 3072), (5, 392, 1024), (64, 1024, 784),
 
 @pytest.mark.parametrize('B,K,N', SHAPES)
 def test_linear_forward_dgrad_wgrad(dev, B, K, N):
+    if dev.type == 'cpu' and B * K * N > 3e7:
+        pytest.skip('full-size FC GEMM: B200 only (the simulator covers the small shapes)')
     g = torch.Generator().manual_seed(B + K + N)
     x = torch.randn(B, K, generator=g)
     w = torch.randn(N, K, generator=g) * 0.1
