@@ -141,12 +141,14 @@ def main():
     step.load(xh, yh)
 
     # ---- per-kernel-class device times: one eager step bracketed with CUDA events (after a warm step)
+    side, step.side_streams = step.side_streams, None      # serialised on one stream: every launch gets its own event pair
     step._eager()
     torch.cuda.synchronize()
     _lib.profile(True)
     n0 = _lib.lib().ibinn_launch_count()
     step._eager()
     prof = _lib.profile(False)
+    step.side_streams = side
     table = prof.summary()
     eager_launches = int(_lib.lib().ibinn_launch_count() - n0)
     total_ms = sum(t for t, _ in table.values())

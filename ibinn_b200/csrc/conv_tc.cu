@@ -56,9 +56,9 @@ static bool tc_geometry(const ibinn_conv_args& a, TcGeom& g) {
     g.cin_p = (a.Cin + 7) & ~7;
     g.np = (a.Cout + 15) & ~15;
     g.lbo_a = g.npos * 16;
-    g.lbo_b = g.np * 16;
+    g.lbo_b = 2 * g.np * 16;                          // hi and lo rows of one k-chunk are adjacent
     g.a_bytes = (g.cin_p / 4) * g.lbo_a;              // one of hi / lo
-    g.tap_bytes = 2 * (g.cin_p / 4) * g.lbo_b;        // hi + lo of one tap
+    g.tap_bytes = (g.cin_p / 4) * g.lbo_b;            // hi + lo of one tap
     if (g.lbo_a >= (1 << 18)) return false;
     g.nstat = a.epi == IBINN_EPI_BNSTATS ? 1 : a.epi == IBINN_EPI_MASKSTATS ? 2 : 0;
     const int stat_bytes = g.nstat * g.np * TP * 4;
@@ -92,8 +92,8 @@ static bool tc_geometry(const ibinn_conv_args& a, TcGeom& g) {
         }
     }
     if (!ok) return false;
-    const int cols = g.nbuf * g.np;
-    g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : 128;
+    const int cols = g.nbuf * 2 * g.np;               // per accumulator: [x_hi w_hi + x_lo w_hi | x_hi w_lo]
+    g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : 256;
     int per_sm = (int)((220 * 1024) / (g.smem_bytes + 2048));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 512 / g.tmem_cols) per_sm = 512 / g.tmem_cols;
@@ -102,7 +102,8 @@ static bool tc_geometry(const ibinn_conv_args& a, TcGeom& g) {
     return true;
 }
 
-// ---- weight preparation: raw filters -> per tap [hi|lo][k4][n][4] (canonical K-major rows of 16 bytes)
+// ---- weight preparation: raw filters -> per tap [k4][hi rows 0..np-1 | lo rows np..2np-1][4] (canonical K-major rows of
+// 16 bytes; hi and lo stacked along N so that ONE MMA of width 2*np forms x_hi*w_hi and x_hi*w_lo side by side)
 __global__ void __launch_bounds__(IBINN_THREADS) wprep_kernel(const float* __restrict__ w, float* __restrict__ out, int Cin, int Cout,
                                                              int cin_p, int np, int kk, int transposed) {
     const int per_tap = (cin_p / 4) * np * 4;
@@ -115,9 +116,9 @@ __global__ void __launch_bounds__(IBINN_THREADS) wprep_kernel(const float* __res
             v = transposed ? __ldg(w + ((size_t)ci * Cout + n) * kk + (kk - 1 - tap)) : __ldg(w + ((size_t)n * Cin + ci) * kk + tap);
         float hi, lo;
         tc::split_tf32(v, hi, lo);
-        const size_t o = (size_t)tap * 2 * per_tap + (size_t)(k4 * np + n) * 4 + i;
+        const size_t o = (size_t)tap * 2 * per_tap + (size_t)(k4 * 2 * np + n) * 4 + i;
         out[o] = hi;
-        out[o + per_tap] = lo;
+        out[o + np * 4] = lo;
     }
 }
 
@@ -135,9 +136,9 @@ __global__ void __launch_bounds__(IBINN_THREADS) wprep_many_kernel(const ibinn_w
             v = d.transposed ? __ldg(d.w + ((size_t)ci * d.Cout + n) * kk + (kk - 1 - tap)) : __ldg(d.w + ((size_t)n * d.Cin + ci) * kk + tap);
         float hi, lo;
         tc::split_tf32(v, hi, lo);
-        const size_t o = (size_t)tap * 2 * per_tap + (size_t)(k4 * np + n) * 4 + i;
+        const size_t o = (size_t)tap * 2 * per_tap + (size_t)(k4 * 2 * np + n) * 4 + i;
         d.out[o] = hi;
-        d.out[o + per_tap] = lo;
+        d.out[o + np * 4] = lo;
     }
 }
 
@@ -288,8 +289,10 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) conv_tc_kernel(const ibinn_con
         if (lane == 0) {
             const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wprep);
             if (g.resident) {
-                tc::mbar_arrive_expect_tx(&w_full[0], (uint32_t)g.kk * g.tap_bytes);
-                for (int t = 0; t < g.kk; ++t) tc::bulk_g2s(wst + (size_t)t * g.tap_bytes, src + (size_t)t * g.tap_bytes, g.tap_bytes, &w_full[0]);
+                for (int t = 0; t < g.kk; ++t) {
+                    tc::mbar_arrive_expect_tx(&w_full[t], (uint32_t)g.tap_bytes);
+                    tc::bulk_g2s(wst + (size_t)t * g.tap_bytes, src + (size_t)t * g.tap_bytes, g.tap_bytes, &w_full[t]);
+                }
             } else {
                 const int total = ntl * g.kk;
                 for (int gi = 0; gi < total; ++gi) {
@@ -306,21 +309,20 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) conv_tc_kernel(const ibinn_con
         // The whole warp walks the loop (descriptor arithmetic stays on the uniform datapath); one
         // elected lane issues the tcgen05 instructions.
         {
-            const uint32_t idesc = tc::idesc_tf32(TM, g.np);
+            // two MMAs per k-step: x_hi * [w_hi | w_lo] (N = 2 np) and x_lo * w_hi (N = np, onto the first np columns)
+            const uint32_t idesc2 = tc::idesc_tf32(TM, 2 * g.np), idesc1 = tc::idesc_tf32(TM, g.np);
             const uint64_t db0 = tc::smem_desc(tc::smem_u32(wst), g.lbo_b);
             const int nks = g.cin_p / 8;
-            const uint32_t b_lo_off = ((uint32_t)(g.cin_p / 4) * g.lbo_b) >> 4;
             const uint32_t a_step = (uint32_t)(2 * g.lbo_a) >> 4, b_step = (uint32_t)(2 * g.lbo_b) >> 4, st_step = (uint32_t)g.tap_bytes >> 4;
             int gi = 0;
             for (int j = 0; j < ntl; ++j) {
                 const int buf = j % g.nbuf, n = j / g.nbuf;
                 const uint32_t a_base = tc::smem_u32(tcs + (size_t)buf * 2 * g.a_bytes);
                 const uint64_t da_hi = tc::smem_desc(a_base, g.lbo_a), da_lo = tc::smem_desc(a_base + g.a_bytes, g.lbo_a);
-                const uint32_t acc_addr = tmem_d + buf * g.np;
+                const uint32_t acc_addr = tmem_d + buf * 2 * g.np;
                 if (n >= 1) tc::mbar_wait(&acc_empty[buf], (n - 1) & 1);      // epilogue has drained this accumulator
                 tc::mbar_wait(&a_full[buf], n & 1);                          // activation tile staged
                 if (j == 0) tc::mbar_wait(&a_help, 0);
-                if (g.resident && j == 0) tc::mbar_wait(&w_full[0], 0);
                 tc::fence_after_sync();
                 if (lane == 0 && j < 4) DBG(10 + 2 * j);
                 uint32_t acc = 0;
@@ -330,21 +332,24 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) conv_tc_kernel(const ibinn_con
                         s = gi % g.nst;
                         tc::mbar_wait(&w_full[s], (gi / g.nst) & 1);
                         tc::fence_after_sync();
+                    } else if (j == 0) {
+                        tc::mbar_wait(&w_full[t], 0);                        // resident filters land tap by tap
+                        tc::fence_after_sync();
                     }
                     const int dy = g.pad ? t / 3 - 1 : 0, dx = g.pad ? t % 3 - 1 : 0;
                     const uint32_t row_off = (uint32_t)(g.halo + dy * g.P + dx);          // 16-byte rows
-                    const uint64_t bh = db0 + (uint64_t)(s * st_step), bl = bh + b_lo_off;
-#pragma unroll 1
-                    for (int pass = 0; pass < 3; ++pass) {
-                        uint64_t da = (pass == 2 ? da_lo : da_hi) + row_off;
-                        uint64_t db = pass == 1 ? bl : bh;
+                    uint64_t dah = da_hi + row_off, dal = da_lo + row_off;
+                    uint64_t db = db0 + (uint64_t)(s * st_step);
 #pragma unroll 4
-                        for (int ks = 0; ks < nks; ++ks) {
-                            if (tc::elect_one()) tc::mma_tf32(acc_addr, da, db, idesc, acc != 0);
-                            acc = 1;
-                            da += a_step;
-                            db += b_step;
+                    for (int ks = 0; ks < nks; ++ks) {
+                        if (tc::elect_one()) {
+                            tc::mma_tf32(acc_addr, dah, db, idesc2, acc != 0);
+                            tc::mma_tf32(acc_addr, dal, db, idesc1, 1);
                         }
+                        acc = 1;
+                        dah += a_step;
+                        dal += a_step;
+                        db += b_step;
                     }
                     if (!g.resident) { if (tc::elect_one()) tc::mma_commit(&w_empty[s]); }
                 }
@@ -405,7 +410,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) conv_tc_kernel(const ibinn_con
             tc::fence_after_sync();
             if (tid == 0 && j < 4) DBG(30 + 2 * j);
             if (STATS) s_valid[row] = valid ? 1.f : 0.f;
-            const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + buf * g.np;
+            const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + buf * 2 * g.np;
             // mask / addend operands of the next 8 columns are fetched while the current 8 are processed
             constexpr bool NEED_H = (EPI == IBINN_EPI_MASKSTATS || EPI == IBINN_EPI_RELUMASK);
             float hn[8], an[8];
@@ -423,12 +428,15 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) conv_tc_kernel(const ibinn_con
             prefetch(0);
 #pragma unroll 1
             for (int c8 = 0; c8 < g.np; c8 += 8) {
-                float v[8], hc[8], ac[8];
+                float v[8], v2[8], hc[8], ac[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { hc[i] = hn[i]; ac[i] = an[i]; }
                 if (c8 + 8 < g.np) prefetch(c8 + 8);
                 tc::tmem_ld8(taddr + c8, v);
+                tc::tmem_ld8(taddr + g.np + c8, v2);
                 tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += v2[i];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int c = c8 + i;
@@ -524,36 +532,40 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) conv_tc_kernel(const ibinn_con
     const int c = tid / tpc, j = tid % tpc;
     const bool cval = (tid < 256) && (c < p.Cout) && (tid < cpad * tpc);
     const size_t rs = 2 * p.Cout + 4;
+    // One pass of independent loads (no loop-carried dependence but the sums): with per-CTA (n_b, mean_b, M2_b)
+    //   N = sum n_b, S1 = sum n_b mean_b, S2 = sum (M2_b + n_b mean_b^2),  mean = S1/N,  M2 = S2 - N mean^2
+    // evaluated in double from fp32 records (the cancellation costs log10(mean^2/var) of 16 digits).
+    double s0 = 0., s1 = 0., s2 = 0.;
+    if (cval) {
+        const float* rp = p.partials + (size_t)j * rs;
+        const size_t step = (size_t)tpc * rs;
+#pragma unroll 8
+        for (unsigned bb = j; bb < nblk; bb += tpc, rp += step) {
+            const float f0 = __ldcg(rp + 2 * p.Cout), f1 = __ldcg(rp + c), f2 = __ldcg(rp + p.Cout + c);
+            if (EPI == IBINN_EPI_BNSTATS) {
+                const double nb = f0, mb = f1;
+                s0 += nb;
+                s1 = fma(nb, mb, s1);
+                s2 += fma(nb * mb, mb, (double)f2);
+            } else {
+                s1 += (double)f1;
+                s2 += (double)f2;
+            }
+        }
+    }
+    for (int o = tpc >> 1; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
     if (EPI == IBINN_EPI_BNSTATS) {
-        double n = 0., mean = 0., m2 = 0.;
-        if (cval) {
-            for (unsigned bb = j; bb < nblk; bb += tpc) {
-                const double nb = p.partials[bb * rs + 2 * p.Cout];
-                if (nb <= 0.) continue;
-                const double mb = p.partials[bb * rs + c], qb = p.partials[bb * rs + p.Cout + c];
-                const double nn = n + nb, d = mb - mean;
-                mean += d * nb / nn;
-                m2 += qb + d * d * n * nb / nn;
-                n = nn;
-            }
-        }
-        for (int o = tpc >> 1; o > 0; o >>= 1) {
-            const double n2 = __shfl_xor_sync(0xffffffffu, n, o);
-            const double mean2 = __shfl_xor_sync(0xffffffffu, mean, o);
-            const double q2 = __shfl_xor_sync(0xffffffffu, m2, o);
-            const double nn = n + n2;
-            if (nn > 0.) {
-                const double d = mean2 - mean;
-                const double nm = (mean * n + mean2 * n2) / nn;
-                m2 = m2 + q2 + d * d * n * n2 / nn;
-                mean = nm;
-                n = nn;
-            }
-        }
         long long nbt = 0;
         if (p.num_batches_tracked) nbt = *p.num_batches_tracked;
         __syncthreads();
         if (cval && j == 0) {
+            const double n = s0, mean = s1 / n;
+            double m2 = s2 - n * mean * mean;
+            if (m2 < 0.) m2 = 0.;
             const double var_b = m2 / n;
             p.save_mean[c] = (float)mean;
             p.save_invstd[c] = (float)(1.0 / sqrt(var_b + (double)p.bn_eps));
@@ -566,22 +578,11 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) conv_tc_kernel(const ibinn_con
         }
         if (tid == 0 && p.num_batches_tracked) *p.num_batches_tracked = nbt + 1;
     } else {
-        double a1 = 0., a2 = 0.;
-        if (cval) {
-            for (unsigned bb = j; bb < nblk; bb += tpc) {
-                a1 += (double)p.partials[bb * rs + c];
-                a2 += (double)p.partials[bb * rs + p.Cout + c];
-            }
-        }
-        for (int o = tpc >> 1; o > 0; o >>= 1) {
-            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-        }
         if (cval && j == 0) {
-            p.sums_out[c] = (float)a1;
-            p.sums_out[p.Cout + c] = (float)a2;
-            if (p.m_dbeta) p.m_dbeta[c] += (float)a1;
-            if (p.m_dgamma) p.m_dgamma[c] += (float)a2;
+            p.sums_out[c] = (float)s1;
+            p.sums_out[p.Cout + c] = (float)s2;
+            if (p.m_dbeta) p.m_dbeta[c] += (float)s1;
+            if (p.m_dgamma) p.m_dgamma[c] += (float)s2;
         }
     }
     if (tid == 0) *p.counter = 0u;

@@ -7,6 +7,8 @@ beta_x = 2/(1+beta), beta_y = 2 beta/(1+beta); clip_grad_norm_ over *all* traina
 Multi-GPU: every rank runs the reference's single-GPU step on its own batch
 with local BatchNorm statistics; the only exchange is one all-reduce of the flat gradient.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -192,6 +194,8 @@ class TrainStep:
         self.x = torch.zeros((batch_size,) + tuple(model.dims), dtype=torch.float32, device=dev)
         self.y = torch.zeros((batch_size, model.n_classes), dtype=torch.float32, device=dev)
         self.use_graph = bool(use_graph) and dev.type == 'cuda'
+        n_side = int(os.environ.get('IBINN_WGRAD_STREAMS', '1'))
+        self.side_streams = [torch.cuda.Stream() for _ in range(n_side)] if dev.type == 'cuda' and n_side > 0 else None
         self._g1 = self._g2 = None
         self.out = None
         self.launches = None
@@ -209,10 +213,13 @@ class TrainStep:
         else:
             loss = self.bx * losses['L_x_tr'] - self.by * losses['L_y_tr']
         ops.DEFERRED_WGRAD = pending = []
+        ops.WGRAD_STREAMS = self.side_streams
         try:
             loss.backward()
+            ops.join_wgrad_streams()
         finally:
             ops.DEFERRED_WGRAD = None
+            ops.WGRAD_STREAMS = None
         self._pinned = ops.flush_deferred_wgrad(pending, self.x, getattr(self, '_pinned', None))
         self._pending = pending            # keeps the record workspaces alive until the reduction has run
         self.out = {k: losses[k].detach() for k in ('L_x_tr', 'L_y_tr', 'acc_tr', 'L_cNLL_tr')}

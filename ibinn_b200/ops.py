@@ -129,11 +129,22 @@ def conv_forward(x, w, ksize, stride=1, *, cout=None, pre=PRE_NONE, pre_bn=None,
 
 
 DEFERRED_WGRAD = None       # list while engine.TrainStep collects deferred wgrad reductions, else None
+WGRAD_STREAMS = None        # engine.TrainStep: side streams the weight-gradient kernels of a backward pass are forked onto
+_wgrad_rr = 0
+
+
+def join_wgrad_streams():
+    """make the current stream wait for everything forked onto the wgrad side streams"""
+    if WGRAD_STREAMS:
+        cur = torch.cuda.current_stream()
+        for s in WGRAD_STREAMS:
+            cur.wait_stream(s)
 
 
 def flush_deferred_wgrad(entries, ref, pinned):
     """one launch for all deferred wgrad record reductions; `pinned` = reusable pinned uint8 staging tensor or None"""
     import numpy as np
+    entries = [e for e in entries if e[1] is not None]
     if not entries:
         return pinned
     raw = b''.join(bytes(d) for _, d in entries)
@@ -192,7 +203,17 @@ def conv_wgrad(g, x, dw, ksize, stride=1, *, g_pre=PRE_NONE, gh=None, g_bn=None,
             DEFERRED_WGRAD.append((ws, _lib.WreduceDesc(ptr(ws), ptr(dw), ptr(dbias), ncta.value, rec.value, Cout, Cin, ksize * ksize)))
     if _lib._profiler is not None:
         _lib.set_tag('k%d s%d %d->%d @%dx%d' % (ksize, stride, Cin, Cout, Hout, Wout))
-    check(_lib.lib().ibinn_conv_wgrad(ctypes.byref(a), stream(g)), 'conv_wgrad')
+    st = stream(g)
+    if DEFERRED_WGRAD is not None and WGRAD_STREAMS and g.is_cuda:
+        # The weight gradient feeds nothing downstream in the backward pass: fork it onto a side stream so it fills the
+        # SMs the (latency-bound) dgrad chain leaves idle.  The operands stay referenced until the join.
+        global _wgrad_rr
+        side = WGRAD_STREAMS[_wgrad_rr % len(WGRAD_STREAMS)]
+        _wgrad_rr += 1
+        side.wait_stream(torch.cuda.current_stream())
+        st = side.cuda_stream
+        DEFERRED_WGRAD.append(((g, x, gh, g_sums, x_mask, dw, dbias), None))
+    check(_lib.lib().ibinn_conv_wgrad(ctypes.byref(a), st), 'conv_wgrad')
     _lib.set_tag('')
 
 
