@@ -11,9 +11,9 @@
 // Weights are pre-arranged per tap in the same canonical layout by a small prep kernel and streamed
 // tap by tap with 1-D TMA bulk copies through a 3-deep mbarrier ring, so 64x64x9 filters (288 KB as
 // hi+lo) never have to fit in shared memory at once.
-// Warp roles: all 8 warps stage the activation tile; then warp 1 lane 0 = weight producer,
-// warp 0 lane 0 = MMA issuer, all 8 warps = epilogue (warps w and w+4 split the columns of TMEM
-// lanes 32(w%4)..+31).
+// The kernel is persistent and warp-specialised (10 warps): warps 0-3 = epilogue (TMEM lane quadrants), warps 4-7 =
+// loaders (stage the activation window of the next tile), warp 8 = MMA issuer, warp 9 = filter producer; the
+// epilogue warps help staging the first tile.
 #include "common.cuh"
 #include "conv_internal.cuh"
 #include "tc.cuh"
@@ -22,10 +22,12 @@
 #ifdef IBINN_DBG
 __device__ unsigned long long ibinn_dbg[64];
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define DBGL(i) do { ibinn_dbg[i] = gtime(); } while (0)
 #define DBG(i) do { if (blockIdx.x == 0) { ibinn_dbg[i] = gtime(); if ((i) == 10 || (i) == 11) ibinn_dbg[(i) + 40] = clock64(); } } while (0)
 extern "C" int ibinn_debug_read(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, ibinn_dbg, sizeof(unsigned long long) * 64); }
 #else
 #define DBG(i)
+#define DBGL(i)
 #endif
 namespace {
 
@@ -62,7 +64,8 @@ static bool tc_geometry(const ibinn_conv_args& a, TcGeom& g) {
     if (g.lbo_a >= (1 << 18)) return false;
     g.nstat = a.epi == IBINN_EPI_BNSTATS ? 1 : a.epi == IBINN_EPI_MASKSTATS ? 2 : 0;
     const int stat_bytes = g.nstat * g.np * TP * 4;
-    const int tab_bytes = (3 * MAXC_TC + 4 * 64 + TM) * 4 + 256;
+    const int red_bytes = g.nstat ? (NTHREADS_TC / 32) * 64 * 2 * 4 : 0;            // cross-warp combine of the last CTA
+    const int tab_bytes = (3 * MAXC_TC + 4 * 64 + TM) * 4 + 256 + red_bytes;
     const int budget = 200 * 1024;
     // candidates, best first: double-buffered activations + resident filters ... single buffer + filter ring
     bool ok = false;
@@ -217,11 +220,12 @@ __device__ __forceinline__ void tc_stage_tile(const ibinn_conv_args& p, const Tc
 
 // Persistent, warp-specialised implicit-GEMM convolution.  Each CTA walks tiles blockIdx.x, +gridDim.x, ...
 template <int PRE, int EPI>
-__global__ void __launch_bounds__(NTHREADS_TC, 1) conv_tc_kernel(const ibinn_conv_args p, const TcGeom g) {
+__global__ void __launch_bounds__(NTHREADS_TC, 2) conv_tc_kernel(const ibinn_conv_args p, const TcGeom g) {
     extern __shared__ __align__(128) unsigned char tcs[];
     __shared__ __align__(8) uint64_t a_full[2], a_empty[2], acc_full[2], acc_empty[2], w_full[MAX_RING], w_empty[MAX_RING], a_help;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_flag;
+    __shared__ uint32_t s_tapoff[MAX_RING];
     constexpr bool STATS = (EPI == IBINN_EPI_BNSTATS || EPI == IBINN_EPI_MASKSTATS);
 
     unsigned char* wst = tcs + g.off_w;
@@ -236,9 +240,11 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) conv_tc_kernel(const ibinn_con
     float* s_ei = s_em + 64;
     float* s_valid = s_ei + 64;     // [128]
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // warp-uniform by construction: role branches stay on the uniform datapath
     const int HsWs = p.Hs * p.Ws;
     if (tid == 0) DBG(0);
+    if (tid < g.kk) s_tapoff[tid] = (uint32_t)(g.halo + (g.pad ? (tid / 3 - 1) * g.P + (tid % 3 - 1) : 0));
 
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
@@ -306,55 +312,56 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) conv_tc_kernel(const ibinn_con
         __syncwarp();        // the warp reaches the closing __syncthreads as one
     } else if (warp == 8) {
         // ================= MMA issuer =================
-        // The whole warp walks the loop (descriptor arithmetic stays on the uniform datapath); one
-        // elected lane issues the tcgen05 instructions.
         {
-            // two MMAs per k-step: x_hi * [w_hi | w_lo] (N = 2 np) and x_lo * w_hi (N = np, onto the first np columns)
+            // two MMAs per k-step: x_hi * [w_hi | w_lo] (N = 2 np) and x_lo * w_hi (N = np, onto the first np columns).
+            // The issue loop is a latency-bound scalar chain: one elected lane runs it, descriptors advance by 32-bit adds
+            // on their low words (address / LBO fields cannot carry), tap offsets come from a table.
             const uint32_t idesc2 = tc::idesc_tf32(TM, 2 * g.np), idesc1 = tc::idesc_tf32(TM, g.np);
             const uint64_t db0 = tc::smem_desc(tc::smem_u32(wst), g.lbo_b);
+            const uint32_t hB = (uint32_t)(db0 >> 32), lB = (uint32_t)db0;
             const int nks = g.cin_p / 8;
             const uint32_t a_step = (uint32_t)(2 * g.lbo_a) >> 4, b_step = (uint32_t)(2 * g.lbo_b) >> 4, st_step = (uint32_t)g.tap_bytes >> 4;
-            int gi = 0;
-            for (int j = 0; j < ntl; ++j) {
-                const int buf = j % g.nbuf, n = j / g.nbuf;
-                const uint32_t a_base = tc::smem_u32(tcs + (size_t)buf * 2 * g.a_bytes);
-                const uint64_t da_hi = tc::smem_desc(a_base, g.lbo_a), da_lo = tc::smem_desc(a_base + g.a_bytes, g.lbo_a);
-                const uint32_t acc_addr = tmem_d + buf * 2 * g.np;
-                if (n >= 1) tc::mbar_wait(&acc_empty[buf], (n - 1) & 1);      // epilogue has drained this accumulator
-                tc::mbar_wait(&a_full[buf], n & 1);                          // activation tile staged
-                if (j == 0) tc::mbar_wait(&a_help, 0);
-                tc::fence_after_sync();
-                if (lane == 0 && j < 4) DBG(10 + 2 * j);
-                uint32_t acc = 0;
-                for (int t = 0; t < g.kk; ++t, ++gi) {
-                    int s = t;
-                    if (!g.resident) {
-                        s = gi % g.nst;
-                        tc::mbar_wait(&w_full[s], (gi / g.nst) & 1);
-                        tc::fence_after_sync();
-                    } else if (j == 0) {
-                        tc::mbar_wait(&w_full[t], 0);                        // resident filters land tap by tap
-                        tc::fence_after_sync();
-                    }
-                    const int dy = g.pad ? t / 3 - 1 : 0, dx = g.pad ? t % 3 - 1 : 0;
-                    const uint32_t row_off = (uint32_t)(g.halo + dy * g.P + dx);          // 16-byte rows
-                    uint64_t dah = da_hi + row_off, dal = da_lo + row_off;
-                    uint64_t db = db0 + (uint64_t)(s * st_step);
-#pragma unroll 4
-                    for (int ks = 0; ks < nks; ++ks) {
-                        if (tc::elect_one()) {
-                            tc::mma_tf32(acc_addr, dah, db, idesc2, acc != 0);
-                            tc::mma_tf32(acc_addr, dal, db, idesc1, 1);
+            if (tc::elect_one()) {
+                int gi = 0;
+                for (int j = 0; j < ntl; ++j) {
+                    const int buf = j % g.nbuf, n = j / g.nbuf;
+                    const uint32_t a_base = tc::smem_u32(tcs + (size_t)buf * 2 * g.a_bytes);
+                    const uint64_t da_hi = tc::smem_desc(a_base, g.lbo_a), da_lo = tc::smem_desc(a_base + g.a_bytes, g.lbo_a);
+                    const uint32_t hA = (uint32_t)(da_hi >> 32), lAh = (uint32_t)da_hi, lAl = (uint32_t)da_lo;
+                    const uint32_t acc_addr = tmem_d + buf * 2 * g.np;
+                    if (n >= 1) tc::mbar_wait(&acc_empty[buf], (n - 1) & 1);      // epilogue has drained this accumulator
+                    tc::mbar_wait(&a_full[buf], n & 1);                          // activation tile staged
+                    if (j == 0) tc::mbar_wait(&a_help, 0);
+                    tc::fence_after_sync();
+                    if (j < 4) DBG(10 + 2 * j);
+                    uint32_t acc = 0;
+                    for (int t = 0; t < g.kk; ++t, ++gi) {
+                        int s = t;
+                        if (!g.resident) {
+                            s = gi % g.nst;
+                            tc::mbar_wait(&w_full[s], (gi / g.nst) & 1);
+                            tc::fence_after_sync();
+                        } else if (j == 0) {
+                            tc::mbar_wait(&w_full[t], 0);                        // resident filters land tap by tap
+                            tc::fence_after_sync();
                         }
-                        acc = 1;
-                        dah += a_step;
-                        dal += a_step;
-                        db += b_step;
+                        const uint32_t row_off = s_tapoff[t];                    // halo + dy P + dx, in 16-byte rows
+                        uint32_t ah = lAh + row_off, al = lAl + row_off, b = lB + (uint32_t)s * st_step;
+#pragma unroll 4
+                        for (int ks = 0; ks < nks; ++ks) {
+                            tc::mma_tf32(acc_addr, ((uint64_t)hA << 32) | ah, ((uint64_t)hB << 32) | b, idesc2, acc);
+                            tc::mma_tf32(acc_addr, ((uint64_t)hA << 32) | al, ((uint64_t)hB << 32) | b, idesc1, 1);
+                            acc = 1;
+                            ah += a_step;
+                            al += a_step;
+                            b += b_step;
+                        }
+                        if (!g.resident) tc::mma_commit(&w_empty[s]);
                     }
-                    if (!g.resident) { if (tc::elect_one()) tc::mma_commit(&w_empty[s]); }
+                    tc::mma_commit(&a_empty[buf]);
+                    tc::mma_commit(&acc_full[buf]);
+                    if (j < 4) DBG(11 + 2 * j);
                 }
-                if (tc::elect_one()) { tc::mma_commit(&a_empty[buf]); tc::mma_commit(&acc_full[buf]); }
-                if (lane == 0 && j < 4) DBG(11 + 2 * j);
             }
         }
         __syncwarp();
@@ -523,70 +530,103 @@ __global__ void __launch_bounds__(NTHREADS_TC, 1) conv_tc_kernel(const ibinn_con
     if (tid == 0) DBG(2);
     if (!STATS) return;
 
-    // ---- last CTA: combine the per-CTA records in CTA order (deterministic for a given grid)
+    // ---- last CTA: combine the per-CTA records (fixed order: deterministic for a given grid).
+    // With per-CTA (n_b, mean_b, M2_b):  N = sum n_b, S1 = sum n_b mean_b, S2 = sum (M2_b + n_b mean_b^2), mean = S1/N,
+    // M2 = S2 - N mean^2, in double from fp32 records (the cancellation costs log10(mean^2/var) of 16 digits).
+    // Every dependent global round trip is ~0.7 us here, so: ONE acq_rel ticket (the CTA barrier above makes it cover the
+    // record stores of the whole CTA), the tail operands prefetched, and all record loads of a thread issued as one batch.
     const unsigned nblk = gridDim.x;
-    if (!last_block_ticket(p.counter, nblk, &s_flag)) return;
-    int cpad = 8;
-    while (cpad < p.Cout) cpad <<= 1;
-    const int tpc = 256 / cpad > 32 ? 32 : 256 / cpad;
-    const int c = tid / tpc, j = tid % tpc;
-    const bool cval = (tid < 256) && (c < p.Cout) && (tid < cpad * tpc);
+    if (tid == 0) {
+        DBGL(5);
+        unsigned t;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(t) : "l"(p.counter) : "memory");
+        s_flag = (t == nblk - 1u) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_flag) return;
+    if (tid == 0) DBGL(4);
     const size_t rs = 2 * p.Cout + 4;
-    // One pass of independent loads (no loop-carried dependence but the sums): with per-CTA (n_b, mean_b, M2_b)
-    //   N = sum n_b, S1 = sum n_b mean_b, S2 = sum (M2_b + n_b mean_b^2),  mean = S1/N,  M2 = S2 - N mean^2
-    // evaluated in double from fp32 records (the cancellation costs log10(mean^2/var) of 16 digits).
-    double s0 = 0., s1 = 0., s2 = 0.;
-    if (cval) {
-        const float* rp = p.partials + (size_t)j * rs;
-        const size_t step = (size_t)tpc * rs;
-#pragma unroll 8
-        for (unsigned bb = j; bb < nblk; bb += tpc, rp += step) {
-            const float f0 = __ldcg(rp + 2 * p.Cout), f1 = __ldcg(rp + c), f2 = __ldcg(rp + p.Cout + c);
-            if (EPI == IBINN_EPI_BNSTATS) {
-                const double nb = f0, mb = f1;
-                s0 += nb;
-                s1 = fma(nb, mb, s1);
-                s2 += fma(nb * mb, mb, (double)f2);
-            } else {
-                s1 += (double)f1;
-                s2 += (double)f2;
-            }
-        }
-    }
-    for (int o = tpc >> 1; o > 0; o >>= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
+    const bool own = tid < p.Cout;                       // thread <-> channel for the tail
+    long long nbt = 0;
+    float rmean = 0.f, rvar = 0.f;
     if (EPI == IBINN_EPI_BNSTATS) {
-        long long nbt = 0;
         if (p.num_batches_tracked) nbt = *p.num_batches_tracked;
-        __syncthreads();
-        if (cval && j == 0) {
-            const double n = s0, mean = s1 / n;
-            double m2 = s2 - n * mean * mean;
-            if (m2 < 0.) m2 = 0.;
-            const double var_b = m2 / n;
-            p.save_mean[c] = (float)mean;
-            p.save_invstd[c] = (float)(1.0 / sqrt(var_b + (double)p.bn_eps));
-            if (p.running_mean) {
-                const double f = p.momentum >= 0.f ? (double)p.momentum : 1.0 / (double)(nbt + 1);
-                const double var_u = n > 1. ? m2 / (n - 1.) : var_b;
-                p.running_mean[c] = (float)((1.0 - f) * p.running_mean[c] + f * mean);
-                p.running_var[c] = (float)((1.0 - f) * p.running_var[c] + f * var_u);
+        if (own && p.running_mean) { rmean = p.running_mean[tid]; rvar = p.running_var[tid]; }
+    } else if (own) {
+        if (p.m_dbeta) rmean = p.m_dbeta[tid];           // accumulation targets, fetched ahead of the record loads
+        if (p.m_dgamma) rvar = p.m_dgamma[tid];
+    }
+    // fp32 throughout, made safe by shifting: with K = mean of record 0 (any value near the mean works),
+    //   s1 = sum n_b (m_b - K),  s2 = sum M2_b + n_b (m_b - K)^2,   mean = K + s1/N,   M2 = s2 - s1^2/N
+    // the subtraction s2 - s1^2/N is benign because |s1/N| is a small fraction of the standard deviation.
+    constexpr int NW = NTHREADS_TC / 32, UB = 15;
+    float* s_red = s_valid + TM;                         // [NW][64][2] (+ one count per warp in s_cnt)
+    __shared__ float s_cnt[NW];
+    float Kown = 0.f;
+    for (int ch0 = 0; ch0 < p.Cout; ch0 += 32) {         // warp <-> records, lane <-> channel
+        const int ca = ch0 + lane;
+        const bool va = ca < p.Cout;
+        float Ka = 0.f;
+        if (EPI == IBINN_EPI_BNSTATS) { if (va) Ka = p.partials[ca]; }
+        float s0 = 0.f, s1a = 0.f, s2a = 0.f;
+        for (unsigned b0 = warp; b0 < nblk; b0 += NW * UB) {
+            float f0[UB], f1a[UB], f2a[UB];
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                const bool in = b0 + u * NW < nblk;
+                const float* rp = p.partials + (size_t)(b0 + u * NW) * rs;
+                f0[u] = (in && EPI == IBINN_EPI_BNSTATS) ? rp[2 * p.Cout] : 0.f;
+                f1a[u] = (in && va) ? rp[ca] : Ka;
+                f2a[u] = (in && va) ? rp[p.Cout + ca] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < UB; ++u) {
+                if (EPI == IBINN_EPI_BNSTATS) {
+                    const float nb = f0[u], da = f1a[u] - Ka;
+                    s0 += nb;
+                    s1a = fmaf(nb, da, s1a);
+                    s2a += fmaf(nb * da, da, f2a[u]);
+                } else {
+                    s1a += f1a[u];
+                    s2a += f2a[u];
+                }
             }
         }
-        if (tid == 0 && p.num_batches_tracked) *p.num_batches_tracked = nbt + 1;
-    } else {
-        if (cval && j == 0) {
-            p.sums_out[c] = (float)s1;
-            p.sums_out[p.Cout + c] = (float)s2;
-            if (p.m_dbeta) p.m_dbeta[c] += (float)s1;
-            if (p.m_dgamma) p.m_dgamma[c] += (float)s2;
+        s_red[(warp * 64 + ca) * 2] = s1a;
+        s_red[(warp * 64 + ca) * 2 + 1] = s2a;
+        if (lane == 0) s_cnt[warp] = s0;
+        if (tid == ca) Kown = Ka;                        // thread tid owns channel tid in the tail
+    }
+    if (tid == 0) DBGL(6);
+    __syncthreads();
+    if (tid == 0) DBGL(7);
+    if (own) {
+        float n = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { n += s_cnt[w]; s1 += s_red[(w * 64 + tid) * 2]; s2 += s_red[(w * 64 + tid) * 2 + 1]; }
+        if (EPI == IBINN_EPI_BNSTATS) {
+            const float d = s1 / n, mean = Kown + d;
+            float m2 = s2 - s1 * d;
+            if (m2 < 0.f) m2 = 0.f;
+            const float var_b = m2 / n;
+            p.save_mean[tid] = mean;
+            p.save_invstd[tid] = 1.0f / sqrtf(var_b + p.bn_eps);
+            if (p.running_mean) {
+                const float f = p.momentum >= 0.f ? p.momentum : 1.0f / (float)(nbt + 1);
+                const float var_u = n > 1.f ? m2 / (n - 1.f) : var_b;
+                p.running_mean[tid] = (1.0f - f) * rmean + f * mean;
+                p.running_var[tid] = (1.0f - f) * rvar + f * var_u;
+            }
+        } else {
+            p.sums_out[tid] = s1;
+            p.sums_out[p.Cout + tid] = s2;
+            if (p.m_dbeta) p.m_dbeta[tid] = rmean + s1;
+            if (p.m_dgamma) p.m_dgamma[tid] = rvar + s2;
         }
     }
+    if (EPI == IBINN_EPI_BNSTATS) { if (tid == 0 && p.num_batches_tracked) *p.num_batches_tracked = nbt + 1; }
     if (tid == 0) *p.counter = 0u;
-    if (tid == 0) DBG(3);
+    if (tid == 0) DBGL(3);
 }
 
 template <int PRE, int EPI>
