@@ -365,36 +365,34 @@ __global__ void __launch_bounds__(NTHREADS_TC, 2) conv_tc_kernel(const ibinn_con
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
-        // ================= loaders: stage the activation window of each tile =================
-        // (the first tile is staged together with the still idle epilogue warps: 256 threads)
-        const int lt = tid - 128;
-        for (int j = 0; j < ntl; ++j) {
-            const int buf = j % g.nbuf, n = j / g.nbuf;
-            const int q0 = ((int)blockIdx.x + j * (int)gridDim.x) * TM;
-            unsigned char* a_hi = tcs + (size_t)buf * 2 * g.a_bytes;
-            if (n >= 1) {
-                tc::mbar_wait(&a_empty[buf], (n - 1) & 1);                     // MMAs that read this buffer are done
-                if (STATS && g.alias_stats) tc::mbar_wait(&acc_empty[buf], (n - 1) & 1);   // ... and so is the epilogue that borrowed it
-            }
-            if (lt == 0 && j < 4) DBG(20 + 2 * j);
-            if (j == 0) tc_stage_tile<PRE>(p, g, q0, a_hi, a_hi + g.a_bytes, s_pa, s_pb, s_pc, lt + 128, 256);
-            else tc_stage_tile<PRE>(p, g, q0, a_hi, a_hi + g.a_bytes, s_pa, s_pb, s_pc, lt, 128);
-            tc::fence_async_smem();
-            mbar_arrive(&a_full[buf]);
-            if (lt == 0 && j < 4) DBG(21 + 2 * j);
-        }
     } else {
+        // ================= warps 0-7: stage the activation window of each tile =================
+        // Warps 4-7 (loaders) stage every tile; the still idle epilogue warps 0-3 help with the first one (256 threads,
+        // signalled on the helper barrier).  One call site: the staging code exists once in the instruction stream.
+        {
+            const bool loader = warp >= 4;
+            const int jend = loader ? ntl : 1;
+            for (int j = 0; j < jend; ++j) {
+                const int buf = j % g.nbuf, n = j / g.nbuf;
+                const int q0 = ((int)blockIdx.x + j * (int)gridDim.x) * TM;
+                unsigned char* a_hi = tcs + (size_t)buf * 2 * g.a_bytes;
+                if (n >= 1) {
+                    tc::mbar_wait(&a_empty[buf], (n - 1) & 1);                     // MMAs that read this buffer are done
+                    if (STATS && g.alias_stats) tc::mbar_wait(&acc_empty[buf], (n - 1) & 1);   // ... and so is the epilogue that borrowed it
+                }
+                if (tid == 128 && j < 4) DBG(20 + 2 * j);
+                tc_stage_tile<PRE>(p, g, q0, a_hi, a_hi + g.a_bytes, s_pa, s_pb, s_pc, j == 0 ? tid : tid - 128, j == 0 ? 256 : 128);
+                tc::fence_async_smem();
+                mbar_arrive(loader ? &a_full[buf] : &a_help);
+                if (tid == 128 && j < 4) DBG(21 + 2 * j);
+            }
+        }
+        if (warp < 4) {
         // ================= epilogue: thread <-> output row of the tile =================
         const int row = tid;                      // 0..127, TMEM lane
         const size_t HWo = (size_t)p.Hout * p.Wout;
         const int sc = tid >> 1, part = tid & 1;  // statistics: thread reduces 64 rows of channel sc
         float run_n = 0.f, run_mean = 0.f, run_m2 = 0.f, run_a1 = 0.f, run_a2 = 0.f;
-        {   // help staging the first tile, then signal on the helper barrier
-            tc_stage_tile<PRE>(p, g, (int)blockIdx.x * TM, tcs, tcs + g.a_bytes, s_pa, s_pb, s_pc, tid, 256);
-            tc::fence_async_smem();
-            mbar_arrive(&a_help);
-        }
         for (int j = 0; j < ntl; ++j) {
             const int buf = j % g.nbuf, n = j / g.nbuf;
             const int q = ((int)blockIdx.x + j * (int)gridDim.x) * TM + row;
@@ -521,6 +519,7 @@ __global__ void __launch_bounds__(NTHREADS_TC, 2) conv_tc_kernel(const ibinn_con
                 else { rec[sc] = run_a1; rec[p.Cout + sc] = run_a2; }
             }
             if (tid == 0) rec[2 * p.Cout] = run_n;
+        }
         }
     }
 

@@ -63,8 +63,10 @@ static bool wg_geometry(const ibinn_wgrad_args& a, WgTcGeom& g) {
     if (g.np > 256 || g.ntile * g.np > 512) return false;
     int cols = g.ntile * g.np;
     g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-    g.lbo_a = 128 * 16;
-    g.lbo_b = g.np * 16;
+    // K-chunk pitch = an ODD number of 16-byte rows: the staging threads of a quarter-warp write the same row of eight
+    // consecutive chunks, which must fall into eight different bank groups
+    g.lbo_a = 129 * 16;
+    g.lbo_b = (g.np + 1) * 16;
     // enough staging work per K block to hide the load latency (>= ~4 chunk tasks per staging thread),
     // but at least 3 stages in shared memory
     const int tasks_per_chunk = g.ntile * g.na * a.Cout + a.Cin;
@@ -107,8 +109,13 @@ __device__ __forceinline__ void wt_store_split(unsigned char* hi, unsigned char*
     *reinterpret_cast<float4*>(lo) = make_float4(l[0], l[1], l[2], l[3]);
 }
 
+// GPRE / XPRE = pre-op of the gradient / activation operand, K3 = 3x3 filter (else 1x1), VEC = 16-byte global loads:
+// compile-time so that each instantiation carries only its own staging path (the loop body is streamed through the
+// instruction cache once per K block).
+template <int GPRE, int XPRE, bool K3, bool VEC>
 __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgrad_args p, const WgTcGeom g, float* __restrict__ partials) {
     extern __shared__ __align__(128) unsigned char wts[];
+    constexpr int ND = K3 ? 3 : 1;                       // dx copies of the activation operand
     __shared__ __align__(8) uint64_t full[4], empty[4], done;
     __shared__ uint32_t tmem_base_s;
     float* s_ga = reinterpret_cast<float*>(wts + (size_t)g.nstage * g.stage_bytes);
@@ -116,6 +123,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
     float* s_gc = s_gb + WT_MAXC;
     float* s_xa = s_gc + WT_MAXC;
     float* s_xb = s_xa + WT_MAXC;
+    __shared__ int s_trow[256];                       // per A row (tile, dy copy, co): smem byte offset | co << 20 | (cp + 2) << 28
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int HW = p.Hin * p.Win;
@@ -126,7 +134,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
         tc::mbar_fence_init();
     }
     if (warp == WT_MMA_WARP) tc::tmem_alloc(&tmem_base_s, g.tmem_cols);
-    if (p.g_pre == IBINN_PRE_BNBWD) {
+    if (GPRE == IBINN_PRE_BNBWD) {
         for (int c = tid; c < p.Cout; c += WT_THREADS) {
             const float is = wt_invstd(p.g_bn, c), k = p.g_bn.gamma[c] * is;
             const float m1 = p.g_sums[c] * p.g_inv_count, m2 = p.g_sums[p.Cout + c] * p.g_inv_count;
@@ -135,12 +143,25 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
             s_gc[c] = -k * m1 + k * m2 * is * p.g_bn.mean[c];
         }
     }
-    if (p.x_pre == IBINN_PRE_BN_RELU) {
+    if (XPRE == IBINN_PRE_BN_RELU) {
         for (int c = tid; c < p.Cin; c += WT_THREADS) {
             const float is = wt_invstd(p.x_bn, c), A = p.x_bn.gamma[c] * is;
             s_xa[c] = A;
             s_xb[c] = p.x_bn.beta[c] - p.x_bn.mean[c] * A;
         }
+    }
+    if (tid < 256) {
+        // A-row table (one division per row here instead of per staging thread and row): row r = cp * Cout + co
+        const int n_rows = g.ntile * g.na * p.Cout;
+        int packed = 0;                                  // cp field 0 -> row does not exist
+        if (tid < n_rows) {
+            const int co = tid % p.Cout, cp = tid / p.Cout;
+            const int t = cp / g.na, dyi = cp - t * g.na;
+            const int off = (t * 2 * g.a_tile_bytes) + (dyi * g.coutp + co) * 16;
+            const int cpv = (cp < ND || !K3) ? cp : -1;  // -1: padding copy of the last tile (rows stay zero)
+            packed = off | (co << 20) | ((cpv + 2) << 28);
+        }
+        s_trow[tid] = packed;
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -149,7 +170,6 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
     if (tid == 0) WDBG(1);
     const int blk0 = blockIdx.x * g.bpc;
     const int nblk = min(g.bpc, g.nblocks - blk0);
-    const int nrows_total = p.B * g.rows_img + g.pad;        // padded rows of the whole sequence
 
     const int KC = g.kc;
     if (warp == WT_MMA_WARP) {
@@ -192,19 +212,26 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
         const int n_ar = g.ntile * g.na * p.Cout;              // A rows that carry data: (tile, dy copy, co)
         const int n_br = p.Cin + (g.ones_row >= 0 ? 1 : 0);    // B source rows: ci (+ the ones row)
         // per-thread task table (fixed for the whole kernel): the channel / copy of each of its A rows
-        constexpr int UA = 4;
-        int t_row[UA], t_co[UA], t_cp[UA];                     // smem row offset, channel, dy copy (-1: no data)
+        constexpr int UA = 6;
+        int t_row[UA], t_co[UA], t_cp[UA];                     // smem row offset, channel, dy copy (-1: no data, -2: no such row)
 #pragma unroll
         for (int u = 0; u < UA; ++u) {
             const int r = lane_t + u * tstride;
-            const bool live = r < n_ar;
-            const int co = live ? r % p.Cout : 0, cp = live ? r / p.Cout : 0;
-            const int t = cp / g.na, dyi = cp - t * g.na;
-            t_row[u] = (t * 2 * g.a_tile_bytes) + (dyi * g.coutp + co) * 16;
-            t_co[u] = co;
-            t_cp[u] = live ? ((cp < g.nd || g.kk == 1) ? cp : -1) : -2;      // -2: row does not exist
+            const int packed = r < 256 ? s_trow[r] : 0;
+            t_row[u] = packed & 0xfffff;
+            t_co[u] = (packed >> 20) & 0xff;
+            t_cp[u] = ((packed >> 28) & 0xf) - 2;
         }
-        const bool many_rows = n_ar > UA * tstride;            // shapes with more than 4 rows per thread take the slow loop
+        const bool many_rows = n_ar > UA * tstride;            // shapes with more than UA rows per thread take the slow loop
+        // Position of this thread's chunk in the padded sequence, kept incrementally (no divisions in the block loop):
+        // q = padded position, R0 = q / P4 (padded row), c0 = q % P4, bimg = R0 / rows_img, rin = R0 % rows_img.
+        const int q_step = 2 * 4 * KC, R_step = q_step / g.P4, c_step = q_step % g.P4;
+        int R0, c0, bimg, rin;
+        {
+            const int q = (blk0 + grp) * 4 * KC + 4 * kc;
+            R0 = q / g.P4; c0 = q - R0 * g.P4;
+            bimg = R0 / g.rows_img; rin = R0 - bimg * g.rows_img;
+        }
         for (int i = grp; i < nblk; i += 2) {
             const int s = i % g.nstage;
             if (i >= g.nstage) tc::mbar_wait(&empty[s], ((i / g.nstage) - 1) & 1);
@@ -212,26 +239,20 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
             unsigned char* st = wts + (size_t)s * g.stage_bytes;
             unsigned char* b_hi = st + 2 * g.ntile * g.a_tile_bytes;
             const size_t b_lo_off = g.b_bytes;
-            const int q = (blk0 + i) * 4 * KC + 4 * kc;        // first padded position of this thread's chunk
-            const int R0 = q / g.P4, c0 = q % g.P4;
-            // pixel coordinates of the (up to) three row-shifted copies, decoded once per block
+            // pixel coordinates of the (up to) three row-shifted copies: padded row R0 - (d3 - 1)
             long long base3[3];
             bool ok3[3];
 #pragma unroll
             for (int d3 = 0; d3 < 3; ++d3) {
-                const int R = R0 - (g.pad ? d3 - 1 : 0);
                 ok3[d3] = false; base3[d3] = 0;
-                if (R >= 0 && R < nrows_total && c0 < p.Win && (g.pad || d3 == 0)) {
-                    const int b = R / g.rows_img, y = R - b * g.rows_img - g.pad;
-                    if (y >= 0 && b < p.B) { ok3[d3] = true; base3[d3] = (long long)b * p.g_bs + (long long)y * p.Win + c0; }
-                }
+                if (!(K3 || d3 == 0)) continue;
+                int b = bimg, r = rin - (K3 ? d3 - 1 : 0);
+                if (r < 0) { r += g.rows_img; --b; } else if (r >= g.rows_img) { r -= g.rows_img; ++b; }
+                const int y = r - g.pad;
+                if (b >= 0 && b < p.B && y >= 0 && c0 < p.Win) { ok3[d3] = true; base3[d3] = (long long)b * p.g_bs + (long long)y * p.Win + c0; }
             }
-            bool rowok = false;
-            int bb = 0, yy = 0;
-            if (R0 >= 0 && R0 < nrows_total) {
-                bb = R0 / g.rows_img; yy = R0 - bb * g.rows_img - g.pad;
-                rowok = (yy >= 0 && bb < p.B);
-            }
+            const int bb = bimg, yy = rin - g.pad;
+            const bool rowok = (yy >= 0 && bb < p.B);
             // ---- issue every global load of this block first, then transform and store
             constexpr int UB = 2;
             float w6[UB][6];
@@ -244,10 +265,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
                 for (int j = 0; j < 6; ++j) w6[u][j] = 0.f;
                 if (ci < p.Cin && rowok) {
                     const float* xp = p.x + (size_t)bb * p.x_bs + (size_t)ci * HW + (size_t)yy * p.Win;
-                    if (g.vec_x && c0 + 3 < p.Win) {
+                    if (VEC && c0 + 3 < p.Win) {
                         const float4 t4 = *reinterpret_cast<const float4*>(xp + c0);
                         w6[u][1] = t4.x; w6[u][2] = t4.y; w6[u][3] = t4.z; w6[u][4] = t4.w;
-                        if (g.nd > 1) {
+                        if (K3) {
                             if (c0 > 0) w6[u][0] = __ldg(xp + c0 - 1);
                             if (c0 + 4 < p.Win) w6[u][5] = __ldg(xp + c0 + 4);
                         }
@@ -255,10 +276,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
 #pragma unroll
                         for (int j = 0; j < 6; ++j) {
                             const int c = c0 - 1 + j;
-                            if (c >= 0 && c < p.Win && (g.nd > 1 || (j >= 1 && j <= 4))) w6[u][j] = __ldg(xp + c);
+                            if (c >= 0 && c < p.Win && (K3 || (j >= 1 && j <= 4))) w6[u][j] = __ldg(xp + c);
                         }
                     }
-                    if (p.x_pre == IBINN_PRE_BN_RELU && p.x_mask) mk[u] = __ldg(p.x_mask + (size_t)bb * p.Cin + ci);
+                    if (XPRE == IBINN_PRE_BN_RELU && p.x_mask) mk[u] = __ldg(p.x_mask + (size_t)bb * p.Cin + ci);
                 }
             }
             if (lt == 0 && i == 0) WDBG(40);
@@ -275,10 +296,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
                     const long long off = (cp == 0 ? base3[0] : cp == 1 ? base3[1] : base3[2]) + (long long)t_co[u] * HW;
                     const float* gp = p.g + off;
                     const float* hp = p.gh + off;     // same (b,c,y,x): gh_bs == g_bs is checked on the host
-                    if (g.vec_g) {
+                    if (VEC) {
                         const float4 t4 = *reinterpret_cast<const float4*>(gp);
                         v[u][0] = t4.x; v[u][1] = t4.y; v[u][2] = t4.z; v[u][3] = t4.w;
-                        if (p.g_pre == IBINN_PRE_BNBWD) {
+                        if (GPRE == IBINN_PRE_BNBWD) {
                             const float4 h4 = *reinterpret_cast<const float4*>(hp);
                             h[u][0] = h4.x; h[u][1] = h4.y; h[u][2] = h4.z; h[u][3] = h4.w;
                         }
@@ -287,7 +308,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
                         for (int j = 0; j < 4; ++j) {
                             if (c0 + j < p.Win) {
                                 v[u][j] = __ldg(gp + j);
-                                if (p.g_pre == IBINN_PRE_BNBWD) h[u][j] = __ldg(hp + j);
+                                if (GPRE == IBINN_PRE_BNBWD) h[u][j] = __ldg(hp + j);
                             }
                         }
                     }
@@ -301,7 +322,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
                     for (int j = 0; j < 4; ++j) {
                         o[j] = v[u][j];
                         // BN backward is affine (a*g + b*h + c): padded positions must stay exactly zero
-                        if (p.g_pre == IBINN_PRE_BNBWD && ok[u] && c0 + j < p.Win) o[j] = fmaf(s_ga[t_co[u]], v[u][j], fmaf(s_gb[t_co[u]], h[u][j], s_gc[t_co[u]]));
+                        if (GPRE == IBINN_PRE_BNBWD && ok[u] && c0 + j < p.Win) o[j] = fmaf(s_ga[t_co[u]], v[u][j], fmaf(s_gb[t_co[u]], h[u][j], s_gc[t_co[u]]));
                     }
                     unsigned char* hi = st + t_row[u] + (size_t)kc * g.lbo_a;
                     wt_store_split(hi, hi + g.a_tile_bytes, o);
@@ -313,14 +334,14 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
                     const int co = r % p.Cout, cp = r / p.Cout;
                     const int t = cp / g.na, dyi = cp - t * g.na;
                     float o[4] = {0.f, 0.f, 0.f, 0.f};
-                    const bool okk = (cp < g.nd || g.kk == 1) && (cp == 0 ? ok3[0] : cp == 1 ? ok3[1] : ok3[2]);
+                    const bool okk = (cp < ND || !K3) && (cp == 0 ? ok3[0] : cp == 1 ? ok3[1] : ok3[2]);
                     if (okk) {
                         const long long off = (cp == 0 ? base3[0] : cp == 1 ? base3[1] : base3[2]) + (long long)co * HW;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             if (c0 + j < p.Win) {
                                 float tv = __ldg(p.g + off + j);
-                                if (p.g_pre == IBINN_PRE_BNBWD) tv = fmaf(s_ga[co], tv, fmaf(s_gb[co], __ldg(p.gh + off + j), s_gc[co]));
+                                if (GPRE == IBINN_PRE_BNBWD) tv = fmaf(s_ga[co], tv, fmaf(s_gb[co], __ldg(p.gh + off + j), s_gc[co]));
                                 o[j] = tv;
                             }
                         }
@@ -358,19 +379,23 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
                 if (u0 < UB) {
 #pragma unroll
                     for (int u = 0; u < UB; ++u) if (u == u0) mkk = mk[u];
-                } else if (rowok && p.x_pre == IBINN_PRE_BN_RELU && p.x_mask) mkk = __ldg(p.x_mask + (size_t)bb * p.Cin + ci);
+                } else if (rowok && XPRE == IBINN_PRE_BN_RELU && p.x_mask) mkk = __ldg(p.x_mask + (size_t)bb * p.Cin + ci);
 #pragma unroll
                 for (int j = 0; j < 6; ++j) {
                     const int c = c0 - 1 + j;
                     if (!rowok || c < 0 || c >= p.Win) { x6[j] = 0.f; continue; }
-                    if (p.x_pre == IBINN_PRE_RELU) x6[j] = fmaxf(x6[j], 0.f);
-                    else if (p.x_pre == IBINN_PRE_BN_RELU) x6[j] = fmaxf(fmaf(x6[j], s_xa[ci], s_xb[ci]), 0.f) * mkk;
+                    if (XPRE == IBINN_PRE_RELU) x6[j] = fmaxf(x6[j], 0.f);
+                    else if (XPRE == IBINN_PRE_BN_RELU) x6[j] = fmaxf(fmaf(x6[j], s_xa[ci], s_xb[ci]), 0.f) * mkk;
                 }
-                for (int d = 0; d < g.nd; ++d) {
-                    const int sh = g.nd > 1 ? d : 1;                 // window offset: dx = d - 1 -> x6[sh .. sh+3]
-                    const float o[4] = {x6[sh], x6[sh + 1], x6[sh + 2], x6[sh + 3]};
+                float h6[6], l6[6];                                  // split once, the dx copies are windows of it
+#pragma unroll
+                for (int j = 0; j < 6; ++j) tc::split_tf32(x6[j], h6[j], l6[j]);
+#pragma unroll
+                for (int d = 0; d < ND; ++d) {
+                    const int sh = K3 ? d : 1;                       // window offset: dx = d - 1 -> x6[sh .. sh+3]
                     unsigned char* hi = b_hi + (size_t)kc * g.lbo_b + (size_t)(d * g.cinp + ci) * 16;
-                    wt_store_split(hi, hi + b_lo_off, o);
+                    *reinterpret_cast<float4*>(hi) = make_float4(h6[sh], h6[sh + 1], h6[sh + 2], h6[sh + 3]);
+                    *reinterpret_cast<float4*>(hi + b_lo_off) = make_float4(l6[sh], l6[sh + 1], l6[sh + 2], l6[sh + 3]);
                 }
             }
             if (lt == 0 && i == 0) WDBG(43);
@@ -378,10 +403,15 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
             if (lt == 0 && i == 0) WDBG(44);
             wt_arrive(&full[s]);
             if (lt == 0 && i < 6) WDBG(21 + 2 * i);
+            // advance to this group's next block
+            c0 += c_step; R0 += R_step; rin += R_step;
+            if (c0 >= g.P4) { c0 -= g.P4; ++R0; ++rin; }
+            while (rin >= g.rows_img) { rin -= g.rows_img; ++bimg; }
         }
     }
 
-    // ---- epilogue: warps 0-3, thread <-> TMEM lane = A row (dy copy, co)
+    // ---- epilogue: warps 0-3, thread <-> TMEM lane = A row (dy copy, co).  (Bound by the record volume written to L2 -
+    // 9 Cout Cin floats per CTA - not by the store pattern: a transposition through shared memory was slower.)
     if (warp < 4) {
         tc::mbar_wait(&done, 0);
         tc::fence_after_sync();
@@ -392,31 +422,38 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
         const bool vec_st = (p.Cin % 4 == 0);
         for (int t = 0; t < g.ntile; ++t) {
             const int cp = t * g.na + dyi;                        // dy copy -> ky
-            const bool rowv = (dyi < g.na) && (co < p.Cout) && (cp < g.nd || g.kk == 1);
+            const bool rowv = (dyi < g.na) && (co < p.Cout) && (cp < ND || !K3);
             const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + t * g.np;
-            for (int d = 0; d < g.nd; ++d) {
-                const int tap = g.pad ? cp * 3 + d : 0;           // ky = cp, kx = d
+            for (int d = 0; d < ND; ++d) {
+                const int tap = K3 ? cp * 3 + d : 0;           // ky = cp, kx = d
                 float* dst = rec + ((size_t)tap * p.Cout + co) * p.Cin;
 #pragma unroll 1
-                for (int c8 = 0; c8 < g.cinp; c8 += 8) {
-                    float v[8];
-                    tc::tmem_ld8(taddr + d * g.cinp + c8, v);
+                for (int c32 = 0; c32 < g.cinp; c32 += 32) {      // up to four 8-column loads in flight per wait
+                    float v[4][8];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (c32 + 8 * k < g.cinp) tc::tmem_ld8(taddr + d * g.cinp + c32 + 8 * k, v[k]);
                     tc::tmem_ld_wait();
                     if (!rowv) continue;
-                    if (vec_st && c8 + 8 <= p.Cin) {
-                        *reinterpret_cast<float4*>(dst + c8) = make_float4(v[0], v[1], v[2], v[3]);
-                        *reinterpret_cast<float4*>(dst + c8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                    } else {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) if (c8 + j < p.Cin) dst[c8 + j] = v[j];
+                    for (int k = 0; k < 4; ++k) {
+                        const int c8 = c32 + 8 * k;
+                        if (c8 >= g.cinp) break;
+                        if (vec_st && c8 + 8 <= p.Cin) {
+                            *reinterpret_cast<float4*>(dst + c8) = make_float4(v[k][0], v[k][1], v[k][2], v[k][3]);
+                            *reinterpret_cast<float4*>(dst + c8 + 4) = make_float4(v[k][4], v[k][5], v[k][6], v[k][7]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) if (c8 + j < p.Cin) dst[c8 + j] = v[k][j];
+                        }
                     }
                 }
             }
-            if (g.ones_row >= 0 && t == 0) {
+            if (g.ones_row >= 0) {
                 float v[8];
                 tc::tmem_ld8(taddr + g.ones_row, v);
                 tc::tmem_ld_wait();
-                if (rowv) rec[g.kk * p.Cout * p.Cin + co] = v[0];
+                if (rowv && cp == (K3 ? 1 : 0)) rec[g.kk * p.Cout * p.Cin + co] = v[0];     // the unshifted (dy = 0) copy sums G over the valid pixels
             }
         }
     }
@@ -531,10 +568,21 @@ int wgrad_tc_launch(const ibinn_wgrad_args& a, float* workspace, cudaStream_t st
     WgTcGeom g;
     if (!wg_geometry(a, g)) return IBINN_EINVAL;
     if (!workspace) return IBINN_ENULL;
-    int e = ibinn_set_smem(wgrad_tc_kernel, g.smem_bytes);
-    if (e) return e;
-    IBINN_LAUNCH(wgrad_tc_kernel, dim3(g.ncta), dim3(WT_THREADS), g.smem_bytes, st, a, g, workspace);
-    e = ibinn_launch_status();
+    const bool vec = g.vec_g && g.vec_x, k3 = a.ksize == 3;
+    int e = IBINN_EINVAL;
+#define WT_CASE(GP, XP, K3_, V_) \
+    if (a.g_pre == GP && a.x_pre == XP && k3 == K3_ && vec == V_) { \
+        auto kfn = wgrad_tc_kernel<GP, XP, K3_, V_>; \
+        e = ibinn_set_smem(kfn, g.smem_bytes); \
+        if (e) return e; \
+        IBINN_LAUNCH(kfn, dim3(g.ncta), dim3(WT_THREADS), g.smem_bytes, st, a, g, workspace); \
+        e = ibinn_launch_status(); \
+    }
+#define WT_CASES(GP, XP) WT_CASE(GP, XP, true, true) WT_CASE(GP, XP, true, false) WT_CASE(GP, XP, false, true) WT_CASE(GP, XP, false, false)
+    WT_CASES(IBINN_PRE_NONE, IBINN_PRE_NONE) WT_CASES(IBINN_PRE_NONE, IBINN_PRE_RELU) WT_CASES(IBINN_PRE_NONE, IBINN_PRE_BN_RELU)
+    WT_CASES(IBINN_PRE_BNBWD, IBINN_PRE_NONE) WT_CASES(IBINN_PRE_BNBWD, IBINN_PRE_RELU) WT_CASES(IBINN_PRE_BNBWD, IBINN_PRE_BN_RELU)
+#undef WT_CASES
+#undef WT_CASE
     if (e || a.defer_reduce) return e;
     int nb = (g.rec_floats + 31) / 32;
     if (nb > 148 * 8) nb = 148 * 8;
