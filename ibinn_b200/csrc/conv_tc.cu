@@ -391,7 +391,10 @@ __global__ void __launch_bounds__(NTHREADS_TC, 2) conv_tc_kernel(const ibinn_con
         // ================= epilogue: thread <-> output row of the tile =================
         const int row = tid;                      // 0..127, TMEM lane
         const size_t HWo = (size_t)p.Hout * p.Wout;
-        const int sc = tid >> 1, part = tid & 1;  // statistics: thread reduces 64 rows of channel sc
+        // statistics: channel sc is reduced by `nparts` adjacent lanes, lane `part` taking rows part, part + nparts, ...
+        int nparts = 1;
+        while (nparts * 2 * g.np <= TM) nparts *= 2;
+        const int sc = tid / nparts, part = tid - sc * nparts, nrows = TM / nparts;
         float run_n = 0.f, run_mean = 0.f, run_m2 = 0.f, run_a1 = 0.f, run_a2 = 0.f;
         for (int j = 0; j < ntl; ++j) {
             const int buf = j % g.nbuf, n = j / g.nbuf;
@@ -467,46 +470,53 @@ __global__ void __launch_bounds__(NTHREADS_TC, 2) conv_tc_kernel(const ibinn_con
                     }
                 }
             }
+            if (tid == 0 && j == 0) DBG(60);
             tc::fence_before_sync();
             if (!(STATS && g.alias_stats)) mbar_arrive(&acc_empty[buf]);       // accumulator (TMEM) is free again
             if (STATS) {
                 epi_sync();
-                float a1 = 0.f, a2 = 0.f, cnt = 0.f;
+                if (tid == 0 && j == 0) DBG(61);
+                // one pass; BatchNorm sums are taken about K = the column's first row (any value near the mean keeps
+                // a2 - a1^2/cnt free of cancellation)
+                float a1 = 0.f, a2 = 0.f, cnt = 0.f, K = 0.f;
                 if (sc < g.np) {
-                    const float* t1 = s_t1 + sc * TP + part * 64;
-                    const float* t2 = s_t2 + sc * TP + part * 64;
+                    const float* t1 = s_t1 + sc * TP + part;
+                    const float* t2 = s_t2 + sc * TP + part;
+                    const float* vv = s_valid + part;
+                    if (EPI == IBINN_EPI_BNSTATS) K = s_t1[sc * TP];
 #pragma unroll 8
-                    for (int r = 0; r < 64; ++r) {
-                        a1 += t1[r];
-                        cnt += s_valid[part * 64 + r];
-                        if (EPI == IBINN_EPI_MASKSTATS) a2 += t2[r];
-                    }
-                }
-                a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-                cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
-                if (EPI == IBINN_EPI_BNSTATS) {
-                    const float mean = cnt > 0.f ? a1 / cnt : 0.f;
-                    if (sc < g.np) {
-                        const float* t1 = s_t1 + sc * TP + part * 64;
-#pragma unroll 8
-                        for (int r = 0; r < 64; ++r) {
-                            const float d = t1[r] - mean;
-                            a2 = fmaf(s_valid[part * 64 + r] * d, d, a2);
+                    for (int r = 0; r < nrows; ++r) {
+                        const float o = t1[r * nparts], w = vv[r * nparts];
+                        cnt += w;
+                        if (EPI == IBINN_EPI_BNSTATS) {
+                            const float d = o - K;
+                            a1 = fmaf(w, d, a1);
+                            a2 = fmaf(w * d, d, a2);
+                        } else {
+                            a1 += o;
+                            a2 += t2[r * nparts];
                         }
                     }
-                    a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
-                    if (cnt > 0.f) {       // Chan: fold the tile (cnt, mean, a2) into the running (n, mean, M2)
+                }
+                for (int o = nparts >> 1; o > 0; o >>= 1) {
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                }
+                if (EPI == IBINN_EPI_BNSTATS) {
+                    if (cnt > 0.f) {       // Chan: fold the tile (cnt, mean, M2) into the running (n, mean, M2)
+                        const float d = a1 / cnt, mean = K + d, m2 = fmaxf(a2 - a1 * d, 0.f);
                         const float nn = run_n + cnt, dlt = mean - run_mean;
                         run_mean += dlt * cnt / nn;
-                        run_m2 += a2 + dlt * dlt * run_n * cnt / nn;
+                        run_m2 += m2 + dlt * dlt * run_n * cnt / nn;
                         run_n = nn;
                     }
                 } else {
-                    a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
                     run_a1 += a1;
                     run_a2 += a2;
                     run_n += cnt;
                 }
+                if (tid == 0 && j == 0) DBG(62);
                 epi_sync();                                                  // tiles may be overwritten by the next pass
                 if (g.alias_stats) mbar_arrive(&acc_empty[buf]);             // borrowed operand area is free again
             }

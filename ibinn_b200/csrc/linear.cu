@@ -147,26 +147,54 @@ __device__ __forceinline__ void tc_stage(const GemmP& p, unsigned char* hi, unsi
     const float* x2 = IS_A ? p.A2 : nullptr;
     const float* mask = IS_A ? p.Amask : p.Bmask;
     const bool kcontig = (sk == 1);
-    for (int c = threadIdx.x; c < ROWS * TC_KC; c += IBINN_THREADS) {
+    // 16-byte loads need k contiguous, aligned rows and a full K block
+    const bool vec = kcontig && (sr % 4 == 0) && (k0 % 4 == 0) && (k0 + TC_BK <= kend) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0) &&
+                     (pre != 2 || (reinterpret_cast<uintptr_t>(x2) & 15) == 0) && (!mask || (reinterpret_cast<uintptr_t>(mask) & 15) == 0);
+    constexpr int NT = ROWS * TC_KC / IBINN_THREADS;              // chunk tasks per thread (4 for A, 2 for B)
+    static_assert(ROWS * TC_KC % IBINN_THREADS == 0, "tile / thread mismatch");
+    // phase 1: every load of this thread's tasks is issued before the first use
+    float v[NT][4], w2[NT][4], mk[NT][4];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const int c = threadIdx.x + t * IBINN_THREADS;
         int r, k4;
         if (kcontig) { k4 = c % TC_KC; r = c / TC_KC; } else { r = c % ROWS; k4 = c / ROWS; }
         const int row = r0 + r, k = k0 + k4 * 4;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (row < nrows) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[t][i] = 0.f; w2[t][i] = 1.f; mk[t][i] = 1.f; }
+        if (row >= nrows) continue;
+        if (vec) {
+            const size_t off = (size_t)row * sr + k;
+            const float4 a4 = *reinterpret_cast<const float4*>(base + off);
+            v[t][0] = a4.x; v[t][1] = a4.y; v[t][2] = a4.z; v[t][3] = a4.w;
+            if (pre == 2) { const float4 b4 = *reinterpret_cast<const float4*>(x2 + off); w2[t][0] = b4.x; w2[t][1] = b4.y; w2[t][2] = b4.z; w2[t][3] = b4.w; }
+            if (pre != 0 && mask) { const float4 m4 = *reinterpret_cast<const float4*>(mask + off); mk[t][0] = m4.x; mk[t][1] = m4.y; mk[t][2] = m4.z; mk[t][3] = m4.w; }
+        } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (k + i < kend) {
                     const size_t off = (size_t)row * sr + (size_t)(k + i) * sk;
-                    float t = __ldg(base + off);
-                    if (pre == 1) { t = fmaxf(t, 0.f); if (mask) t *= __ldg(mask + off); }
-                    else if (pre == 2) { t = __ldg(x2 + off) > 0.f ? t : 0.f; if (mask) t *= __ldg(mask + off); }
-                    v[i] = t;
+                    v[t][i] = __ldg(base + off);
+                    if (pre == 2) w2[t][i] = __ldg(x2 + off);
+                    if (pre != 0 && mask) mk[t][i] = __ldg(mask + off);
                 }
             }
         }
+    }
+    // phase 2: pre-op, split, store
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        const int c = threadIdx.x + t * IBINN_THREADS;
+        int r, k4;
+        if (kcontig) { k4 = c % TC_KC; r = c / TC_KC; } else { r = c % ROWS; k4 = c / ROWS; }
         float h[4], l[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) tc::split_tf32(v[i], h[i], l[i]);
+        for (int i = 0; i < 4; ++i) {
+            float tv = v[t][i];
+            if (pre == 1) tv = fmaxf(tv, 0.f) * mk[t][i];
+            else if (pre == 2) tv = (w2[t][i] > 0.f ? tv : 0.f) * mk[t][i];
+            tc::split_tf32(tv, h[i], l[i]);
+        }
         *reinterpret_cast<float4*>(hi + k4 * LBO + r * 16) = make_float4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<float4*>(lo + k4 * LBO + r * 16) = make_float4(l[0], l[1], l[2], l[3]);
     }
