@@ -199,18 +199,42 @@ def main():
     pk = peaks()
     ms_step = ms / a.steps
     value = world * B / (ms_step * 1e-3)
-    # dominant kernel class (largest share of device time in the eager profile)
-    top = max(table.items(), key=lambda kv: kv[1][0])
-    conv_ms = sum(t for k, (t, n) in table.items() if k.startswith('ibinn_conv_forward') or k.startswith('ibinn_conv_wgrad') or k.startswith('ibinn_linear'))
-    conv_n = sum(n for k, (t, n) in table.items() if k.startswith('ibinn_conv_forward') or k.startswith('ibinn_conv_wgrad') or k.startswith('ibinn_linear'))
-    flops_step = TRAIN_FLOP_PER_IMG * B
-    ach = flops_step / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.
-    roofline = {'bound': 'tensor', 'kernel': 'subnet contractions (conv fwd/dgrad/wgrad + fc), %d launches per step' % conv_n,
-                'achieved': ach, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s', 'frac': ach / pk['bf16_sustained'],
-                'traffic': None, 'peak_source': pk['source'] + ' bf16 dense sustained (MEASURED_PEAKS.json has no TF32/FP32 figure)',
-                'share_of_step': conv_ms / total_ms if total_ms else None,
-                'note': 'exact-fp32 CUDA-core kernels in this round; algorithmic FLOPs = 1.175 GFLOP/img x batch, time = sum of the CUDA-event '
-                        'durations of these launches in one eager step'}
+    # ---- roofline of the dominant kernel.  The profiler keys carry the launch shapes
+    # ('ibinn_conv_forward[k3 s1 N 32->32 @16x16 pre2 epi1]'), so the algorithmic FLOPs (2 x MAC, counted once although the
+    # 3xTF32 arithmetic issues 2-3 MMAs per product) are exact per launch; the duration is the CUDA-event time of the same launches.
+    import re
+
+    def tag_flops(key):
+        m = re.search(r'\[k(\d) s(\d) (?:[NT] )?(\d+)->(\d+) @(\d+)x(\d+)', key)
+        if not m:
+            return 0.
+        k, _, ci, co, h, w = (int(v) for v in m.groups())
+        return 2. * B * h * w * ci * co * k * k
+    fam = {'conv_tc_kernel (subnet conv forward + dgrad)': lambda k: k.startswith('ibinn_conv_forward[') and ' s1 ' in k,
+           'wgrad_tc_kernel (subnet conv weight gradient)': lambda k: k.startswith('ibinn_conv_wgrad[') and ' s1 ' in k}
+    stats = {}
+    for name, pred in fam.items():
+        keys = [k for k in table if pred(k)]
+        stats[name] = dict(ms=sum(table[k][0] for k in keys), n=sum(table[k][1] for k in keys), flops=sum(tag_flops(k) * table[k][1] for k in keys))
+    top = max(stats, key=lambda n: stats[n]['ms'])
+    st = stats[top]
+    ach = st['flops'] / (st['ms'] * 1e-3) / 1e12 if st['ms'] > 0 else 0.
+    traffic = None
+    try:
+        ncu = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_full.json')))
+        traffic = ncu[top.split(' ')[0]]['dram_bytes_per_launch']
+    except Exception:
+        pass
+    roofline = {'bound': 'tensor', 'kernel': top, 'launches_per_step': st['n'], 'avg_launch_us': st['ms'] * 1e3 / max(st['n'], 1),
+                'flops_per_launch': st['flops'] / max(st['n'], 1), 'achieved': ach, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s',
+                'frac': ach / pk['bf16_sustained'], 'traffic': traffic,
+                'peak_source': pk['source'] + ' bf16 dense sustained (MEASURED_PEAKS.json has no TF32 figure; nominal TF32 dense is half of it)',
+                'share_of_step': st['ms'] / total_ms if total_ms else None,
+                'families': {n: {'ms_per_step': v['ms'], 'launches': v['n'], 'tflops': (v['flops'] / (v['ms'] * 1e-3) / 1e12 if v['ms'] > 0 else 0.)}
+                             for n, v in stats.items()},
+                'note': 'fp32-accurate 3xTF32 on tcgen05; channel widths are 16/32/64, so one MMA uses N <= 128 of 256 columns and the kernels are '
+                        'latency- rather than throughput-bound (DESIGN.md section 7); time = CUDA-event durations of these launches in one eager '
+                        'step, traffic = ncu dram bytes per launch (profiles/)'}
     line = {'metric': 'train_images_per_sec', 'value': value, 'unit': 'img/s', 'n_gpus': world, 'steps': a.steps, 'warmup': warmup,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'per_gpu_batch': B, 'global_batch': B * world, 'parallelism': 'dp%d' % world,

@@ -48,22 +48,46 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_mix_kernel(const AioP p) {
     if (MODE == 1) __syncthreads();
 
     float jsum = 0.f;
-    for (int e = tid; e < C * HW; e += IBINN_THREADS) {
-        const int c = e / HW, q = e - c * HW;
-        float u = __ldg(xb + e);
-        if (MODE == 0) {
-            if (c >= c1) {
-                const float* ab = p.a + (size_t)b * 2 * c2 * HW;
-                const float s = __ldg(ab + (size_t)(c - c1) * HW + q);
-                const float t = __ldg(ab + (size_t)(c2 + c - c1) * HW + q);
-                const float sig = p.clamp * tanhf(p.alpha * s);
-                u = fmaf(u, expf(sig), t);
-                jsum += sig;
+    {
+        // all loads of a batch of elements are issued before the first use (the kernel is latency-bound: 12 elements per thread)
+        constexpr int KB = 6;
+        const int n = C * HW;
+        const float* ab = p.a + (size_t)b * 2 * c2 * HW;
+        for (int e0 = 0; e0 < n; e0 += IBINN_THREADS * KB) {
+            float xv[KB], sv[KB], tv[KB];
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                const int e = e0 + tid + IBINN_THREADS * k;
+                xv[k] = 0.f; sv[k] = 0.f; tv[k] = 0.f;
+                if (e < n) {
+                    xv[k] = __ldg(xb + e);
+                    if (MODE == 0) {
+                        const int c = e / HW, q = e - c * HW;
+                        if (c >= c1) {
+                            sv[k] = __ldg(ab + (size_t)(c - c1) * HW + q);
+                            tv[k] = __ldg(ab + (size_t)(c2 + c - c1) * HW + q);
+                        }
+                    }
+                }
             }
-        } else {
-            u = (u - s_of[c]) * s_sc[c];
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                const int e = e0 + tid + IBINN_THREADS * k;
+                if (e >= n) continue;
+                const int c = e / HW, q = e - c * HW;
+                float u = xv[k];
+                if (MODE == 0) {
+                    if (c >= c1) {
+                        const float sig = p.clamp * tanhf(p.alpha * sv[k]);
+                        u = fmaf(u, expf(sig), tv[k]);
+                        jsum += sig;
+                    }
+                } else {
+                    u = (u - s_of[c]) * s_sc[c];
+                }
+                s_u[(size_t)c * HWp + q] = u;
+            }
         }
-        s_u[(size_t)c * HWp + q] = u;
     }
     // zero the pixel padding so that the 4-wide reads below stay finite
     if (HWp != HW)
@@ -152,7 +176,44 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
         const int o = e / Cp, i = e - o * Cp;
         s_w[e] = (i < C) ? __ldg(p.w + (size_t)o * C + i) : 0.f;
     }
-    // phase A: one warp per output channel: g_v = g_out * exp(an), per-channel partial sums
+    // phase A: g_v = g_out * exp(an) into shared memory, per-channel sums of g and g (y - off) for the ActNorm gradients
+    if (HW % 32 == 0) {
+        // fast path: every load of the sample is in flight at once; a warp's 32 consecutive elements share a channel, so
+        // a warp reduction per element group and a fixed-order sum of the HW/32 group partials per channel finish the job
+        float* s_sc = s_w + (size_t)C * Cp;
+        float* s_of = s_sc + Cp;
+        float* s_part = s_of + Cp + 16;                      // [C * HW / 32][2]
+        for (int c = tid; c < C; c += IBINN_THREADS) { s_sc[c] = expf(p.an[c]); s_of[c] = p.off[c]; }
+        __syncthreads();
+        constexpr int KB = 12;
+        const int n = C * HW;
+        for (int e0 = 0; e0 < n; e0 += IBINN_THREADS * KB) {
+            float g[KB], y[KB];
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                const int e = e0 + tid + IBINN_THREADS * k;
+                g[k] = 0.f; y[k] = 0.f;
+                if (e < n) { g[k] = __ldg(p.g_out + ib + e); y[k] = __ldg(p.out_saved + ib + e); }
+            }
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                const int e = e0 + tid + IBINN_THREADS * k;
+                if (e - lane >= n) continue;                 // whole warp in or out (n is a multiple of 32)
+                const int o = e / HW, q = e - o * HW;
+                s_u[(size_t)o * HWp + q] = g[k] * s_sc[o];
+                const float so = warp_sum(g[k]), sn = warp_sum(g[k] * (y[k] - s_of[o]));
+                if (lane == 0) { s_part[(e >> 5) * 2] = so; s_part[(e >> 5) * 2 + 1] = sn; }
+            }
+        }
+        __syncthreads();
+        if (tid < C) {
+            const int per = HW / 32;
+            float so = 0.f, sn = 0.f;
+            for (int i = tid * per; i < (tid + 1) * per; ++i) { so += s_part[2 * i]; sn += s_part[2 * i + 1]; }
+            p.partials[((size_t)b * 2 + 0) * C + tid] = so;
+            p.partials[((size_t)b * 2 + 1) * C + tid] = sn + (float)HW * gj;
+        }
+    } else {
     for (int o = wid; o < C; o += IBINN_THREADS / 32) {
         const float sc = expf(p.an[o]), of = p.off[o];
         float so = 0.f, sn = 0.f;
@@ -173,6 +234,7 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
             p.partials[((size_t)b * 2 + 0) * C + o] = so;
             p.partials[((size_t)b * 2 + 1) * C + o] = sn + (float)HW * gj;
         }
+    }
     }
     __syncthreads();
 
@@ -242,20 +304,50 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
         }
     }
 
-    // ActNorm parameter gradients: last CTA sums the per-sample partials in sample order
+    // ActNorm parameter gradients: the last CTA sums the per-sample partials (fixed order: sample groups, then groups)
     if (!last_block_ticket(p.counter, gridDim.x, &s_flag)) return;
-    for (int e = tid; e < 2 * C; e += IBINN_THREADS) {
-        double t = 0.;
-        for (int bb = 0; bb < p.B; ++bb) t += (double)p.partials[(size_t)bb * 2 * C + e];
-        if (e < C) { if (p.g_off) p.g_off[e] += (float)t; }
-        else if (p.g_an) p.g_an[e - C] += (float)t;
+    {
+        const int T = 2 * C, ngrp = IBINN_THREADS / T > 0 ? IBINN_THREADS / T : 1;
+        const bool par = (ngrp * T <= C * HWp) && (T <= IBINN_THREADS);
+        if (par) {
+            const int e = tid % T, grp = tid / T;
+            float t = 0.f;
+            if (grp < ngrp) {
+                constexpr int UB = 8;
+                for (int b0 = grp; b0 < p.B; b0 += ngrp * UB) {
+                    float v[UB];
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) {
+                        const int bb = b0 + u * ngrp;
+                        v[u] = bb < p.B ? __ldcg(p.partials + (size_t)bb * T + e) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < UB; ++u) t += v[u];
+                }
+                s_u[grp * T + e] = t;
+            }
+            __syncthreads();
+            if (tid < T) {
+                float tot = 0.f;
+                for (int gi = 0; gi < ngrp; ++gi) tot += s_u[gi * T + tid];
+                if (tid < C) { if (p.g_off) p.g_off[tid] += tot; }
+                else if (p.g_an) p.g_an[tid - C] += tot;
+            }
+        } else {
+            for (int e = tid; e < T; e += IBINN_THREADS) {
+                float t = 0.f;
+                for (int bb = 0; bb < p.B; ++bb) t += __ldcg(p.partials + (size_t)bb * T + e);
+                if (e < C) { if (p.g_off) p.g_off[e] += t; }
+                else if (p.g_an) p.g_an[e - C] += t;
+            }
+        }
     }
     if (tid == 0) *p.counter = 0u;
 }
 
 static size_t aio_smem(int C, int HW) {
     const int HWp = (HW + 3) & ~3, Cp = (C + 3) & ~3;
-    return ((size_t)C * HWp + (size_t)C * Cp + 2 * Cp + 16) * sizeof(float);
+    return ((size_t)C * HWp + (size_t)C * Cp + 2 * Cp + 32 + 2 * ((size_t)C * HWp / 32 + 1)) * sizeof(float);
 }
 
 // ------------------------------------------------------------------------------------ S2D
