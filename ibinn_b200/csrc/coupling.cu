@@ -246,6 +246,26 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
     const float ak = p.alpha * p.clamp;
     for (int item = tid; item < npg * nig; item += IBINN_THREADS) {
         const int pg = item % npg, ig = item / npg;
+        // the coupling operands (s and x2 of the passive-half channels) do not depend on the channel mix: fetch them first so
+        // that their latency hides behind the C-deep FMA loop
+        float sv[4][4], xv[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int ic = ig * 4 + i;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { sv[i][j] = 0.f; xv[i][j] = 0.f; }
+            if (ic >= C || ic < c1) continue;
+            const float* sp = ab + (size_t)(ic - c1) * HW + pg * 4;
+            const float* xp = p.x + ib + (size_t)ic * HW + pg * 4;
+            if (vec) {
+                const float4 s4 = ld4(sp), x4 = ld4(xp);
+                sv[i][0] = s4.x; sv[i][1] = s4.y; sv[i][2] = s4.z; sv[i][3] = s4.w;
+                xv[i][0] = x4.x; xv[i][1] = x4.y; xv[i][2] = x4.z; xv[i][3] = x4.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (pg * 4 + j < HW) { sv[i][j] = __ldg(sp + j); xv[i][j] = __ldg(xp + j); }
+            }
+        }
         float acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -277,13 +297,11 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
                     const int q = pg * 4 + j;
                     gx[j] = 0.f; gs[j] = 0.f;
                     if (q < HW) {
-                        const float s = __ldg(ab + (size_t)k * HW + q);
-                        const float th = tanhf(p.alpha * s);
+                        const float th = tanhf(p.alpha * sv[i][j]);
                         const float es = expf(p.clamp * th);
-                        const float x2 = __ldg(p.x + ib + (size_t)ic * HW + q);
                         const float gu = acc[i][j];
                         gx[j] = gu * es;
-                        gs[j] = (gu * x2 * es + gj) * ak * (1.f - th * th);
+                        gs[j] = (gu * xv[i][j] * es + gj) * ak * (1.f - th * th);
                     }
                 }
                 float* ds = gab + (size_t)k * HW + pg * 4;
