@@ -68,7 +68,7 @@ static bool wg_geometry(const ibinn_wgrad_args& a, WgTcGeom& g) {
     g.lbo_a = 129 * 16;
     g.lbo_b = (g.np + 1) * 16;
     // enough staging work per K block to hide the load latency (>= ~4 chunk tasks per staging thread),
-    // but at least 3 stages in shared memory
+    // but at least 2 stages in shared memory (one per staging group)
     const int tasks_per_chunk = g.ntile * g.na * a.Cout + a.Cin;
     g.kc = tasks_per_chunk * 4 >= 1200 ? 4 : tasks_per_chunk * 8 >= 1200 ? 8 : KC_MAX;
     for (;;) {
@@ -76,7 +76,7 @@ static bool wg_geometry(const ibinn_wgrad_args& a, WgTcGeom& g) {
         g.b_bytes = g.kc * g.lbo_b;
         g.stage_bytes = 2 * (g.ntile * g.a_tile_bytes + g.b_bytes);
         g.nstage = (200 * 1024) / g.stage_bytes;
-        if (g.nstage >= 3 || g.kc == 4) break;
+        if (g.nstage >= 2 || g.kc == 4) break;
         g.kc /= 2;
     }
     if (g.nstage > 4) g.nstage = 4;
