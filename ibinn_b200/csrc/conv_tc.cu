@@ -69,6 +69,29 @@ static bool tc_geometry(const ibinn_conv_args& a, TcGeom& g) {
     const int budget = 200 * 1024;
     // candidates, best first: double-buffered activations + resident filters ... single buffer + filter ring
     bool ok = false;
+    if (g.ntiles > 148 && g.ntiles <= 2 * 148) {
+        // Between one and two tiles per SM a persistent CTA pipelines nothing (tile 1 waits for tile 0's MMAs), and 40 of the
+        // 148 CTAs would idle through the second tile.  Two co-resident single-tile CTAs per SM overlap their phases instead:
+        // one activation buffer, statistics tiles borrowed from it, filters through a ring - within half an SM's shared memory.
+        const int half = 108 * 1024;
+        g.nbuf = 1;
+        g.alias_stats = stat_bytes <= 2 * g.a_bytes;
+        const long long fixed = 2LL * g.a_bytes + (g.alias_stats ? 0 : stat_bytes) + tab_bytes;
+        int nst = (int)((half - fixed) / g.tap_bytes);
+        if (nst > g.kk) nst = g.kk;
+        if (nst > MAX_RING) nst = MAX_RING;
+        if (half > fixed && (nst >= 3 || nst == g.kk)) {
+            g.resident = (nst == g.kk);
+            g.nst = nst;
+            const long long op = 2LL * g.a_bytes + (long long)nst * g.tap_bytes;
+            ok = true;
+            g.off_w = 2 * g.a_bytes;
+            g.off_stat = g.alias_stats ? 0 : (int)op;
+            g.off_tab = (int)(op + (g.alias_stats ? 0 : stat_bytes));
+            g.off_tab = (g.off_tab + 15) & ~15;
+            g.smem_bytes = (size_t)g.off_tab + tab_bytes;
+        }
+    }
     for (int cand = 0; cand < 4 && !ok; ++cand) {
         g.nbuf = cand == 0 ? 2 : 1;
         g.resident = cand <= 2;

@@ -28,7 +28,8 @@ extern "C" int ibinn_wdebug_read(unsigned long long* out) { return (int)cudaMemc
 #endif
 namespace {
 
-constexpr int WT_STAGERS = 512;     // warps 0-15 stage operands in two groups of 256 (warps 0-3 also run the epilogue)
+constexpr int WT_GROUPS = 2;        // staging groups of 256 threads taking K blocks round-robin (warps 0-3 also run the epilogue)
+constexpr int WT_STAGERS = 256 * WT_GROUPS;
 constexpr int WT_THREADS = WT_STAGERS + 32;   // + warp 16: MMA issuer
 constexpr int WT_MMA_WARP = WT_STAGERS / 32;
 constexpr int KC_MAX = 16;          // K chunks per stage: 4, 8 or 16 (16 / 32 / 64 pixels), chosen per layer
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
     const int HW = p.Hin * p.Win;
     if (tid == 0) WDBG(0);
     if (tid == 0) {
-        for (int i = 0; i < 4; ++i) { tc::mbar_init(&full[i], WT_STAGERS / 2); tc::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < 4; ++i) { tc::mbar_init(&full[i], 256); tc::mbar_init(&empty[i], 1); }
         tc::mbar_init(&done, 1);
         tc::mbar_fence_init();
     }
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
         if (lane == 0) WDBG(2);
         __syncwarp();
     } else {
-        // ================= operand staging: two groups of 256 threads take alternate K blocks =================
+        // ================= operand staging: WT_GROUPS groups of 256 threads take K blocks round-robin =================
         // 256 % KC == 0, so a thread always works on the same chunk column kc of a block: its pixel
         // coordinates are decoded once per block; what varies over its tasks is the channel / copy.
         const int grp = tid >> 8, lt = tid & 255;
@@ -229,14 +230,14 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
         const bool many_rows = n_ar > UA * tstride;            // shapes with more than UA rows per thread take the slow loop
         // Position of this thread's chunk in the padded sequence, kept incrementally (no divisions in the block loop):
         // q = padded position, R0 = q / P4 (padded row), c0 = q % P4, bimg = R0 / rows_img, rin = R0 % rows_img.
-        const int q_step = 2 * 4 * KC, R_step = q_step / g.P4, c_step = q_step % g.P4;
+        const int q_step = WT_GROUPS * 4 * KC, R_step = q_step / g.P4, c_step = q_step % g.P4;
         int R0, c0, bimg, rin;
         {
             const int q = (blk0 + grp) * 4 * KC + 4 * kc;
             R0 = q / g.P4; c0 = q - R0 * g.P4;
             bimg = R0 / g.rows_img; rin = R0 - bimg * g.rows_img;
         }
-        for (int i = grp; i < nblk; i += 2) {
+        for (int i = grp; i < nblk; i += WT_GROUPS) {
             const int s = i % g.nstage;
             if (i >= g.nstage) tc::mbar_wait(&empty[s], ((i / g.nstage) - 1) & 1);
             if (lt == 0 && i < 6) WDBG(20 + 2 * i);

@@ -120,3 +120,35 @@ def test_conv_backward_pieces(dev, B, Cin, Cout, H, ks, st):
                      mask=dict(h=ud), addend=accd, out=accd)
     full = torch.nn.grad.conv2d_input((B, Cin, H, H), w.detach(), gz, stride=st, padding=ks // 2)
     assert rel(accd, acc0.double() + full * (u.detach() > 0)) < 5e-5
+
+
+@pytest.mark.parametrize('B,Cin,Cout,H,ks', [(3, 16, 16, 16, 3), (2, 32, 12, 16, 1), (3, 24, 40, 8, 3), (2, 64, 48, 8, 1)])
+def test_conv_wgrad_with_bias(dev, B, Cin, Cout, H, ks):
+    """plain wgrad + dbias (the 1x1 convs of the subnets carry a bias; for 3x3 the bias gradient must come from the
+    unshifted copy of the gradient operand only)."""
+    g = torch.Generator().manual_seed(5 * Cin + Cout + ks)
+    x = torch.randn(B, Cin, H, H, generator=g).double()
+    w = (torch.randn(Cout, Cin, ks, ks, generator=g) * 0.2).double().requires_grad_()
+    b = torch.randn(Cout, generator=g).double().requires_grad_()
+    gy = torch.randn(B, Cout, H, H, generator=g).double()
+    (F.conv2d(F.relu(x), w, b, padding=ks // 2) * gy).sum().backward()
+    dw0, db0 = torch.randn(Cout, Cin, ks, ks, generator=g), torch.randn(Cout, generator=g)
+    dw, db = dw0.clone().to(dev), db0.clone().to(dev)
+    ops.conv_wgrad(gy.float().to(dev), x.float().to(dev), dw, ks, 1, x_pre=ops.PRE_RELU, dbias=db)      # accumulates
+    assert rel(dw, dw0.double() + w.grad) < 5e-5
+    assert rel(db, db0.double() + b.grad) < 5e-5
+
+
+def test_bn_statistics_with_large_mean(dev):
+    """batch statistics of channels whose mean dwarfs their spread (mean 50, std 0.1): the per-tile, per-CTA and
+    last-CTA sums are all taken about a nearby shift, so fp32 is enough."""
+    g = torch.Generator().manual_seed(3)
+    B, C, H = 6, 16, 16
+    x = (50. + 5. * torch.arange(C).view(1, C, 1, 1) + 0.1 * torch.randn(B, C, H, H, generator=g)).float()
+    w = torch.eye(C).view(C, C, 1, 1)
+    sm, si = torch.empty(C, device=dev), torch.empty(C, device=dev)
+    y = ops.conv_forward(x.to(dev), w.to(dev), 1, 1, epi=ops.EPI_BNSTATS, stats=dict(save_mean=sm, save_invstd=si, momentum=0.999, eps=1e-4))
+    assert rel(y, x.double()) < 1e-6
+    xd = x.double()
+    assert rel(sm, xd.mean(dim=(0, 2, 3))) < 1e-6
+    assert rel(si, torch.rsqrt(xd.var(dim=(0, 2, 3), unbiased=False) + 1e-4)) < 2e-4
