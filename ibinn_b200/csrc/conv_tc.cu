@@ -45,8 +45,14 @@ struct TcGeom {
 };
 
 static bool tc_geometry(const ibinn_conv_args& a, TcGeom& g) {
-    if (a.stride != 1 || a.Cout > 64 || a.Cin > MAXC_TC) return false;
-    if (a.Hout != a.Hin || a.Wout != a.Win) return false;
+    if (a.Cout > 64 || a.Cin > MAXC_TC) return false;
+    if (a.stride == 2) {
+        // A stride-2 3x3 convolution is the stride-1 result at the even positions: the tiles walk the INPUT grid and the
+        // epilogue keeps (stores, counts in the statistics) only even rows / columns.  Three quarters of the MMAs are thrown
+        // away - the tensor pipe is idle most of the time in these kernels anyway (two such layers per network).
+        if (a.ksize != 3 || a.upsample2 || (a.Hin & 1) || (a.Win & 1) || a.Hout != a.Hin / 2 || a.Wout != a.Win / 2) return false;
+        if (a.epi != IBINN_EPI_STORE && a.epi != IBINN_EPI_BNSTATS) return false;
+    } else if (a.stride != 1 || a.Hout != a.Hin || a.Wout != a.Win) return false;
     g.pad = a.ksize / 2;
     g.kk = a.ksize * a.ksize;
     g.P = a.Win + g.pad;
@@ -428,10 +434,11 @@ __global__ void __launch_bounds__(NTHREADS_TC, 2) conv_tc_kernel(const ibinn_con
             if (q < g.Qout) {
                 const int b = q / g.S, rem = q - b * g.S;
                 const int yy = rem / g.P - g.pad, xx = rem % g.P;
-                if (yy >= 0 && yy < p.Hout && xx < p.Wout) {
+                if (yy >= 0 && yy < p.Hin && xx < p.Win && (p.stride == 1 || !((yy | xx) & 1))) {
                     valid = true;
                     bimg = b;
-                    const size_t in_img = (size_t)yy * p.Wout + xx;
+                    const int sh = p.stride - 1;
+                    const size_t in_img = (size_t)(yy >> sh) * p.Wout + (xx >> sh);
                     obase = (size_t)b * p.y_bs + in_img;
                     mbase = (size_t)b * p.m_bs + in_img;
                     abase = (size_t)b * p.addend_bs + in_img;

@@ -137,9 +137,18 @@ constexpr int TC_A_BYTES = TC_KC * TC_LBO_A, TC_B_BYTES = TC_KC * TC_LBO_B;
 constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;                 // hi + lo of both operands
 constexpr int TC_SMEM = 2 * TC_STAGE_BYTES + 64;
 
-// stage one operand tile: rows [r0, r0+ROWS) x k [k0, k0+32) -> hi / lo buffers
-template <int ROWS, int LBO, bool IS_A>
-__device__ __forceinline__ void tc_stage(const GemmP& p, unsigned char* hi, unsigned char* lo, int r0, int k0, int kend) {
+// One operand tile (rows [r0, r0+ROWS) x k [k0, k0+32)) travels global -> registers (tc_fetch) -> pre-op, hi/lo split ->
+// shared memory (tc_commit).  The two halves are separate so that the fetch of K block i+1 is in flight while block i is
+// split, stored and multiplied: the FC GEMMs have 3-12 K blocks per CTA and would otherwise expose one HBM latency each.
+template <int ROWS>
+struct TcRegs {
+    static constexpr int NT = ROWS * TC_KC / IBINN_THREADS;       // chunk tasks per thread (4 for A, 2 for B)
+    static_assert(ROWS * TC_KC % IBINN_THREADS == 0, "tile / thread mismatch");
+    float v[NT][4], w2[NT][4], mk[NT][4];
+};
+
+template <int ROWS, bool IS_A>
+__device__ __forceinline__ void tc_fetch(const GemmP& p, TcRegs<ROWS>& R, int r0, int k0, int kend) {
     const float* base = IS_A ? p.A : p.Bm;
     const long long sr = IS_A ? p.sAi : p.sBj, sk = IS_A ? p.sAk : p.sBk;
     const int nrows = IS_A ? p.M : p.N;
@@ -150,49 +159,51 @@ __device__ __forceinline__ void tc_stage(const GemmP& p, unsigned char* hi, unsi
     // 16-byte loads need k contiguous, aligned rows and a full K block
     const bool vec = kcontig && (sr % 4 == 0) && (k0 % 4 == 0) && (k0 + TC_BK <= kend) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0) &&
                      (pre != 2 || (reinterpret_cast<uintptr_t>(x2) & 15) == 0) && (!mask || (reinterpret_cast<uintptr_t>(mask) & 15) == 0);
-    constexpr int NT = ROWS * TC_KC / IBINN_THREADS;              // chunk tasks per thread (4 for A, 2 for B)
-    static_assert(ROWS * TC_KC % IBINN_THREADS == 0, "tile / thread mismatch");
-    // phase 1: every load of this thread's tasks is issued before the first use
-    float v[NT][4], w2[NT][4], mk[NT][4];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
+    for (int t = 0; t < TcRegs<ROWS>::NT; ++t) {
         const int c = threadIdx.x + t * IBINN_THREADS;
         int r, k4;
         if (kcontig) { k4 = c % TC_KC; r = c / TC_KC; } else { r = c % ROWS; k4 = c / ROWS; }
         const int row = r0 + r, k = k0 + k4 * 4;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { v[t][i] = 0.f; w2[t][i] = 1.f; mk[t][i] = 1.f; }
+        for (int i = 0; i < 4; ++i) { R.v[t][i] = 0.f; R.w2[t][i] = 1.f; R.mk[t][i] = 1.f; }
         if (row >= nrows) continue;
         if (vec) {
             const size_t off = (size_t)row * sr + k;
             const float4 a4 = *reinterpret_cast<const float4*>(base + off);
-            v[t][0] = a4.x; v[t][1] = a4.y; v[t][2] = a4.z; v[t][3] = a4.w;
-            if (pre == 2) { const float4 b4 = *reinterpret_cast<const float4*>(x2 + off); w2[t][0] = b4.x; w2[t][1] = b4.y; w2[t][2] = b4.z; w2[t][3] = b4.w; }
-            if (pre != 0 && mask) { const float4 m4 = *reinterpret_cast<const float4*>(mask + off); mk[t][0] = m4.x; mk[t][1] = m4.y; mk[t][2] = m4.z; mk[t][3] = m4.w; }
+            R.v[t][0] = a4.x; R.v[t][1] = a4.y; R.v[t][2] = a4.z; R.v[t][3] = a4.w;
+            if (pre == 2) { const float4 b4 = *reinterpret_cast<const float4*>(x2 + off); R.w2[t][0] = b4.x; R.w2[t][1] = b4.y; R.w2[t][2] = b4.z; R.w2[t][3] = b4.w; }
+            if (pre != 0 && mask) { const float4 m4 = *reinterpret_cast<const float4*>(mask + off); R.mk[t][0] = m4.x; R.mk[t][1] = m4.y; R.mk[t][2] = m4.z; R.mk[t][3] = m4.w; }
         } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 if (k + i < kend) {
                     const size_t off = (size_t)row * sr + (size_t)(k + i) * sk;
-                    v[t][i] = __ldg(base + off);
-                    if (pre == 2) w2[t][i] = __ldg(x2 + off);
-                    if (pre != 0 && mask) mk[t][i] = __ldg(mask + off);
+                    R.v[t][i] = __ldg(base + off);
+                    if (pre == 2) R.w2[t][i] = __ldg(x2 + off);
+                    if (pre != 0 && mask) R.mk[t][i] = __ldg(mask + off);
                 }
             }
         }
     }
-    // phase 2: pre-op, split, store
+}
+
+template <int ROWS, int LBO, bool IS_A>
+__device__ __forceinline__ void tc_commit(const GemmP& p, const TcRegs<ROWS>& R, unsigned char* hi, unsigned char* lo) {
+    const long long sk = IS_A ? p.sAk : p.sBk;
+    const int pre = IS_A ? p.a_pre : p.b_pre;
+    const bool kcontig = (sk == 1);
 #pragma unroll
-    for (int t = 0; t < NT; ++t) {
+    for (int t = 0; t < TcRegs<ROWS>::NT; ++t) {
         const int c = threadIdx.x + t * IBINN_THREADS;
         int r, k4;
         if (kcontig) { k4 = c % TC_KC; r = c / TC_KC; } else { r = c % ROWS; k4 = c / ROWS; }
         float h[4], l[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            float tv = v[t][i];
-            if (pre == 1) tv = fmaxf(tv, 0.f) * mk[t][i];
-            else if (pre == 2) tv = (w2[t][i] > 0.f ? tv : 0.f) * mk[t][i];
+            float tv = R.v[t][i];
+            if (pre == 1) tv = fmaxf(tv, 0.f) * R.mk[t][i];
+            else if (pre == 2) tv = (R.w2[t][i] > 0.f ? tv : 0.f) * R.mk[t][i];
             tc::split_tf32(tv, h[i], l[i]);
         }
         *reinterpret_cast<float4*>(hi + k4 * LBO + r * 16) = make_float4(h[0], h[1], h[2], h[3]);
@@ -208,6 +219,11 @@ __global__ void __launch_bounds__(IBINN_THREADS) gemm_tc_kernel(const GemmP p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * TC_M, n0 = blockIdx.x * TC_N;
     const int kbeg = blockIdx.z * p.kchunk, kend = min(p.K, kbeg + p.kchunk);
+
+    TcRegs<TC_M> ra;
+    TcRegs<TC_N> rb;
+    tc_fetch<TC_M, true>(p, ra, m0, kbeg, kend);          // first K block: in flight during the set-up below
+    tc_fetch<TC_N, false>(p, rb, n0, kbeg, kend);
 
     if (tid == 0) {
         tc::mbar_init(&bar_stage[0], 1);
@@ -228,8 +244,12 @@ __global__ void __launch_bounds__(IBINN_THREADS) gemm_tc_kernel(const GemmP p) {
         unsigned char* st = tc_smem + s * TC_STAGE_BYTES;
         unsigned char *a_hi = st, *a_lo = st + TC_A_BYTES, *b_hi = st + 2 * TC_A_BYTES, *b_lo = b_hi + TC_B_BYTES;
         if (it >= 2) tc::mbar_wait(&bar_stage[s], ((it >> 1) - 1) & 1);      // MMAs that read this stage are done
-        tc_stage<TC_M, TC_LBO_A, true>(p, a_hi, a_lo, m0, k0, kend);
-        tc_stage<TC_N, TC_LBO_B, false>(p, b_hi, b_lo, n0, k0, kend);
+        tc_commit<TC_M, TC_LBO_A, true>(p, ra, a_hi, a_lo);
+        tc_commit<TC_N, TC_LBO_B, false>(p, rb, b_hi, b_lo);
+        if (k0 + TC_BK < kend) {                                             // next K block: loads overlap this block's MMAs
+            tc_fetch<TC_M, true>(p, ra, m0, k0 + TC_BK, kend);
+            tc_fetch<TC_N, false>(p, rb, n0, k0 + TC_BK, kend);
+        }
         tc::fence_async_smem();
         __syncthreads();
         if (tid == 0) {
@@ -237,7 +257,7 @@ __global__ void __launch_bounds__(IBINN_THREADS) gemm_tc_kernel(const GemmP p) {
             const uint32_t ah = tc::smem_u32(a_hi), al = tc::smem_u32(a_lo), bh = tc::smem_u32(b_hi), bl = tc::smem_u32(b_lo);
 #pragma unroll
             for (int pass = 0; pass < 3; ++pass) {
-                const uint32_t aa = pass == 2 ? al : ah, bb = pass == 1 ? bl : bh;       // lo terms first would be nicer; order is immaterial in fp32 TMEM
+                const uint32_t aa = pass == 2 ? al : ah, bb = pass == 1 ? bl : bh;
 #pragma unroll
                 for (int ks = 0; ks < TC_BK / 8; ++ks) {
                     const uint64_t da = tc::smem_desc(aa + ks * 2 * TC_LBO_A, TC_LBO_A);
@@ -253,25 +273,38 @@ __global__ void __launch_bounds__(IBINN_THREADS) gemm_tc_kernel(const GemmP p) {
     tc::fence_after_sync();
 
     if (warp < 4) {
-        const int row = m0 + warp * 32 + lane;
+        // TMEM lane = output row, so a thread owns a row: storing from here would scatter every instruction over 32 rows.
+        // Each warp transposes its 32 x 64 block through the (idle) stage buffers and writes rows as 128-byte segments.
+        float* s_o = reinterpret_cast<float*>(tc_smem) + warp * 32 * (TC_N + 1);
         const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16);
 #pragma unroll
         for (int c8 = 0; c8 < TC_N / 8; ++c8) {
             float v[8];
             tc::tmem_ld8(taddr + c8 * 8, v);
             tc::tmem_ld_wait();
-            if (row < p.M) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int j = n0 + c8 * 8 + i;
-                    if (j >= p.N) continue;
-                    float o = v[i];
-                    if (p.bias && blockIdx.z == 0) o += __ldg(p.bias + j);
-                    float* dst = p.C + (size_t)row * p.ldc + j;
-                    if (p.splits > 1) atomicAdd(dst, o);
-                    else if (p.accumulate) *dst += o;
-                    else *dst = o;
-                }
+            for (int i = 0; i < 8; ++i) s_o[lane * (TC_N + 1) + c8 * 8 + i] = v[i];
+        }
+        __syncwarp();
+        float bj[TC_N / 32];
+#pragma unroll
+        for (int h = 0; h < TC_N / 32; ++h) {
+            const int j = n0 + h * 32 + lane;
+            bj[h] = (p.bias && blockIdx.z == 0 && j < p.N) ? __ldg(p.bias + j) : 0.f;
+        }
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            const int row = m0 + warp * 32 + r;
+            if (row >= p.M) break;
+#pragma unroll
+            for (int h = 0; h < TC_N / 32; ++h) {
+                const int j = n0 + h * 32 + lane;
+                if (j >= p.N) continue;
+                const float o = s_o[r * (TC_N + 1) + h * 32 + lane] + bj[h];
+                float* dst = p.C + (size_t)row * p.ldc + j;
+                if (p.splits > 1) atomicAdd(dst, o);
+                else if (p.accumulate) *dst += o;
+                else *dst = o;
             }
         }
     }
@@ -281,20 +314,40 @@ __global__ void __launch_bounds__(IBINN_THREADS) gemm_tc_kernel(const GemmP p) {
 }
 #endif  // !IBINN_EMU
 
-// out[j] (+)= sum_i pre(A)[i][j]   -- bias gradient
+// out[j] (+)= sum_i pre(A)[i][j]   -- bias gradient.  Block = 32 columns x 8 row slices; every slice keeps 8 independent
+// loads in flight and the slices are combined in fixed order (deterministic).
 __global__ void __launch_bounds__(IBINN_THREADS) colsum_kernel(const float* __restrict__ A, const float* __restrict__ A2,
                                                                const float* __restrict__ mask, int a_pre, float* __restrict__ out,
                                                                int M, int N) {
-    const int j = blockIdx.x * IBINN_THREADS + threadIdx.x;
-    if (j >= N) return;
+    __shared__ float s_part[8][33];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + lane;
     float s = 0.f;
-    for (int i = 0; i < M; ++i) {
-        const size_t off = (size_t)i * N + j;
-        float v = __ldg(A + off);
-        if (a_pre == 2) { v = __ldg(A2 + off) > 0.f ? v : 0.f; if (mask) v *= __ldg(mask + off); }
-        s += v;
+    if (j < N) {
+        for (int i0 = slice; i0 < M; i0 += 8 * 8) {
+            float v[8], h[8], mk[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + 8 * u;
+                v[u] = 0.f; h[u] = 1.f; mk[u] = 1.f;
+                if (i < M) {
+                    const size_t off = (size_t)i * N + j;
+                    v[u] = __ldg(A + off);
+                    if (a_pre == 2) { h[u] = __ldg(A2 + off); if (mask) mk[u] = __ldg(mask + off); }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += (a_pre == 2) ? (h[u] > 0.f ? v[u] : 0.f) * mk[u] : v[u];
+        }
     }
-    out[j] += s;
+    s_part[slice][lane] = s;
+    __syncthreads();
+    if (slice == 0 && j < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += s_part[k][lane];
+        out[j] += t;
+    }
 }
 
 static int gemm_run(GemmP p, cudaStream_t st) {
@@ -377,7 +430,7 @@ extern "C" int ibinn_linear_wgrad(const float* g, const float* h, const float* g
     e = gemm_run(p, st);
     if (e) return e;
     if (db) {
-        IBINN_LAUNCH(colsum_kernel, dim3((N + IBINN_THREADS - 1) / IBINN_THREADS), dim3(IBINN_THREADS), 0, st, g, h, g_mask,
+        IBINN_LAUNCH(colsum_kernel, dim3((N + 31) / 32), dim3(IBINN_THREADS), 0, st, g, h, g_mask,
                      g_pre, db, B, N);
         return ibinn_launch_status();
     }

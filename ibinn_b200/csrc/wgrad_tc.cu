@@ -46,7 +46,11 @@ struct WgTcGeom {
 static inline int rup(int v, int m) { return (v + m - 1) / m * m; }
 
 static bool wg_geometry(const ibinn_wgrad_args& a, WgTcGeom& g) {
-    if (a.stride != 1 || a.Hout != a.Hin || a.Wout != a.Win) return false;
+    if (a.stride == 2) {
+        // stride 2: the gradient is zero-inserted onto the input grid while it is staged (even rows / columns carry g, the
+        // rest is zero), after which the layer is an ordinary stride-1 weight gradient over the input pixels
+        if (a.ksize != 3 || (a.Hin & 1) || (a.Win & 1) || a.Hout != a.Hin / 2 || a.Wout != a.Win / 2) return false;
+    } else if (a.stride != 1 || a.Hout != a.Hin || a.Wout != a.Win) return false;
     if (a.Cout > 64 || a.Cin > 80 || a.Cout > WT_MAXC || a.Cin > WT_MAXC) return false;
     g.pad = a.ksize / 2;
     g.kk = a.ksize * a.ksize;
@@ -93,7 +97,7 @@ static bool wg_geometry(const ibinn_wgrad_args& a, WgTcGeom& g) {
     g.ncta = (g.nblocks + g.bpc - 1) / g.bpc;
     g.rec_floats = rup(g.kk * a.Cout * a.Cin + (a.dbias ? a.Cout : 0), 4);      // records stay 16-byte aligned
     if (a.g_pre == IBINN_PRE_BNBWD && a.gh_bs != a.g_bs) return false;      // the staging code addresses g and gh with one offset
-    g.vec_g = (a.Win % 4 == 0) && (a.g_bs % 4 == 0) && (((uintptr_t)a.g & 15) == 0) &&
+    g.vec_g = (a.stride == 1) && (a.Win % 4 == 0) && (a.g_bs % 4 == 0) && (((uintptr_t)a.g & 15) == 0) &&
               (a.g_pre != IBINN_PRE_BNBWD || ((a.gh_bs % 4 == 0) && (((uintptr_t)a.gh & 15) == 0)));
     g.vec_x = (a.Win % 4 == 0) && (a.x_bs % 4 == 0) && (((uintptr_t)a.x & 15) == 0);
     return true;
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
     __shared__ int s_trow[256];                       // per A row (tile, dy copy, co): smem byte offset | co << 20 | (cp + 2) << 28
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int HW = p.Hin * p.Win;
+    const int HW = p.Hin * p.Win, HWg = p.Hout * p.Wout;      // channel strides of x and of g / gh
     if (tid == 0) WDBG(0);
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) { tc::mbar_init(&full[i], 256); tc::mbar_init(&empty[i], 1); }
@@ -254,7 +258,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
                 int b = bimg, r = rin - (K3 ? d3 - 1 : 0);
                 if (r < 0) { r += g.rows_img; --b; } else if (r >= g.rows_img) { r -= g.rows_img; ++b; }
                 const int y = r - g.pad;
-                if (b >= 0 && b < p.B && y >= 0 && c0 < p.Win) { ok3[d3] = true; base3[d3] = (long long)b * p.g_bs + (long long)y * p.Win + c0; }
+                if (b >= 0 && b < p.B && y >= 0 && c0 < p.Win) {
+                    if (p.stride == 1) { ok3[d3] = true; base3[d3] = (long long)b * p.g_bs + (long long)y * p.Win + c0; }
+                    else if (!(y & 1)) { ok3[d3] = true; base3[d3] = (long long)b * p.g_bs + (long long)(y >> 1) * p.Wout + (c0 >> 1); }
+                }
             }
             const int bb = bimg, yy = rin - g.pad;
             const bool rowok = (yy >= 0 && bb < p.B);
@@ -298,7 +305,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
                     const int cp = t_cp[u];
                     ok[u] = cp >= 0 && (cp == 0 ? ok3[0] : cp == 1 ? ok3[1] : ok3[2]);
                     if (!ok[u]) continue;
-                    const long long off = (cp == 0 ? base3[0] : cp == 1 ? base3[1] : base3[2]) + (long long)t_co[u] * HW;
+                    const long long off = (cp == 0 ? base3[0] : cp == 1 ? base3[1] : base3[2]) + (long long)t_co[u] * HWg;
                     const float* gp = p.g + off;
                     const float* hp = p.gh + off;     // same (b,c,y,x): gh_bs == g_bs is checked on the host
                     if (VEC) {
@@ -311,9 +318,10 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
                     } else {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            if (c0 + j < p.Win) {
-                                v[u][j] = __ldg(gp + j);
-                                if (GPRE == IBINN_PRE_BNBWD) h[u][j] = __ldg(hp + j);
+                            if (c0 + j < p.Win && (p.stride == 1 || !(j & 1))) {
+                                const int jj = p.stride == 1 ? j : j >> 1;
+                                v[u][j] = __ldg(gp + jj);
+                                if (GPRE == IBINN_PRE_BNBWD) h[u][j] = __ldg(hp + jj);
                             }
                         }
                     }
@@ -327,7 +335,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
                     for (int j = 0; j < 4; ++j) {
                         o[j] = v[u][j];
                         // BN backward is affine (a*g + b*h + c): padded positions must stay exactly zero
-                        if (GPRE == IBINN_PRE_BNBWD && ok[u] && c0 + j < p.Win) o[j] = fmaf(s_ga[t_co[u]], v[u][j], fmaf(s_gb[t_co[u]], h[u][j], s_gc[t_co[u]]));
+                        if (GPRE == IBINN_PRE_BNBWD && ok[u] && c0 + j < p.Win && (VEC || p.stride == 1 || !(j & 1))) o[j] = fmaf(s_ga[t_co[u]], v[u][j], fmaf(s_gb[t_co[u]], h[u][j], s_gc[t_co[u]]));
                     }
                     unsigned char* hi = st + t_row[u] + (size_t)kc * g.lbo_a;
                     wt_store_split(hi, hi + g.a_tile_bytes, o);
@@ -341,12 +349,13 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
                     float o[4] = {0.f, 0.f, 0.f, 0.f};
                     const bool okk = (cp < ND || !K3) && (cp == 0 ? ok3[0] : cp == 1 ? ok3[1] : ok3[2]);
                     if (okk) {
-                        const long long off = (cp == 0 ? base3[0] : cp == 1 ? base3[1] : base3[2]) + (long long)co * HW;
+                        const long long off = (cp == 0 ? base3[0] : cp == 1 ? base3[1] : base3[2]) + (long long)co * HWg;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            if (c0 + j < p.Win) {
-                                float tv = __ldg(p.g + off + j);
-                                if (GPRE == IBINN_PRE_BNBWD) tv = fmaf(s_ga[co], tv, fmaf(s_gb[co], __ldg(p.gh + off + j), s_gc[co]));
+                            if (c0 + j < p.Win && (p.stride == 1 || !(j & 1))) {
+                                const int jj = p.stride == 1 ? j : j >> 1;
+                                float tv = __ldg(p.g + off + jj);
+                                if (GPRE == IBINN_PRE_BNBWD) tv = fmaf(s_ga[co], tv, fmaf(s_gb[co], __ldg(p.gh + off + jj), s_gc[co]));
                                 o[j] = tv;
                             }
                         }

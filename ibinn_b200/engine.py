@@ -99,8 +99,6 @@ class WeightPrep:
             if not isinstance(m, ConvSubnet):
                 continue
             for conv in (m.conv1, m.conv2, m.conv3):
-                if conv.stride[0] != 1:
-                    continue
                 w = conv.weight
                 entry = {'valid': False}
                 for tr in (False, True):
