@@ -88,10 +88,12 @@ static bool wg_geometry(const ibinn_wgrad_args& a, WgTcGeom& g) {
     if (g.nstage < 2) return false;
     g.nblocks = (g.Q + 4 * g.kc - 1) / (4 * g.kc);
     g.smem_bytes = (size_t)g.nstage * g.stage_bytes + (5 * WT_MAXC) * 4 + 256;
-    // Small layers (<= 16k padded pixels: the 8x8 stage) get at most 64 CTAs: their dgrad chain occupies only 64-81 SMs, so a
-    // weight-gradient kernel forked onto a side stream fits beside it, and the record volume (one 9 Cout Cin record per CTA,
-    // written and re-read through L2/HBM) drops with the CTA count.
-    const int cta_cap = g.Q <= 16384 ? 64 : 148;
+    // CTA caps (measured on the full step, side stream on).  The 8x8 stage (<= 16k padded pixels) gets at most 64 CTAs: its
+    // dgrad chain occupies 64-81 SMs, so a weight-gradient kernel forked onto the side stream fits beside it, and the record
+    // volume (one 9 Cout Cin record per CTA, written and re-read through L2/HBM) drops with the CTA count.  The 16x16 stage
+    // gets 80: half-width weight-gradient kernels interleave with the main chain's launch gaps, tails and single-tile CTAs
+    // (10.8 vs 11.1 ms per step); wider layers keep all SMs.
+    const int cta_cap = g.Q <= 16384 ? 64 : g.Q <= 65536 ? 80 : 148;
     g.ncta = g.nblocks < cta_cap ? g.nblocks : cta_cap;
     g.bpc = (g.nblocks + g.ncta - 1) / g.ncta;
     g.ncta = (g.nblocks + g.bpc - 1) / g.bpc;
