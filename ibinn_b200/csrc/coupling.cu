@@ -20,6 +20,7 @@ struct AioP {
     // backward only
     const float* g_out; const float* g_jac; const float* out_saved;
     float* g_x; float* g_a; float* g_an; float* g_off; float* partials; unsigned* counter;
+    int nsplit, defer;
 };
 
 // MODE 0: forward   out = (w . [x1 | x2*exp(sig)+t]) * exp(an) + off ; jac = sum sig + HW*sum an
@@ -164,12 +165,14 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_affine_inverse_kernel(const
 __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
     IBINN_DYN_SMEM(float, smem);
     __shared__ int s_flag;
-    const int C = p.C, HW = p.HW, HWp = round4(HW), Cp = round4(C);
+    // A sample may be split over `nsplit` CTAs along the pixel axis (HWl pixels each, starting at qo): nothing in the backward
+    // couples pixels except the ActNorm sums, which are per-CTA partial records anyway.
+    const int C = p.C, HW = p.HW, HWl = HW / p.nsplit, HWp = round4(HWl), Cp = round4(C);
     const int c1 = C - C / 2, c2 = C / 2;
     float* s_u = smem;                   // g_v [C][HWp]
     float* s_w = s_u + (size_t)C * HWp;  // [C(out)][Cp(in)]
-    const int tid = threadIdx.x, b = blockIdx.x, lane = tid & 31, wid = tid >> 5;
-    const size_t ib = (size_t)b * C * HW;
+    const int tid = threadIdx.x, b = blockIdx.x / p.nsplit, qo = (blockIdx.x % p.nsplit) * HWl, lane = tid & 31, wid = tid >> 5;
+    const size_t ib = (size_t)b * C * HW + qo;
     const float gj = p.g_jac ? __ldg(p.g_jac + b) : 0.f;
 
     for (int e = tid; e < C * Cp; e += IBINN_THREADS) {
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
         s_w[e] = (i < C) ? __ldg(p.w + (size_t)o * C + i) : 0.f;
     }
     // phase A: g_v = g_out * exp(an) into shared memory, per-channel sums of g and g (y - off) for the ActNorm gradients
-    if (HW % 32 == 0) {
+    if (HWl % 32 == 0) {
         // fast path: every load of the sample is in flight at once; a warp's 32 consecutive elements share a channel, so
         // a warp reduction per element group and a fixed-order sum of the HW/32 group partials per channel finish the job
         float* s_sc = s_w + (size_t)C * Cp;
@@ -186,20 +189,23 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
         for (int c = tid; c < C; c += IBINN_THREADS) { s_sc[c] = expf(p.an[c]); s_of[c] = p.off[c]; }
         __syncthreads();
         constexpr int KB = 12;
-        const int n = C * HW;
+        const int n = C * HWl;
         for (int e0 = 0; e0 < n; e0 += IBINN_THREADS * KB) {
             float g[KB], y[KB];
 #pragma unroll
             for (int k = 0; k < KB; ++k) {
                 const int e = e0 + tid + IBINN_THREADS * k;
                 g[k] = 0.f; y[k] = 0.f;
-                if (e < n) { g[k] = __ldg(p.g_out + ib + e); y[k] = __ldg(p.out_saved + ib + e); }
+                if (e < n) {
+                    const int o = e / HWl, q = e - o * HWl;
+                    g[k] = __ldg(p.g_out + ib + (size_t)o * HW + q); y[k] = __ldg(p.out_saved + ib + (size_t)o * HW + q);
+                }
             }
 #pragma unroll
             for (int k = 0; k < KB; ++k) {
                 const int e = e0 + tid + IBINN_THREADS * k;
                 if (e - lane >= n) continue;                 // whole warp in or out (n is a multiple of 32)
-                const int o = e / HW, q = e - o * HW;
+                const int o = e / HWl, q = e - o * HWl;
                 s_u[(size_t)o * HWp + q] = g[k] * s_sc[o];
                 const float so = warp_sum(g[k]), sn = warp_sum(g[k] * (y[k] - s_of[o]));
                 if (lane == 0) { s_part[(e >> 5) * 2] = so; s_part[(e >> 5) * 2 + 1] = sn; }
@@ -207,11 +213,11 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
         }
         __syncthreads();
         if (tid < C) {
-            const int per = HW / 32;
+            const int per = HWl / 32;
             float so = 0.f, sn = 0.f;
             for (int i = tid * per; i < (tid + 1) * per; ++i) { so += s_part[2 * i]; sn += s_part[2 * i + 1]; }
-            p.partials[((size_t)b * 2 + 0) * C + tid] = so;
-            p.partials[((size_t)b * 2 + 1) * C + tid] = sn + (float)HW * gj;
+            p.partials[((size_t)blockIdx.x * 2 + 0) * C + tid] = so;
+            p.partials[((size_t)blockIdx.x * 2 + 1) * C + tid] = sn + (float)HWl * gj;
         }
     } else {
     for (int o = wid; o < C; o += IBINN_THREADS / 32) {
@@ -219,7 +225,7 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
         float so = 0.f, sn = 0.f;
         for (int q = lane; q < HWp; q += 32) {
             float gv = 0.f;
-            if (q < HW) {
+            if (q < HWl) {
                 const float g = __ldg(p.g_out + ib + (size_t)o * HW + q);
                 const float y = __ldg(p.out_saved + ib + (size_t)o * HW + q);
                 so += g;
@@ -231,8 +237,8 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
         so = warp_sum(so);
         sn = warp_sum(sn);
         if (lane == 0) {
-            p.partials[((size_t)b * 2 + 0) * C + o] = so;
-            p.partials[((size_t)b * 2 + 1) * C + o] = sn + (float)HW * gj;
+            p.partials[((size_t)blockIdx.x * 2 + 0) * C + o] = so;
+            p.partials[((size_t)blockIdx.x * 2 + 1) * C + o] = sn + (float)HWl * gj;
         }
     }
     }
@@ -240,9 +246,9 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
 
     // phase B: g_u = w^T g_v, then the affine-coupling backward per element
     const int npg = HWp / 4, nig = Cp / 4;
-    const bool vec = (HW % 4) == 0;
-    const float* ab = p.a + (size_t)b * 2 * c2 * HW;
-    float* gab = p.g_a + (size_t)b * 2 * c2 * HW;
+    const bool vec = (HW % 4) == 0 && (HWl % 4) == 0;
+    const float* ab = p.a + (size_t)b * 2 * c2 * HW + qo;
+    float* gab = p.g_a + (size_t)b * 2 * c2 * HW + qo;
     const float ak = p.alpha * p.clamp;
     for (int item = tid; item < npg * nig; item += IBINN_THREADS) {
         const int pg = item % npg, ig = item / npg;
@@ -263,7 +269,7 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
                 xv[i][0] = x4.x; xv[i][1] = x4.y; xv[i][2] = x4.z; xv[i][3] = x4.w;
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (pg * 4 + j < HW) { sv[i][j] = __ldg(sp + j); xv[i][j] = __ldg(xp + j); }
+                for (int j = 0; j < 4; ++j) if (pg * 4 + j < HWl) { sv[i][j] = __ldg(sp + j); xv[i][j] = __ldg(xp + j); }
             }
         }
         float acc[4][4];
@@ -296,7 +302,7 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
                 for (int j = 0; j < 4; ++j) {
                     const int q = pg * 4 + j;
                     gx[j] = 0.f; gs[j] = 0.f;
-                    if (q < HW) {
+                    if (q < HWl) {
                         const float th = tanhf(p.alpha * sv[i][j]);
                         const float es = expf(p.clamp * th);
                         const float gu = acc[i][j];
@@ -311,20 +317,22 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
                     st4(dt, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) if (pg * 4 + j < HW) { ds[j] = gs[j]; dt[j] = acc[i][j]; }
+                    for (int j = 0; j < 4; ++j) if (pg * 4 + j < HWl) { ds[j] = gs[j]; dt[j] = acc[i][j]; }
                 }
             }
             float* dx = p.g_x + ib + (size_t)ic * HW + pg * 4;
             if (vec) st4(dx, make_float4(gx[0], gx[1], gx[2], gx[3]));
             else
 #pragma unroll
-                for (int j = 0; j < 4; ++j) if (pg * 4 + j < HW) dx[j] = gx[j];
+                for (int j = 0; j < 4; ++j) if (pg * 4 + j < HWl) dx[j] = gx[j];
         }
     }
 
     // ActNorm parameter gradients: the last CTA sums the per-sample partials (fixed order: sample groups, then groups)
+    if (p.defer) return;                 // the caller sums the records of many blocks with one launch (ibinn_aio_param_reduce_many)
     if (!last_block_ticket(p.counter, gridDim.x, &s_flag)) return;
     {
+        const int nrec = p.B * p.nsplit;
         const int T = 2 * C, ngrp = IBINN_THREADS / T > 0 ? IBINN_THREADS / T : 1;
         const bool par = (ngrp * T <= C * HWp) && (T <= IBINN_THREADS);
         if (par) {
@@ -332,12 +340,12 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
             float t = 0.f;
             if (grp < ngrp) {
                 constexpr int UB = 8;
-                for (int b0 = grp; b0 < p.B; b0 += ngrp * UB) {
+                for (int b0 = grp; b0 < nrec; b0 += ngrp * UB) {
                     float v[UB];
 #pragma unroll
                     for (int u = 0; u < UB; ++u) {
                         const int bb = b0 + u * ngrp;
-                        v[u] = bb < p.B ? __ldcg(p.partials + (size_t)bb * T + e) : 0.f;
+                        v[u] = bb < nrec ? __ldcg(p.partials + (size_t)bb * T + e) : 0.f;
                     }
 #pragma unroll
                     for (int u = 0; u < UB; ++u) t += v[u];
@@ -354,7 +362,7 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
         } else {
             for (int e = tid; e < T; e += IBINN_THREADS) {
                 float t = 0.f;
-                for (int bb = 0; bb < p.B; ++bb) t += __ldcg(p.partials + (size_t)bb * T + e);
+                for (int bb = 0; bb < nrec; ++bb) t += __ldcg(p.partials + (size_t)bb * T + e);
                 if (e < C) { if (p.g_off) p.g_off[e] += t; }
                 else if (p.g_an) p.g_an[e - C] += t;
             }
@@ -509,23 +517,79 @@ extern "C" int ibinn_aio_affine_inverse(float* u, const float* a, const float* a
     return ibinn_launch_status();
 }
 
+static int aio_bwd_nsplit(int HW) { return (HW % 64 == 0) ? 2 : 1; }      // two CTAs per sample when each half keeps whole warps
+
+extern "C" int ibinn_aio_backward_records(int B, int C, int H, int W) {
+    (void)C;
+    if (B <= 0 || H <= 0 || W <= 0) return IBINN_EINVAL;
+    return B * aio_bwd_nsplit(H * W);
+}
+
 extern "C" int ibinn_aio_coupling_backward(const float* g_out, const float* g_jac, const float* x, const float* a,
                                            const float* out, const float* w, const float* act_norm,
                                            const float* act_offset, float* g_x, float* g_a, float* g_act_norm,
                                            float* g_act_offset, float* partials, uint32_t* counter, int B, int C, int H,
-                                           int W, float clamp, float alpha, ibinn_stream_t stream) {
+                                           int W, float clamp, float alpha, int defer_reduce, ibinn_stream_t stream) {
     IBINN_ENTRY_GUARD();
-    if (!g_out || !x || !out || !w || !act_norm || !act_offset || !g_x || !partials || !counter) return IBINN_ENULL;
+    if (!g_out || !x || !out || !w || !act_norm || !act_offset || !g_x || !partials || (!defer_reduce && !counter)) return IBINN_ENULL;
     if (C > 1 && (!a || !g_a)) return IBINN_ENULL;
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return IBINN_EINVAL;
     AioP p{};
     p.g_out = g_out; p.g_jac = g_jac; p.x = x; p.a = a; p.out_saved = out; p.w = w; p.an = act_norm; p.off = act_offset;
     p.g_x = g_x; p.g_a = g_a; p.g_an = g_act_norm; p.g_off = g_act_offset; p.partials = partials; p.counter = counter;
     p.B = B; p.C = C; p.HW = H * W; p.clamp = clamp; p.alpha = alpha;
-    size_t sm = aio_smem(C, H * W);
+    p.nsplit = aio_bwd_nsplit(H * W);
+    p.defer = defer_reduce ? 1 : 0;
+    size_t sm = aio_smem(C, H * W / p.nsplit);
     int e = ibinn_set_smem(aio_bwd_kernel, sm);
     if (e) return e;
-    IBINN_LAUNCH(aio_bwd_kernel, dim3(B), dim3(IBINN_THREADS), sm, (cudaStream_t)stream, p);
+    IBINN_LAUNCH(aio_bwd_kernel, dim3(B * p.nsplit), dim3(IBINN_THREADS), sm, (cudaStream_t)stream, p);
+    return ibinn_launch_status();
+}
+
+namespace {
+// one block per table entry: thread <-> (record group, element); groups combined in fixed order
+__global__ void __launch_bounds__(IBINN_THREADS) aio_reduce_many_kernel(const ibinn_aio_reduce_desc* __restrict__ table) {
+    __shared__ float s_red[IBINN_THREADS];
+    const ibinn_aio_reduce_desc d = table[blockIdx.x];
+    const int T = 2 * d.C, tid = threadIdx.x;
+    for (int e0 = 0; e0 < T; e0 += IBINN_THREADS) {              // T <= 256 in every shipped config: one pass
+        const int Tl = min(T - e0, IBINN_THREADS);
+        const int ngrp = IBINN_THREADS / Tl;
+        const int e = tid % Tl, grp = tid / Tl;
+        float t = 0.f;
+        if (grp < ngrp) {
+            constexpr int UB = 8;
+            for (int r0 = grp; r0 < d.nrec; r0 += ngrp * UB) {
+                float v[UB];
+#pragma unroll
+                for (int u = 0; u < UB; ++u) {
+                    const int r = r0 + u * ngrp;
+                    v[u] = r < d.nrec ? __ldg(d.partials + (size_t)r * T + e0 + e) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < UB; ++u) t += v[u];
+            }
+        }
+        __syncthreads();
+        s_red[tid] = t;
+        __syncthreads();
+        if (tid < Tl) {
+            float tot = 0.f;
+            for (int gi = 0; gi < ngrp; ++gi) tot += s_red[gi * Tl + tid];
+            const int c = e0 + tid;
+            if (c < d.C) { if (d.g_act_offset) d.g_act_offset[c] += tot; }
+            else if (d.g_act_norm) d.g_act_norm[c - d.C] += tot;
+        }
+    }
+}
+}  // namespace
+
+extern "C" int ibinn_aio_param_reduce_many(const ibinn_aio_reduce_desc* table, int n, ibinn_stream_t stream) {
+    IBINN_ENTRY_GUARD();
+    if (!table) return IBINN_ENULL;
+    if (n <= 0 || n > 65535) return IBINN_EINVAL;
+    IBINN_LAUNCH(aio_reduce_many_kernel, dim3(n), dim3(IBINN_THREADS), 0, (cudaStream_t)stream, table);
     return ibinn_launch_status();
 }
 

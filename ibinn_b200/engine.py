@@ -211,13 +211,18 @@ class TrainStep:
         else:
             loss = self.bx * losses['L_x_tr'] - self.by * losses['L_y_tr']
         ops.DEFERRED_WGRAD = pending = []
+        ops.DEFERRED_AIO = pending_aio = [] if self.x.is_cuda else None
         ops.WGRAD_STREAMS = self.side_streams
         try:
             loss.backward()
             ops.join_wgrad_streams()
         finally:
             ops.DEFERRED_WGRAD = None
+            ops.DEFERRED_AIO = None
             ops.WGRAD_STREAMS = None
+        if pending_aio:
+            self._pinned_aio = ops.flush_deferred_aio(pending_aio, self.x, getattr(self, '_pinned_aio', None))
+            self._pending_aio = pending_aio    # keeps the records alive until the reduction has run
         self._pinned = ops.flush_deferred_wgrad(pending, self.x, getattr(self, '_pinned', None))
         self._pending = pending            # keeps the record workspaces alive until the reduction has run
         self.out = {k: losses[k].detach() for k in ('L_x_tr', 'L_y_tr', 'acc_tr', 'L_cNLL_tr')}

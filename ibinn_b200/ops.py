@@ -229,18 +229,44 @@ def aio_coupling_forward(x, a, w, act_norm, act_offset, clamp, alpha=0.1):
     return out, jac
 
 
+DEFERRED_AIO = None         # list while engine.TrainStep collects the ActNorm-gradient records of the AIO blocks, else None
+
+
 def aio_coupling_backward(g_out, g_jac, x, a, out, w, act_norm, act_offset, clamp, alpha, g_act_norm, g_act_offset):
     """returns g_x, g_a; accumulates into g_act_norm / g_act_offset (C)."""
     B, C, H, W = x.shape
     g_out = g_out.contiguous()
     g_x = torch.empty_like(x)
     g_a = torch.empty_like(a)
-    part = torch.empty(B * 2 * C, dtype=torch.float32, device=x.device)
-    check(_lib.lib().ibinn_aio_coupling_backward(ptr(g_out), ptr(g_jac), ptr(x), ptr(a), ptr(out), ptr(w), ptr(act_norm),
-                                                 ptr(act_offset), ptr(g_x), ptr(g_a), ptr(g_act_norm), ptr(g_act_offset),
-                                                 ptr(part), counter_ptr(x), B, C, H, W, clamp, alpha, stream(x)),
+    L = _lib.lib()
+    nrec = L.ibinn_aio_backward_records(B, C, H, W)
+    if nrec <= 0:
+        check(nrec, 'aio_backward_records')
+    part = torch.empty(nrec * 2 * C, dtype=torch.float32, device=x.device)
+    defer = DEFERRED_AIO is not None
+    check(L.ibinn_aio_coupling_backward(ptr(g_out), ptr(g_jac), ptr(x), ptr(a), ptr(out), ptr(w), ptr(act_norm),
+                                        ptr(act_offset), ptr(g_x), ptr(g_a), ptr(g_act_norm), ptr(g_act_offset),
+                                        ptr(part), None if defer else counter_ptr(x), B, C, H, W, clamp, alpha, int(defer), stream(x)),
           'aio_coupling_backward')
+    if defer:
+        # engine.TrainStep: one launch sums the records of all blocks after the backward pass
+        DEFERRED_AIO.append((part, _lib.AioReduceDesc(ptr(part), ptr(g_act_offset), ptr(g_act_norm), nrec, C)))
     return g_x, g_a
+
+
+def flush_deferred_aio(entries, ref, pinned):
+    """one launch for the ActNorm-gradient records of every AIO block; `pinned` = reusable pinned uint8 staging tensor or None"""
+    import numpy as np
+    if not entries:
+        return pinned
+    raw = b''.join(bytes(d) for _, d in entries)
+    if pinned is None or pinned.numel() < len(raw):
+        pinned = torch.empty(len(raw), dtype=torch.uint8).pin_memory()
+    pinned[:len(raw)].copy_(torch.from_numpy(np.frombuffer(raw, dtype=np.uint8).copy()))
+    table = torch.empty(len(raw), dtype=torch.uint8, device=ref.device)
+    table.copy_(pinned[:len(raw)], non_blocking=True)
+    check(_lib.lib().ibinn_aio_param_reduce_many(ptr(table, torch.uint8), len(entries), stream(ref)), 'aio_param_reduce_many')
+    return pinned
 
 
 def aio_unpermute(y, w_inv, act_norm, act_offset):

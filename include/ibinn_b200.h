@@ -157,12 +157,25 @@ int ibinn_aio_coupling_forward(const float* x, const float* a, const float* w, c
                                const float* act_offset, float* out, float* jac, int B, int C, int H, int W,
                                float clamp, float alpha, ibinn_stream_t stream);
 /* hand-derived backward.  `out` is the forward output.  g_act_norm /
- * g_act_offset (C) are accumulated into; partials: B*2*C floats. */
+ * g_act_offset (C) are accumulated into.  A sample is processed by ibinn_aio_backward_records(...)/B CTAs; each CTA
+ * writes one record of 2*C floats (sum g, sum g*(y - offset) + pixels*g_jac) to `partials`
+ * (ibinn_aio_backward_records(B,C,H,W) * 2*C floats).  defer_reduce = 0: the last CTA adds the records to g_act_offset /
+ * g_act_norm; 1: the caller does it for many blocks at once with ibinn_aio_param_reduce_many. */
+int ibinn_aio_backward_records(int B, int C, int H, int W);
 int ibinn_aio_coupling_backward(const float* g_out, const float* g_jac, const float* x, const float* a,
                                 const float* out, const float* w, const float* act_norm, const float* act_offset,
                                 float* g_x, float* g_a, float* g_act_norm, float* g_act_offset, float* partials,
                                 uint32_t* counter, int B, int C, int H, int W, float clamp, float alpha,
-                                ibinn_stream_t stream);
+                                int defer_reduce, ibinn_stream_t stream);
+typedef struct {
+    const float* partials;   /* nrec records of 2*C floats */
+    float* g_act_offset;     /* (C), accumulated into; may be NULL */
+    float* g_act_norm;       /* (C), accumulated into; may be NULL */
+    int32_t nrec, C;
+} ibinn_aio_reduce_desc;
+/* g_act_offset[c] += sum_r partials[r][c],  g_act_norm[c] += sum_r partials[r][C + c]  for every entry of the table
+ * (device memory, n entries), records summed in index order. */
+int ibinn_aio_param_reduce_many(const ibinn_aio_reduce_desc* table, int n, ibinn_stream_t stream);
 /* inverse direction (all_in_one_block.py:69,93-103): u = w_inv . ((y - act_offset) * exp(-act_norm)),
  * then, with a = subnet(u[:, :C-C/2]):  u[:, C-C/2:] <- (u2 - t) * exp(-sig) in place; jac = -(...) */
 int ibinn_aio_unpermute(const float* y, const float* w_inv, const float* act_norm, const float* act_offset, float* u,

@@ -225,3 +225,33 @@ def test_permute(dev, D):
     run_node(blk, spec, x, dev, False)
     y = blk([x.to(dev)])[0]
     assert torch.equal(y.cpu(), x[:, blk.perm])          # bit-exact gather
+
+
+def test_aio_backward_deferred_record_reduction(dev):
+    """ActNorm gradients through the per-CTA records + ibinn_aio_param_reduce_many (what engine.TrainStep does for all
+    blocks with one launch) equal the in-kernel last-CTA reduction."""
+    import numpy as np
+    from ibinn_b200 import _lib, ops
+    g = torch.Generator().manual_seed(9)
+    B, C, H = 5, 12, 8
+    c2 = C // 2
+    d = lambda t: t.to(dev)
+    x, a = torch.randn(B, C, H, H, generator=g), torch.randn(B, 2 * c2, H, H, generator=g)
+    w = torch.linalg.qr(torch.randn(C, C, generator=g))[0].contiguous()
+    an, off = torch.randn(C, generator=g) * 0.1, torch.randn(C, generator=g) * 0.1
+    out, _ = ops.aio_coupling_forward(d(x), d(a), d(w), d(an), d(off), 2.0)
+    go, gj = torch.randn(B, C, H, H, generator=g), torch.randn(B, generator=g)
+    ref_an, ref_off = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    gx0, ga0 = ops.aio_coupling_backward(d(go), d(gj), d(x), d(a), out, d(w), d(an), d(off), 2.0, 0.1, ref_an, ref_off)
+    got_an, got_off = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    ops.DEFERRED_AIO = entries = []
+    try:
+        gx1, ga1 = ops.aio_coupling_backward(d(go), d(gj), d(x), d(a), out, d(w), d(an), d(off), 2.0, 0.1, got_an, got_off)
+    finally:
+        ops.DEFERRED_AIO = None
+    assert len(entries) == 1 and float(got_an.abs().max()) == 0.
+    raw = b''.join(bytes(e[1]) for e in entries)
+    table = torch.from_numpy(np.frombuffer(raw, dtype=np.uint8).copy()).to(dev)
+    _lib.check(_lib.lib().ibinn_aio_param_reduce_many(_lib.ptr(table, torch.uint8), len(entries), _lib.stream(table)), 'aio_param_reduce_many')
+    assert torch.equal(gx0, gx1) and torch.equal(ga0, ga1)
+    assert rel(got_an, ref_an) < 1e-6 and rel(got_off, ref_off) < 1e-6
