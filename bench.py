@@ -126,6 +126,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+            os.environ['NCCL_DEBUG'] = 'WARN'          # NCCL prints its version banner on stdout: keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
     torch.manual_seed(0)
     np.random.seed(0)

@@ -11,7 +11,7 @@ from ctypes import POINTER, Structure, c_float, c_int, c_int32, c_int64, c_size_
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libibinn_b200.so')
+LIB_PATH = os.environ.get('IBINN_B200_LIB') or os.path.join(_HERE, 'csrc', 'libibinn_b200.so')      # override: A/B runs of two builds
 
 _lib = None
 _allow_host_pointers = False      # set only by tests/emu (simulator build of the kernels)
