@@ -194,6 +194,11 @@ class TrainStep:
         self.use_graph = bool(use_graph) and dev.type == 'cuda'
         n_side = int(os.environ.get('IBINN_WGRAD_STREAMS', '1'))
         self.side_streams = [torch.cuda.Stream() for _ in range(n_side)] if dev.type == 'cuda' and n_side > 0 else None
+        # layers per record reduction on a third stream; 0 = one reduction after the backward pass.  Measured: 8 / 16 / 32 are
+        # within noise of 0 (10.76 / 10.90 / 10.81 vs 10.80 ms per step), so the simpler schedule is the default.
+        self.reduce_group = int(os.environ.get('IBINN_WGRAD_REDUCE_GROUP', '0'))
+        self.reduce_stream = torch.cuda.Stream() if self.side_streams and self.reduce_group > 0 else None
+        self._pinned_groups = []
         self._g1 = self._g2 = None
         self.out = None
         self.launches = None
@@ -213,17 +218,25 @@ class TrainStep:
         ops.DEFERRED_WGRAD = pending = []
         ops.DEFERRED_AIO = pending_aio = [] if self.x.is_cuda else None
         ops.WGRAD_STREAMS = self.side_streams
+        grouped = self.side_streams is not None and self.reduce_stream is not None
+        if grouped:
+            ops.WGRAD_REDUCE = dict(stream=self.reduce_stream, group=self.reduce_group, pinned=self._pinned_groups, upto=0, keep=[])
         try:
             loss.backward()
+            if grouped:
+                ops.flush_wgrad_group(final=True)
+                self._reduce_keep = ops.WGRAD_REDUCE['keep']
             ops.join_wgrad_streams()
         finally:
             ops.DEFERRED_WGRAD = None
             ops.DEFERRED_AIO = None
             ops.WGRAD_STREAMS = None
+            ops.WGRAD_REDUCE = None
         if pending_aio:
             self._pinned_aio = ops.flush_deferred_aio(pending_aio, self.x, getattr(self, '_pinned_aio', None))
             self._pending_aio = pending_aio    # keeps the records alive until the reduction has run
-        self._pinned = ops.flush_deferred_wgrad(pending, self.x, getattr(self, '_pinned', None))
+        if not grouped:
+            self._pinned = ops.flush_deferred_wgrad(pending, self.x, getattr(self, '_pinned', None))
         self._pending = pending            # keeps the record workspaces alive until the reduction has run
         self.out = {k: losses[k].detach() for k in ('L_x_tr', 'L_y_tr', 'acc_tr', 'L_cNLL_tr')}
 
