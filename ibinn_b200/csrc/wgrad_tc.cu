@@ -39,6 +39,7 @@ struct WgTcGeom {
     int pad, kk, P4, rows_img, S4, Q, nblocks, ncta, bpc;     // bpc = K blocks per CTA
     int coutp, cinp, na, ntile, nd, np, ones_row, nstage, tmem_cols;
     int a_tile_bytes, b_bytes, stage_bytes, lbo_a, lbo_b, rec_floats;
+    int sdec, sh, G8, sbo_a, kcs;          // chunks per padded row, chunk shift between dy slots, 8-row groups of G, A group stride, strip chunks
     int vec_g, vec_x, kc;
     size_t smem_bytes;
 };
@@ -54,11 +55,19 @@ static bool wg_geometry(const ibinn_wgrad_args& a, WgTcGeom& g) {
     if (a.Cout > 64 || a.Cin > 80 || a.Cout > WT_MAXC || a.Cin > WT_MAXC) return false;
     g.pad = a.ksize / 2;
     g.kk = a.ksize * a.ksize;
-    g.P4 = rup(a.Win + g.pad, 4);
+    g.coutp = rup(a.Cout, 8);
+    g.G8 = g.coutp / 8;
+    // chunks per padded row: coprime with the number of 8-row groups of G (see the strip layout below)
+    g.sdec = (a.Win + g.pad + 3) / 4;
+    if (a.ksize == 3) {
+        auto gcd = [](int x, int y) { while (y) { const int t = x % y; x = y; y = t; } return x; };
+        while (gcd(g.sdec, g.G8) != 1) ++g.sdec;
+    }
+    g.P4 = 4 * g.sdec;
+    g.sh = a.ksize == 3 ? g.sdec : 0;
     g.rows_img = a.Hin + g.pad;
     g.S4 = g.rows_img * g.P4;
     g.Q = a.B * g.S4 + g.pad * g.P4;
-    g.coutp = rup(a.Cout, 8);
     g.cinp = rup(a.Cin, 8);
     g.nd = a.ksize;                                   // dx copies
     g.na = 128 / g.coutp < a.ksize ? 128 / g.coutp : a.ksize;   // dy copies stacked in one A tile
@@ -68,18 +77,27 @@ static bool wg_geometry(const ibinn_wgrad_args& a, WgTcGeom& g) {
     if (g.np > 256 || g.ntile * g.np > 512) return false;
     int cols = g.ntile * g.np;
     g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-    // K-chunk pitch = an ODD number of 16-byte rows: the staging threads of a quarter-warp write the same row of eight
-    // consecutive chunks, which must fall into eight different bank groups
-    g.lbo_a = 129 * 16;
+    // A operand = ONE strip of G per K block, no row-shifted copies: chunk kappa, 8-row group gg of G live at byte
+    // 128 (kappa G8 + gg sh) (+16 per row); read with LBO = 128 G8 and SBO = 128 sh, descriptor row (slot d, co) of chunk k lands
+    // on strip chunk k + d sh, i.e. the gradient one padded row further.  (kappa, gg) -> kappa G8 + gg sh is injective because
+    // gcd(G8, sh) = 1.  The strip covers chunks [k0 - sh, k0 + kc + sh).
+    g.lbo_a = 128 * g.G8;
+    g.sbo_a = a.ksize == 3 ? 128 * g.sh : 128;
+    // B: K-chunk pitch = an ODD number of 16-byte rows (the eight lanes of a quarter-warp write the same row of eight
+    // consecutive chunks, which must fall into eight different bank groups)
     g.lbo_b = (g.np + 1) * 16;
     // enough staging work per K block to hide the load latency (>= ~4 chunk tasks per staging thread),
     // but at least 2 stages in shared memory (one per staging group)
-    const int tasks_per_chunk = g.ntile * g.na * a.Cout + a.Cin;
+    const int tasks_per_chunk = a.Cout + g.nd * a.Cin;
     g.kc = tasks_per_chunk * 4 >= 1200 ? 4 : tasks_per_chunk * 8 >= 1200 ? 8 : KC_MAX;
     for (;;) {
-        g.a_tile_bytes = g.kc * g.lbo_a;                  // one of hi / lo of one A tile
+        g.kcs = g.kc + 2 * g.sh;
+        const int gs = a.ksize == 3 ? g.sh : 1;
+        const int need = g.kcs * g.G8 + (g.G8 - 1) * gs + 1;                                         // written by the staging threads
+        const int reach = (g.ntile - 1) * g.na * g.sh * g.G8 + (g.kc - 1) * g.G8 + 15 * gs + 1;      // read by an M = 128 descriptor (rows past the data are don't-care)
+        g.a_tile_bytes = 128 * (need > reach ? need : reach);     // one of hi / lo of the strip
         g.b_bytes = g.kc * g.lbo_b;
-        g.stage_bytes = 2 * (g.ntile * g.a_tile_bytes + g.b_bytes);
+        g.stage_bytes = 2 * (g.a_tile_bytes + g.b_bytes);
         g.nstage = (200 * 1024) / g.stage_bytes;
         if (g.nstage >= 2 || g.kc == 4) break;
         g.kc /= 2;
@@ -99,6 +117,7 @@ static bool wg_geometry(const ibinn_wgrad_args& a, WgTcGeom& g) {
     g.ncta = (g.nblocks + g.bpc - 1) / g.bpc;
     g.rec_floats = rup(g.kk * a.Cout * a.Cin + (a.dbias ? a.Cout : 0), 4);      // records stay 16-byte aligned
     if (a.g_pre == IBINN_PRE_BNBWD && a.gh_bs != a.g_bs) return false;      // the staging code addresses g and gh with one offset
+    if ((long long)a.B * a.g_bs >= (1ll << 31) || g.kcs > 64) return false;   // 32-bit position table of <= 64 strip chunks
     g.vec_g = (a.stride == 1) && (a.Win % 4 == 0) && (a.g_bs % 4 == 0) && (((uintptr_t)a.g & 15) == 0) &&
               (a.g_pre != IBINN_PRE_BNBWD || ((a.gh_bs % 4 == 0) && (((uintptr_t)a.gh & 15) == 0)));
     g.vec_x = (a.Win % 4 == 0) && (a.x_bs % 4 == 0) && (((uintptr_t)a.x & 15) == 0);
@@ -134,7 +153,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
     float* s_gc = s_gb + WT_MAXC;
     float* s_xa = s_gc + WT_MAXC;
     float* s_xb = s_xa + WT_MAXC;
-    __shared__ int s_trow[256];                       // per A row (tile, dy copy, co): smem byte offset | co << 20 | (cp + 2) << 28
+    __shared__ int s_postab[WT_GROUPS][64];            // per staging group: g offset of every strip chunk of the current K block (-1: padding)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int HW = p.Hin * p.Win, HWg = p.Hout * p.Wout;      // channel strides of x and of g / gh
@@ -161,19 +180,6 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
             s_xb[c] = p.x_bn.beta[c] - p.x_bn.mean[c] * A;
         }
     }
-    if (tid < 256) {
-        // A-row table (one division per row here instead of per staging thread and row): row r = cp * Cout + co
-        const int n_rows = g.ntile * g.na * p.Cout;
-        int packed = 0;                                  // cp field 0 -> row does not exist
-        if (tid < n_rows) {
-            const int co = tid % p.Cout, cp = tid / p.Cout;
-            const int t = cp / g.na, dyi = cp - t * g.na;
-            const int off = (t * 2 * g.a_tile_bytes) + (dyi * g.coutp + co) * 16;
-            const int cpv = (cp < ND || !K3) ? cp : -1;  // -1: padding copy of the last tile (rows stay zero)
-            packed = off | (co << 20) | ((cpv + 2) << 28);
-        }
-        s_trow[tid] = packed;
-    }
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -193,13 +199,14 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
             tc::fence_after_sync();
             if (lane == 0 && i < 6) WDBG(10 + i);
             const uint32_t st = tc::smem_u32(wts + (size_t)s * g.stage_bytes);
-            const uint32_t b_hi = st + 2 * g.ntile * g.a_tile_bytes, b_lo = b_hi + g.b_bytes;
+            const uint32_t b_hi = st + 2 * g.a_tile_bytes, b_lo = b_hi + g.b_bytes;
             for (int t = 0; t < g.ntile; ++t) {
-                const uint32_t a_hi = st + t * 2 * g.a_tile_bytes, a_lo = a_hi + g.a_tile_bytes;
+                // tile t holds the dy slots [t na, t na + na): its rows start na sh chunks further into the strip
+                const uint32_t a_hi = st + t * g.na * g.sh * g.lbo_a, a_lo = a_hi + g.a_tile_bytes;
                 const uint32_t acc = tmem_d + t * g.np;
 #pragma unroll 1
                 for (int pass = 0; pass < 3; ++pass) {
-                    uint64_t da = tc::smem_desc(pass == 2 ? a_lo : a_hi, g.lbo_a);
+                    uint64_t da = tc::smem_desc_sbo(pass == 2 ? a_lo : a_hi, g.lbo_a, g.sbo_a);
                     uint64_t db = tc::smem_desc(pass == 1 ? b_lo : b_hi, g.lbo_b);
 #pragma unroll 2
                     for (int ks = 0; ks < KC / 2; ++ks) {
@@ -216,24 +223,13 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
         __syncwarp();
     } else {
         // ================= operand staging: WT_GROUPS groups of 256 threads take K blocks round-robin =================
-        // 256 % KC == 0, so a thread always works on the same chunk column kc of a block: its pixel
-        // coordinates are decoded once per block; what varies over its tasks is the channel / copy.
+        // B operand: 256 % KC == 0, so a thread always works on the same chunk column kc of a block and its pixel coordinates
+        // are decoded once per block.  A operand: one strip of G per block (see wg_geometry), tasks = (strip chunk, channel).
         const int grp = tid >> 8, lt = tid & 255;
         const int kc = lt % KC, lane_t = lt / KC, tstride = 256 / KC;
-        const int n_ar = g.ntile * g.na * p.Cout;              // A rows that carry data: (tile, dy copy, co)
         const int n_br = p.Cin + (g.ones_row >= 0 ? 1 : 0);    // B source rows: ci (+ the ones row)
-        // per-thread task table (fixed for the whole kernel): the channel / copy of each of its A rows
-        constexpr int UA = 6;
-        int t_row[UA], t_co[UA], t_cp[UA];                     // smem row offset, channel, dy copy (-1: no data, -2: no such row)
-#pragma unroll
-        for (int u = 0; u < UA; ++u) {
-            const int r = lane_t + u * tstride;
-            const int packed = r < 256 ? s_trow[r] : 0;
-            t_row[u] = packed & 0xfffff;
-            t_co[u] = (packed >> 20) & 0xff;
-            t_cp[u] = ((packed >> 28) & 0xf) - 2;
-        }
-        const bool many_rows = n_ar > UA * tstride;            // shapes with more than UA rows per thread take the slow loop
+        const int gs = K3 ? g.sh : 1;                          // A strip: 8-row groups are gs * 128 bytes apart
+        const int a_dk = 256 / p.Cout, a_dc = 256 % p.Cout;    // strip task e -> (chunk e / Cout, channel e % Cout), advanced by 256
         // Position of this thread's chunk in the padded sequence, kept incrementally (no divisions in the block loop):
         // q = padded position, R0 = q / P4 (padded row), c0 = q % P4, bimg = R0 / rows_img, rin = R0 % rows_img.
         const int q_step = WT_GROUPS * 4 * KC, R_step = q_step / g.P4, c_step = q_step % g.P4;
@@ -248,23 +244,24 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
             if (i >= g.nstage) tc::mbar_wait(&empty[s], ((i / g.nstage) - 1) & 1);
             if (lt == 0 && i < 6) WDBG(20 + 2 * i);
             unsigned char* st = wts + (size_t)s * g.stage_bytes;
-            unsigned char* b_hi = st + 2 * g.ntile * g.a_tile_bytes;
+            unsigned char* b_hi = st + 2 * g.a_tile_bytes;
             const size_t b_lo_off = g.b_bytes;
-            // pixel coordinates of the (up to) three row-shifted copies: padded row R0 - (d3 - 1)
-            long long base3[3];
-            bool ok3[3];
-#pragma unroll
-            for (int d3 = 0; d3 < 3; ++d3) {
-                ok3[d3] = false; base3[d3] = 0;
-                if (!(K3 || d3 == 0)) continue;
-                int b = bimg, r = rin - (K3 ? d3 - 1 : 0);
-                if (r < 0) { r += g.rows_img; --b; } else if (r >= g.rows_img) { r -= g.rows_img; ++b; }
-                const int y = r - g.pad;
-                if (b >= 0 && b < p.B && y >= 0 && c0 < p.Win) {
-                    if (p.stride == 1) { ok3[d3] = true; base3[d3] = (long long)b * p.g_bs + (long long)y * p.Win + c0; }
-                    else if (!(y & 1)) { ok3[d3] = true; base3[d3] = (long long)b * p.g_bs + (long long)(y >> 1) * p.Wout + (c0 >> 1); }
+            // g offsets of the strip chunks [k0 - sh, k0 + KC + sh) of this block (one division chain per chunk, not per task)
+            int* s_pos = s_postab[grp];
+            if (lt < g.kcs) {
+                const int kq = (blk0 + i) * KC - g.sh + lt;
+                int off = -1;
+                if (kq >= 0) {
+                    const int R = kq / g.sdec, c0k = (kq - R * g.sdec) * 4;
+                    const int b = R / g.rows_img, y = R - b * g.rows_img - g.pad;
+                    if (c0k < p.Win && b < p.B && y >= 0) {
+                        if (p.stride == 1) off = b * (int)p.g_bs + y * p.Win + c0k;
+                        else if (!(y & 1)) off = b * (int)p.g_bs + (y >> 1) * p.Wout + (c0k >> 1);
+                    }
                 }
+                s_pos[lt] = off;
             }
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
             const int bb = bimg, yy = rin - g.pad;
             const bool rowok = (yy >= 0 && bb < p.B);
             // ---- issue every global load of this block first, then transform and store
@@ -298,74 +295,68 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
             }
             if (lt == 0 && i == 0) WDBG(40);
             {
-                float v[UA][4], h[UA][4];
-                bool ok[UA];
+                // ---- A: the strip of G.  Lanes run along the channel (8 channels = one 128-byte row group: conflict-free
+                // stores); every task is one 16-byte chunk = 4 pixels of one channel.
+                constexpr int UA = 4;
+                const int ntask = g.kcs * p.Cout;
+                int kap = lt / p.Cout, co = lt - kap * p.Cout;
+                unsigned char* a_hi = st;
+                for (int e0 = lt; e0 < ntask; e0 += 256 * UA) {
+                    float v[UA][4], h[UA][4];
+                    int adr[UA], cch[UA], offs[UA];
 #pragma unroll
-                for (int u = 0; u < UA; ++u) {
+                    for (int u = 0; u < UA; ++u) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { v[u][j] = 0.f; h[u][j] = 0.f; }
-                    const int cp = t_cp[u];
-                    ok[u] = cp >= 0 && (cp == 0 ? ok3[0] : cp == 1 ? ok3[1] : ok3[2]);
-                    if (!ok[u]) continue;
-                    const long long off = (cp == 0 ? base3[0] : cp == 1 ? base3[1] : base3[2]) + (long long)t_co[u] * HWg;
-                    const float* gp = p.g + off;
-                    const float* hp = p.gh + off;     // same (b,c,y,x): gh_bs == g_bs is checked on the host
-                    if (VEC) {
-                        const float4 t4 = *reinterpret_cast<const float4*>(gp);
-                        v[u][0] = t4.x; v[u][1] = t4.y; v[u][2] = t4.z; v[u][3] = t4.w;
-                        if (GPRE == IBINN_PRE_BNBWD) {
-                            const float4 h4 = *reinterpret_cast<const float4*>(hp);
-                            h[u][0] = h4.x; h[u][1] = h4.y; h[u][2] = h4.z; h[u][3] = h4.w;
-                        }
-                    } else {
+                        for (int j = 0; j < 4; ++j) { v[u][j] = 0.f; h[u][j] = 0.f; }
+                        adr[u] = -1; cch[u] = co; offs[u] = -1;
+                        if (kap < g.kcs) {
+                            adr[u] = 128 * (kap * g.G8 + (co >> 3) * gs) + (co & 7) * 16;
+                            const int off = s_pos[kap];
+                            offs[u] = off;
+                            if (off >= 0) {
+                                const float* gp = p.g + (size_t)off + (size_t)co * HWg;
+                                const float* hp = p.gh + (size_t)off + (size_t)co * HWg;     // same (b,c,y,x): gh_bs == g_bs is checked on the host
+                                if (VEC) {
+                                    const float4 t4 = *reinterpret_cast<const float4*>(gp);
+                                    v[u][0] = t4.x; v[u][1] = t4.y; v[u][2] = t4.z; v[u][3] = t4.w;
+                                    if (GPRE == IBINN_PRE_BNBWD) {
+                                        const float4 h4 = *reinterpret_cast<const float4*>(hp);
+                                        h[u][0] = h4.x; h[u][1] = h4.y; h[u][2] = h4.z; h[u][3] = h4.w;
+                                    }
+                                } else {
+                                    // scalar path: ragged widths, unaligned tensors, and stride 2 (g zero-inserted: even pixels only)
+                                    const int R = ((blk0 + i) * KC - g.sh + kap) / g.sdec;
+                                    const int c0k = (((blk0 + i) * KC - g.sh + kap) - R * g.sdec) * 4;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (c0 + j < p.Win && (p.stride == 1 || !(j & 1))) {
-                                const int jj = p.stride == 1 ? j : j >> 1;
-                                v[u][j] = __ldg(gp + jj);
-                                if (GPRE == IBINN_PRE_BNBWD) h[u][j] = __ldg(hp + jj);
+                                    for (int j = 0; j < 4; ++j) {
+                                        if (c0k + j < p.Win && (p.stride == 1 || !(j & 1))) {
+                                            const int jj = p.stride == 1 ? j : j >> 1;
+                                            v[u][j] = __ldg(gp + jj);
+                                            if (GPRE == IBINN_PRE_BNBWD) h[u][j] = __ldg(hp + jj);
+                                        } else h[u][j] = __int_as_float(0x7fc00000);      // marks "no pixel here" for the affine pre-op below
+                                    }
+                                }
                             }
                         }
+                        kap += a_dk; co += a_dc;
+                        if (co >= p.Cout) { co -= p.Cout; ++kap; }
                     }
-                }
-                if (lt == 0 && i == 0) WDBG(41);
 #pragma unroll
-                for (int u = 0; u < UA; ++u) {
-                    if (t_cp[u] == -2) continue;
-                    float o[4];
+                    for (int u = 0; u < UA; ++u) {
+                        if (adr[u] < 0) continue;
+                        float o[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        o[j] = v[u][j];
-                        // BN backward is affine (a*g + b*h + c): padded positions must stay exactly zero
-                        if (GPRE == IBINN_PRE_BNBWD && ok[u] && c0 + j < p.Win && (VEC || p.stride == 1 || !(j & 1))) o[j] = fmaf(s_ga[t_co[u]], v[u][j], fmaf(s_gb[t_co[u]], h[u][j], s_gc[t_co[u]]));
+                        for (int j = 0; j < 4; ++j) {
+                            o[j] = v[u][j];
+                            // BN backward is affine (a*g + b*h + c): padded positions must stay exactly zero
+                            if (GPRE == IBINN_PRE_BNBWD && offs[u] >= 0 && (VEC || h[u][j] == h[u][j]))
+                                o[j] = fmaf(s_ga[cch[u]], v[u][j], fmaf(s_gb[cch[u]], h[u][j], s_gc[cch[u]]));
+                        }
+                        wt_store_split(a_hi + adr[u], a_hi + g.a_tile_bytes + adr[u], o);
                     }
-                    unsigned char* hi = st + t_row[u] + (size_t)kc * g.lbo_a;
-                    wt_store_split(hi, hi + g.a_tile_bytes, o);
                 }
             }
             if (lt == 0 && i == 0) WDBG(42);
-            if (many_rows) {
-                for (int r = lane_t + UA * tstride; r < n_ar; r += tstride) {
-                    const int co = r % p.Cout, cp = r / p.Cout;
-                    const int t = cp / g.na, dyi = cp - t * g.na;
-                    float o[4] = {0.f, 0.f, 0.f, 0.f};
-                    const bool okk = (cp < ND || !K3) && (cp == 0 ? ok3[0] : cp == 1 ? ok3[1] : ok3[2]);
-                    if (okk) {
-                        const long long off = (cp == 0 ? base3[0] : cp == 1 ? base3[1] : base3[2]) + (long long)co * HWg;
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            if (c0 + j < p.Win && (p.stride == 1 || !(j & 1))) {
-                                const int jj = p.stride == 1 ? j : j >> 1;
-                                float tv = __ldg(p.g + off + jj);
-                                if (GPRE == IBINN_PRE_BNBWD) tv = fmaf(s_ga[co], tv, fmaf(s_gb[co], __ldg(p.gh + off + jj), s_gc[co]));
-                                o[j] = tv;
-                            }
-                        }
-                    }
-                    unsigned char* hi = st + (t * 2 * g.a_tile_bytes) + (dyi * g.coutp + co) * 16 + (size_t)kc * g.lbo_a;
-                    wt_store_split(hi, hi + g.a_tile_bytes, o);
-                }
-            }
             // ---- B: activation copies shifted by dx (and the row of ones)
             for (int u0 = 0; u0 * tstride + lane_t < n_br; ++u0) {
                 const int ci = lane_t + u0 * tstride;
@@ -437,8 +428,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
         float* rec = partials + (size_t)blockIdx.x * g.rec_floats;
         const bool vec_st = (p.Cin % 4 == 0);
         for (int t = 0; t < g.ntile; ++t) {
-            const int cp = t * g.na + dyi;                        // dy copy -> ky
-            const bool rowv = (dyi < g.na) && (co < p.Cout) && (cp < ND || !K3);
+            const int cp = K3 ? 2 - (t * g.na + dyi) : 0;         // dy slot -> ky (slot d holds the gradient d - 1 padded rows further)
+            const bool rowv = (dyi < g.na) && (co < p.Cout) && cp >= 0 && (K3 || t * g.na + dyi == 0);
             const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + t * g.np;
             for (int d = 0; d < ND; ++d) {
                 const int tap = K3 ? cp * 3 + d : 0;           // ky = cp, kx = d
