@@ -417,149 +417,149 @@ __global__ void __launch_bounds__(NTHREADS_TC, 2) conv_tc_kernel(const ibinn_con
             }
         }
         if (warp < 4) {
-        // ================= epilogue: thread <-> output row of the tile =================
-        const int row = tid;                      // 0..127, TMEM lane
-        const size_t HWo = (size_t)p.Hout * p.Wout;
-        // statistics: channel sc is reduced by `nparts` adjacent lanes, lane `part` taking rows part, part + nparts, ...
-        int nparts = 1;
-        while (nparts * 2 * g.np <= TM) nparts *= 2;
-        const int sc = tid / nparts, part = tid - sc * nparts, nrows = TM / nparts;
-        float run_n = 0.f, run_mean = 0.f, run_m2 = 0.f, run_a1 = 0.f, run_a2 = 0.f;
-        for (int j = 0; j < ntl; ++j) {
-            const int buf = j % g.nbuf, n = j / g.nbuf;
-            const int q = ((int)blockIdx.x + j * (int)gridDim.x) * TM + row;
-            bool valid = false;
-            size_t obase = 0, mbase = 0, abase = 0;
-            int bimg = 0;
-            if (q < g.Qout) {
-                const int b = q / g.S, rem = q - b * g.S;
-                const int yy = rem / g.P - g.pad, xx = rem % g.P;
-                if (yy >= 0 && yy < p.Hin && xx < p.Win && (p.stride == 1 || !((yy | xx) & 1))) {
-                    valid = true;
-                    bimg = b;
-                    const int sh = p.stride - 1;
-                    const size_t in_img = (size_t)(yy >> sh) * p.Wout + (xx >> sh);
-                    obase = (size_t)b * p.y_bs + in_img;
-                    mbase = (size_t)b * p.m_bs + in_img;
-                    abase = (size_t)b * p.addend_bs + in_img;
-                }
-            }
-            tc::mbar_wait(&acc_full[buf], n & 1);
-            tc::fence_after_sync();
-            if (tid == 0 && j < 4) DBG(30 + 2 * j);
-            if (STATS) s_valid[row] = valid ? 1.f : 0.f;
-            const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + buf * 2 * g.np;
-            // mask / addend operands of the next 8 columns are fetched while the current 8 are processed
-            constexpr bool NEED_H = (EPI == IBINN_EPI_MASKSTATS || EPI == IBINN_EPI_RELUMASK);
-            float hn[8], an[8];
-            auto prefetch = [&](int c8n) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int c = c8n + i;
-                    hn[i] = 0.f; an[i] = 0.f;
-                    if (valid && c < p.Cout) {
-                        if (NEED_H) hn[i] = __ldg(p.m_h + mbase + (size_t)c * HWo);
-                        if ((EPI == IBINN_EPI_STORE || EPI == IBINN_EPI_RELUMASK) && p.addend) an[i] = p.addend[abase + (size_t)c * HWo];
+            // ================= epilogue: thread <-> output row of the tile =================
+            const int row = tid;                      // 0..127, TMEM lane
+            const size_t HWo = (size_t)p.Hout * p.Wout;
+            // statistics: channel sc is reduced by `nparts` adjacent lanes, lane `part` taking rows part, part + nparts, ...
+            int nparts = 1;
+            while (nparts * 2 * g.np <= TM) nparts *= 2;
+            const int sc = tid / nparts, part = tid - sc * nparts, nrows = TM / nparts;
+            float run_n = 0.f, run_mean = 0.f, run_m2 = 0.f, run_a1 = 0.f, run_a2 = 0.f;
+            for (int j = 0; j < ntl; ++j) {
+                const int buf = j % g.nbuf, n = j / g.nbuf;
+                const int q = ((int)blockIdx.x + j * (int)gridDim.x) * TM + row;
+                bool valid = false;
+                size_t obase = 0, mbase = 0, abase = 0;
+                int bimg = 0;
+                if (q < g.Qout) {
+                    const int b = q / g.S, rem = q - b * g.S;
+                    const int yy = rem / g.P - g.pad, xx = rem % g.P;
+                    if (yy >= 0 && yy < p.Hin && xx < p.Win && (p.stride == 1 || !((yy | xx) & 1))) {
+                        valid = true;
+                        bimg = b;
+                        const int sh = p.stride - 1;
+                        const size_t in_img = (size_t)(yy >> sh) * p.Wout + (xx >> sh);
+                        obase = (size_t)b * p.y_bs + in_img;
+                        mbase = (size_t)b * p.m_bs + in_img;
+                        abase = (size_t)b * p.addend_bs + in_img;
                     }
                 }
-            };
-            prefetch(0);
+                tc::mbar_wait(&acc_full[buf], n & 1);
+                tc::fence_after_sync();
+                if (tid == 0 && j < 4) DBG(30 + 2 * j);
+                if (STATS) s_valid[row] = valid ? 1.f : 0.f;
+                const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + buf * 2 * g.np;
+                // mask / addend operands of the next 8 columns are fetched while the current 8 are processed
+                constexpr bool NEED_H = (EPI == IBINN_EPI_MASKSTATS || EPI == IBINN_EPI_RELUMASK);
+                float hn[8], an[8];
+                auto prefetch = [&](int c8n) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int c = c8n + i;
+                        hn[i] = 0.f; an[i] = 0.f;
+                        if (valid && c < p.Cout) {
+                            if (NEED_H) hn[i] = __ldg(p.m_h + mbase + (size_t)c * HWo);
+                            if ((EPI == IBINN_EPI_STORE || EPI == IBINN_EPI_RELUMASK) && p.addend) an[i] = p.addend[abase + (size_t)c * HWo];
+                        }
+                    }
+                };
+                prefetch(0);
 #pragma unroll 1
-            for (int c8 = 0; c8 < g.np; c8 += 8) {
-                float v[8], v2[8], hc[8], ac[8];
+                for (int c8 = 0; c8 < g.np; c8 += 8) {
+                    float v[8], v2[8], hc[8], ac[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { hc[i] = hn[i]; ac[i] = an[i]; }
-                if (c8 + 8 < g.np) prefetch(c8 + 8);
-                tc::tmem_ld8(taddr + c8, v);
-                tc::tmem_ld8(taddr + g.np + c8, v2);
-                tc::tmem_ld_wait();
+                    for (int i = 0; i < 8; ++i) { hc[i] = hn[i]; ac[i] = an[i]; }
+                    if (c8 + 8 < g.np) prefetch(c8 + 8);
+                    tc::tmem_ld8(taddr + c8, v);
+                    tc::tmem_ld8(taddr + g.np + c8, v2);
+                    tc::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += v2[i];
+                    for (int i = 0; i < 8; ++i) v[i] += v2[i];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int c = c8 + i;
-                    float o = 0.f, xh = 0.f;
-                    if (valid && c < p.Cout) {
-                        o = v[i];
-                        if (EPI == IBINN_EPI_STORE || EPI == IBINN_EPI_RELUMASK) { if (p.bias) o += __ldg(p.bias + c); }
-                        if (EPI == IBINN_EPI_MASKSTATS) {
-                            const float h = hc[i];
-                            o = fmaf(h, s_ea[c], s_eb[c]) > 0.f ? o : 0.f;
-                            if (p.m_drop) o *= __ldg(p.m_drop + (size_t)bimg * p.Cout + c);
-                            xh = (h - s_em[c]) * s_ei[c];
-                        } else if (EPI == IBINN_EPI_RELUMASK) {
-                            o = hc[i] > 0.f ? o : 0.f;
+                    for (int i = 0; i < 8; ++i) {
+                        const int c = c8 + i;
+                        float o = 0.f, xh = 0.f;
+                        if (valid && c < p.Cout) {
+                            o = v[i];
+                            if (EPI == IBINN_EPI_STORE || EPI == IBINN_EPI_RELUMASK) { if (p.bias) o += __ldg(p.bias + c); }
+                            if (EPI == IBINN_EPI_MASKSTATS) {
+                                const float h = hc[i];
+                                o = fmaf(h, s_ea[c], s_eb[c]) > 0.f ? o : 0.f;
+                                if (p.m_drop) o *= __ldg(p.m_drop + (size_t)bimg * p.Cout + c);
+                                xh = (h - s_em[c]) * s_ei[c];
+                            } else if (EPI == IBINN_EPI_RELUMASK) {
+                                o = hc[i] > 0.f ? o : 0.f;
+                            }
+                            float st = o;
+                            if (EPI == IBINN_EPI_STORE || EPI == IBINN_EPI_RELUMASK) st += ac[i];
+                            p.y[obase + (size_t)c * HWo] = st;
                         }
-                        float st = o;
-                        if (EPI == IBINN_EPI_STORE || EPI == IBINN_EPI_RELUMASK) st += ac[i];
-                        p.y[obase + (size_t)c * HWo] = st;
-                    }
-                    if (STATS) {
-                        s_t1[c * TP + row] = o;
-                        if (EPI == IBINN_EPI_MASKSTATS) s_t2[c * TP + row] = o * xh;
+                        if (STATS) {
+                            s_t1[c * TP + row] = o;
+                            if (EPI == IBINN_EPI_MASKSTATS) s_t2[c * TP + row] = o * xh;
+                        }
                     }
                 }
-            }
-            if (tid == 0 && j == 0) DBG(60);
-            tc::fence_before_sync();
-            if (!(STATS && g.alias_stats)) mbar_arrive(&acc_empty[buf]);       // accumulator (TMEM) is free again
-            if (STATS) {
-                epi_sync();
-                if (tid == 0 && j == 0) DBG(61);
-                // one pass; BatchNorm sums are taken about K = the column's first row (any value near the mean keeps
-                // a2 - a1^2/cnt free of cancellation)
-                float a1 = 0.f, a2 = 0.f, cnt = 0.f, K = 0.f;
-                if (sc < g.np) {
-                    const float* t1 = s_t1 + sc * TP + part;
-                    const float* t2 = s_t2 + sc * TP + part;
-                    const float* vv = s_valid + part;
-                    if (EPI == IBINN_EPI_BNSTATS) K = s_t1[sc * TP];
+                if (tid == 0 && j == 0) DBG(60);
+                tc::fence_before_sync();
+                if (!(STATS && g.alias_stats)) mbar_arrive(&acc_empty[buf]);       // accumulator (TMEM) is free again
+                if (STATS) {
+                    epi_sync();
+                    if (tid == 0 && j == 0) DBG(61);
+                    // one pass; BatchNorm sums are taken about K = the column's first row (any value near the mean keeps
+                    // a2 - a1^2/cnt free of cancellation)
+                    float a1 = 0.f, a2 = 0.f, cnt = 0.f, K = 0.f;
+                    if (sc < g.np) {
+                        const float* t1 = s_t1 + sc * TP + part;
+                        const float* t2 = s_t2 + sc * TP + part;
+                        const float* vv = s_valid + part;
+                        if (EPI == IBINN_EPI_BNSTATS) K = s_t1[sc * TP];
 #pragma unroll 8
-                    for (int r = 0; r < nrows; ++r) {
-                        const float o = t1[r * nparts], w = vv[r * nparts];
-                        cnt += w;
-                        if (EPI == IBINN_EPI_BNSTATS) {
-                            const float d = o - K;
-                            a1 = fmaf(w, d, a1);
-                            a2 = fmaf(w * d, d, a2);
-                        } else {
-                            a1 += o;
-                            a2 += t2[r * nparts];
+                        for (int r = 0; r < nrows; ++r) {
+                            const float o = t1[r * nparts], w = vv[r * nparts];
+                            cnt += w;
+                            if (EPI == IBINN_EPI_BNSTATS) {
+                                const float d = o - K;
+                                a1 = fmaf(w, d, a1);
+                                a2 = fmaf(w * d, d, a2);
+                            } else {
+                                a1 += o;
+                                a2 += t2[r * nparts];
+                            }
                         }
                     }
-                }
-                for (int o = nparts >> 1; o > 0; o >>= 1) {
-                    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-                    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-                    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-                }
-                if (EPI == IBINN_EPI_BNSTATS) {
-                    if (cnt > 0.f) {       // Chan: fold the tile (cnt, mean, M2) into the running (n, mean, M2)
-                        const float d = a1 / cnt, mean = K + d, m2 = fmaxf(a2 - a1 * d, 0.f);
-                        const float nn = run_n + cnt, dlt = mean - run_mean;
-                        run_mean += dlt * cnt / nn;
-                        run_m2 += m2 + dlt * dlt * run_n * cnt / nn;
-                        run_n = nn;
+                    for (int o = nparts >> 1; o > 0; o >>= 1) {
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+                        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
                     }
-                } else {
-                    run_a1 += a1;
-                    run_a2 += a2;
-                    run_n += cnt;
+                    if (EPI == IBINN_EPI_BNSTATS) {
+                        if (cnt > 0.f) {       // Chan: fold the tile (cnt, mean, M2) into the running (n, mean, M2)
+                            const float d = a1 / cnt, mean = K + d, m2 = fmaxf(a2 - a1 * d, 0.f);
+                            const float nn = run_n + cnt, dlt = mean - run_mean;
+                            run_mean += dlt * cnt / nn;
+                            run_m2 += m2 + dlt * dlt * run_n * cnt / nn;
+                            run_n = nn;
+                        }
+                    } else {
+                        run_a1 += a1;
+                        run_a2 += a2;
+                        run_n += cnt;
+                    }
+                    if (tid == 0 && j == 0) DBG(62);
+                    epi_sync();                                                  // tiles may be overwritten by the next pass
+                    if (g.alias_stats) mbar_arrive(&acc_empty[buf]);             // borrowed operand area is free again
                 }
-                if (tid == 0 && j == 0) DBG(62);
-                epi_sync();                                                  // tiles may be overwritten by the next pass
-                if (g.alias_stats) mbar_arrive(&acc_empty[buf]);             // borrowed operand area is free again
+                if (tid == 0 && j < 4) DBG(31 + 2 * j);
             }
-            if (tid == 0 && j < 4) DBG(31 + 2 * j);
-        }
-        if (STATS) {
-            float* rec = p.partials + (size_t)blockIdx.x * (2 * p.Cout + 4);
-            if (part == 0 && sc < p.Cout) {
-                if (EPI == IBINN_EPI_BNSTATS) { rec[sc] = run_mean; rec[p.Cout + sc] = run_m2; }
-                else { rec[sc] = run_a1; rec[p.Cout + sc] = run_a2; }
+            if (STATS) {
+                float* rec = p.partials + (size_t)blockIdx.x * (2 * p.Cout + 4);
+                if (part == 0 && sc < p.Cout) {
+                    if (EPI == IBINN_EPI_BNSTATS) { rec[sc] = run_mean; rec[p.Cout + sc] = run_m2; }
+                    else { rec[sc] = run_a1; rec[p.Cout + sc] = run_a2; }
+                }
+                if (tid == 0) rec[2 * p.Cout] = run_n;
             }
-            if (tid == 0) rec[2 * p.Cout] = run_n;
-        }
         }
     }
 
