@@ -145,3 +145,46 @@ def test_data_parallel_equals_gradient_accumulation(tmp_path):
                 assert rel(r0[k], sd[k]) < 1e-5, k
     finally:
         _lib._use_library_for_tests(None, False)
+
+
+@pytest.mark.gpu
+def test_train_step_schedules_agree():
+    """The same step with every stream / graph schedule: eager on one stream, weight gradients on a side stream, grouped
+    record reductions on a third stream, and the captured CUDA graphs: the same parameters after two steps (the schedules
+    only reorder independent launches; what remains is the fp32 atomic order of the split-K FC GEMMs)."""
+    if not torch.cuda.is_available():
+        pytest.skip('needs a B200')
+    dev = torch.device('cuda:0')
+    base = _model(dev, overrides={'model': {'n_coupling_blocks_conv': '[1, 2, 2]', 'fc_width': '16'}})
+    gen = torch.Generator().manual_seed(5)
+    batches = [_batch(8, 10, gen) for _ in range(2)]
+    results = []
+    for env, graph in (({'IBINN_WGRAD_STREAMS': '0'}, False), ({'IBINN_WGRAD_STREAMS': '1'}, False),
+                       ({'IBINN_WGRAD_STREAMS': '1', 'IBINN_WGRAD_REDUCE_GROUP': '3'}, False), ({'IBINN_WGRAD_STREAMS': '1'}, True)):
+        old = {k: os.environ.get(k) for k in ('IBINN_WGRAD_STREAMS', 'IBINN_WGRAD_REDUCE_GROUP')}
+        os.environ.pop('IBINN_WGRAD_REDUCE_GROUP', None)
+        os.environ.update(env)
+        try:
+            m = copy.deepcopy(base)
+            m.eval()                                   # no dropout masks to draw
+            step = TrainStep(m, batch_size=8, beta=1.0, clip=8., use_graph=graph)
+            if graph:
+                step.load(*[t.to(dev) for t in batches[0]])
+                snap = copy.deepcopy({k: v.clone() for k, v in m.state_dict().items()})
+                mom = step.flat.buf.clone()
+                step.capture()                         # warm-up steps move the parameters: restore them
+                m.load_state_dict(snap)
+                step.flat.buf.copy_(mom)
+            for x, y in batches:
+                step.step(x.to(dev), y.to(dev))
+            torch.cuda.synchronize()
+            results.append({k: v.clone() for k, v in m.state_dict().items() if v.is_floating_point()})
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+    for other in results[1:]:
+        for k in results[0]:
+            assert rel(other[k], results[0][k].double()) < 1e-4, k
