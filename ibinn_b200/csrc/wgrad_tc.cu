@@ -32,7 +32,7 @@ constexpr int WT_GROUPS = 2;        // staging groups of 256 threads taking K bl
 constexpr int WT_STAGERS = 256 * WT_GROUPS;
 constexpr int WT_THREADS = WT_STAGERS + 32;   // + warp 16: MMA issuer
 constexpr int WT_MMA_WARP = WT_STAGERS / 32;
-constexpr int KC_MAX = 16;          // K chunks per stage: 4, 8 or 16 (16 / 32 / 64 pixels), chosen per layer
+constexpr int KC_MAX = 32;          // K chunks per stage: 4 ... 32 (16 ... 128 pixels), chosen per layer
 constexpr int WT_MAXC = 128;
 
 struct WgTcGeom {
@@ -89,7 +89,7 @@ static bool wg_geometry(const ibinn_wgrad_args& a, WgTcGeom& g) {
     // enough staging work per K block to hide the load latency (>= ~4 chunk tasks per staging thread),
     // but at least 2 stages in shared memory (one per staging group)
     const int tasks_per_chunk = a.Cout + g.nd * a.Cin;
-    g.kc = tasks_per_chunk * 4 >= 1200 ? 4 : tasks_per_chunk * 8 >= 1200 ? 8 : KC_MAX;
+    g.kc = tasks_per_chunk * 4 >= 1200 ? 4 : tasks_per_chunk * 8 >= 1200 ? 8 : tasks_per_chunk * 16 >= 1200 ? 16 : KC_MAX;
     for (;;) {
         g.kcs = g.kc + 2 * g.sh;
         const int gs = a.ksize == 3 ? g.sh : 1;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
             const int bb = bimg, yy = rin - g.pad;
             const bool rowok = (yy >= 0 && bb < p.B);
             // ---- issue every global load of this block first, then transform and store
-            constexpr int UB = 2;
+            constexpr int UB = 3;
             float w6[UB][6];
             float mk[UB];
 #pragma unroll
