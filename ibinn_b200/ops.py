@@ -255,7 +255,9 @@ def conv_wgrad(g, x, dw, ksize, stride=1, *, g_pre=PRE_NONE, gh=None, g_bn=None,
         _wgrad_rr += 1
         side.wait_stream(torch.cuda.current_stream())
         st = side.cuda_stream
-        DEFERRED_WGRAD.append(((g, x, gh, g_sums, x_mask, dw, dbias), None))
+        # every tensor the kernel reads through a pointer stays referenced until the join - including the BatchNorm statistics
+        # inside g_bn / x_bn, which autograd frees right after this block's backward while the kernel may still be queued
+        DEFERRED_WGRAD.append(((g, x, gh, g_sums, x_mask, dw, dbias, g_bn, x_bn), None))
     check(_lib.lib().ibinn_conv_wgrad(ctypes.byref(a), st), 'conv_wgrad')
     _lib.set_tag('')
     if DEFERRED_WGRAD is not None and WGRAD_REDUCE is not None:

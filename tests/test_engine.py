@@ -150,8 +150,10 @@ def test_data_parallel_equals_gradient_accumulation(tmp_path):
 @pytest.mark.gpu
 def test_train_step_schedules_agree():
     """The same step with every stream / graph schedule: eager on one stream, weight gradients on a side stream, grouped
-    record reductions on a third stream, and the captured CUDA graphs: the same parameters after two steps (the schedules
-    only reorder independent launches; what remains is the fp32 atomic order of the split-K FC GEMMs)."""
+    record reductions on a third stream, and the captured CUDA graphs: the same parameters after two steps.  The schedules
+    only reorder independent launches; what remains is the fp32 atomic order of the split-K FC GEMMs (1e-7), which now and
+    then flips one ReLU mask element and moves a small tensor by 1e-3 (`scripts/schedule_noise.py`: the same happens between
+    two runs of ONE schedule) - hence a tight gate on the whole parameter vector and a loose one per tensor."""
     if not torch.cuda.is_available():
         pytest.skip('needs a B200')
     dev = torch.device('cuda:0')
@@ -185,6 +187,8 @@ def test_train_step_schedules_agree():
                     os.environ.pop(k, None)
                 else:
                     os.environ[k] = v
+    flat = lambda r: torch.cat([r[k].flatten().double() for k in results[0]])
     for other in results[1:]:
+        assert float((flat(other) - flat(results[0])).norm() / flat(results[0]).norm()) < 1e-4
         for k in results[0]:
-            assert rel(other[k], results[0][k].double()) < 1e-4, k
+            assert rel(other[k], results[0][k].double()) < 2e-2, k
