@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_mix_kernel(const AioP p) {
     float jsum = 0.f;
     {
         // all loads of a batch of elements are issued before the first use (the kernel is latency-bound: 12 elements per thread)
-        constexpr int KB = 6;
+        constexpr int KB = 12;
         const int n = C * HW;
         const float* ab = p.a + (size_t)b * 2 * c2 * HW;
         for (int e0 = 0; e0 < n; e0 += IBINN_THREADS * KB) {
