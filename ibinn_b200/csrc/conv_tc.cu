@@ -129,7 +129,7 @@ static bool tc_geometry(const ibinn_conv_args& a, TcGeom& g) {
     int per_sm = (int)((220 * 1024) / (g.smem_bytes + 2048));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 512 / g.tmem_cols) per_sm = 512 / g.tmem_cols;
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 2) per_sm = 2;                       // __launch_bounds__(NTHREADS_TC, 2): two CTAs per SM are resident at most
     g.grid = g.ntiles < 148 * per_sm ? g.ntiles : 148 * per_sm;
     return true;
 }
