@@ -227,7 +227,19 @@ def main():
         traffic = ncu[top.split(' ')[0]]['dram_bytes_per_launch']
     except Exception:
         pass
-    roofline = {'bound': 'tensor', 'kernel': top, 'launches_per_step': st['n'], 'avg_launch_us': st['ms'] * 1e3 / max(st['n'], 1),
+    # HBM-bound kernel families at the training batch: algorithmic bytes / CUDA-event time of the same
+    # launches.  At batch 128 a launch moves 3-8 MB (L2-resident), so these are latency-bound; scripts/hbm_ops_bench.py measures the
+    # same kernels at the scoring batch (profiles/r01_hbm_ops.json).
+    n_param = sum(q.numel() for q in model.parameters() if q.requires_grad)
+    hbm_bytes = {'ibinn_aio_coupling_forward': 8 * 32768 * B + 48 * 36864 * B,      # 8 blocks of 32 768 B + 48 of 36 864 B per image
+                 'ibinn_aio_coupling_backward': 8 * 53248 * B + 48 * 61440 * B,
+                 'ibinn_sgd_step': 20. * n_param, 'ibinn_grad_norm_clip': 4. * n_param}
+    hbm_fam = {}
+    for k, nbytes in hbm_bytes.items():
+        if k in table and table[k][0] > 0:
+            gbs = nbytes / (table[k][0] * 1e-3) / 1e9
+            hbm_fam[k] = {'ms_per_step': table[k][0], 'launches': table[k][1], 'bytes_per_step': nbytes, 'gbs': gbs, 'frac_of_hbm_peak': gbs / pk['hbm']}
+    roofline = {'bound': 'tensor', 'kernel': top, 'hbm_families': hbm_fam, 'launches_per_step': st['n'], 'avg_launch_us': st['ms'] * 1e3 / max(st['n'], 1),
                 'flops_per_launch': st['flops'] / max(st['n'], 1), 'achieved': ach, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s',
                 'frac': ach / pk['bf16_sustained'], 'traffic': traffic,
                 'peak_source': pk['source'] + ' bf16 dense sustained (MEASURED_PEAKS.json has no TF32 figure; nominal TF32 dense is half of it)',
