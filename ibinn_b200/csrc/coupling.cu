@@ -21,14 +21,16 @@ struct AioP {
     const float* g_out; const float* g_jac; const float* out_saved;
     float* g_x; float* g_a; float* g_an; float* g_off; float* partials; unsigned* counter;
     int nsplit, defer;
+    int hw_shift;        // log2(HW) when HW is a power of two >= 4 and x / a / out are 16-byte aligned (vector path), else 0
 };
 
 // MODE 0: forward   out = (w . [x1 | x2*exp(sig)+t]) * exp(an) + off ; jac = sum sig + HW*sum an
 // MODE 1: unpermute u = w_inv . ((y - off) * exp(-an))                (first half of the inverse)
 template <int MODE>
-__global__ void __launch_bounds__(IBINN_THREADS) aio_mix_kernel(const AioP p) {
+__global__ void __launch_bounds__(IBINN_THREADS, 4) aio_mix_kernel(const AioP p) {
     IBINN_DYN_SMEM(float, smem);
     __shared__ float s_scr[40];
+    __shared__ float s_san;
     const int C = p.C, HW = p.HW, HWp = round4(HW), Cp = round4(C);
     const int c1 = C - C / 2, c2 = C / 2;
     float* s_u = smem;                 // [C][HWp]
@@ -38,18 +40,69 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_mix_kernel(const AioP p) {
     const int tid = threadIdx.x, b = blockIdx.x;
     const float* xb = p.x + (size_t)b * C * HW;
 
-    for (int e = tid; e < C * Cp; e += IBINN_THREADS) {
-        const int i = e / Cp, o = e - i * Cp;
-        s_w[e] = (o < C) ? __ldg(p.w + (size_t)o * C + i) : 0.f;
-    }
+    // (warp <-> input channel, lane <-> output channel: no integer divisions in the prologue)
+    for (int i = tid >> 5; i < C; i += IBINN_THREADS / 32)
+        for (int o = tid & 31; o < Cp; o += 32) s_w[i * Cp + o] = (o < C) ? __ldg(p.w + (size_t)o * C + i) : 0.f;
     for (int c = tid; c < C; c += IBINN_THREADS) {
         s_sc[c] = expf(MODE == 0 ? p.an[c] : -p.an[c]);
         s_of[c] = p.off[c];
     }
+    if (MODE == 0 && (tid >> 5) == IBINN_THREADS / 32 - 1) {      // sum of the ActNorm log-scales for the log-det, off the tail
+        float v = 0.f;
+        for (int c = tid & 31; c < C; c += 32) v += p.an[c];
+        v = warp_sum(v);
+        if ((tid & 31) == 0) s_san = v;
+    }
     if (MODE == 1) __syncthreads();
 
     float jsum = 0.f;
-    {
+    if (p.hw_shift) {
+        // vector path: 128-bit loads, channel / pixel from shifts (the scalar path below spends ~40 instructions per element on the
+        // two runtime divisions, which made the kernel issue-bound at the scoring batch: 100 M warp instructions at B = 8192)
+        constexpr int KB4 = 3;
+        const int sh = p.hw_shift, n4 = (C * HW) >> 2;
+        const float* ab = p.a + (size_t)b * 2 * c2 * HW;
+        for (int i0 = 0; i0 < n4; i0 += IBINN_THREADS * KB4) {
+            float4 xv[KB4], sv[KB4], tv[KB4];
+#pragma unroll
+            for (int k = 0; k < KB4; ++k) {
+                const int e = (i0 + tid + IBINN_THREADS * k) * 4;
+                xv[k] = make_float4(0.f, 0.f, 0.f, 0.f); sv[k] = xv[k]; tv[k] = xv[k];
+                if (e < n4 * 4) {
+                    xv[k] = __ldg(reinterpret_cast<const float4*>(xb + e));
+                    if (MODE == 0) {
+                        const int c = e >> sh, q = e & (HW - 1);
+                        if (c >= c1) {
+                            sv[k] = __ldg(reinterpret_cast<const float4*>(ab + (size_t)(c - c1) * HW + q));
+                            tv[k] = __ldg(reinterpret_cast<const float4*>(ab + (size_t)(c2 + c - c1) * HW + q));
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < KB4; ++k) {
+                const int e = (i0 + tid + IBINN_THREADS * k) * 4;
+                if (e >= n4 * 4) continue;
+                const int c = e >> sh, q = e & (HW - 1);
+                float u[4] = {xv[k].x, xv[k].y, xv[k].z, xv[k].w};
+                if (MODE == 0) {
+                    if (c >= c1) {
+                        const float ss[4] = {sv[k].x, sv[k].y, sv[k].z, sv[k].w}, tt[4] = {tv[k].x, tv[k].y, tv[k].z, tv[k].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float sig = p.clamp * tanhf(p.alpha * ss[j]);
+                            u[j] = fmaf(u[j], expf(sig), tt[j]);
+                            jsum += sig;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) u[j] = (u[j] - s_of[c]) * s_sc[c];
+                }
+                st4(s_u + (size_t)c * HWp + q, make_float4(u[0], u[1], u[2], u[3]));
+            }
+        }
+    } else {
         // all loads of a batch of elements are issued before the first use (the kernel is latency-bound: 12 elements per thread)
         constexpr int KB = 12;
         const int n = C * HW;
@@ -132,11 +185,7 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_mix_kernel(const AioP p) {
     }
     if (MODE == 0) {
         const float tot = block_sum(jsum, s_scr);
-        if (tid == 0) {
-            float san = 0.f;
-            for (int c = 0; c < C; ++c) san += p.an[c];
-            p.jac[b] = tot + (float)HW * san;
-        }
+        if (tid == 0) p.jac[b] = tot + (float)HW * s_san;
     }
 }
 
@@ -371,6 +420,15 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
     if (tid == 0) *p.counter = 0u;
 }
 
+// log2(HW) if the vector path of aio_mix_kernel applies (HW a power of two >= 4, 16-byte aligned operands), else 0
+static int aio_hw_shift(int HW, const void* x, const void* a, const void* out) {
+    if (HW < 4 || (HW & (HW - 1)) != 0) return 0;
+    if (((uintptr_t)x | (uintptr_t)a | (uintptr_t)out) & 15) return 0;
+    int sh = 0;
+    while ((1 << sh) < HW) ++sh;
+    return sh;
+}
+
 static size_t aio_smem(int C, int HW) {
     const int HWp = (HW + 3) & ~3, Cp = (C + 3) & ~3;
     return ((size_t)C * HWp + (size_t)C * Cp + 2 * Cp + 32 + 2 * ((size_t)C * HWp / 32 + 1)) * sizeof(float);
@@ -484,6 +542,7 @@ extern "C" int ibinn_aio_coupling_forward(const float* x, const float* a, const 
     AioP p{};
     p.x = x; p.a = a; p.w = w; p.an = act_norm; p.off = act_offset; p.out = out; p.jac = jac;
     p.B = B; p.C = C; p.HW = H * W; p.clamp = clamp; p.alpha = alpha;
+    p.hw_shift = aio_hw_shift(H * W, x, a, out);
     size_t sm = aio_smem(C, H * W);
     int e = ibinn_set_smem(aio_mix_kernel<0>, sm);
     if (e) return e;
@@ -499,6 +558,7 @@ extern "C" int ibinn_aio_unpermute(const float* y, const float* w_inv, const flo
     AioP p{};
     p.x = y; p.w = w_inv; p.an = act_norm; p.off = act_offset; p.out = u;
     p.B = B; p.C = C; p.HW = H * W;
+    p.hw_shift = aio_hw_shift(H * W, y, nullptr, u);
     size_t sm = aio_smem(C, H * W);
     int e = ibinn_set_smem(aio_mix_kernel<1>, sm);
     if (e) return e;

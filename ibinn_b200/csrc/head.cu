@@ -36,41 +36,66 @@ __device__ __forceinline__ void log_softmax_phi(const float* phi, int C, float* 
     }
 }
 
+// SB samples per CTA: every CTA streams all of mu (C x D floats, L2-resident) once, so at the scoring batch sizes one sample per
+// CTA is bound by B x C x D x 4 bytes of L2 traffic (1 GB at B = 8192, C = 10) instead of by reading z once from HBM.  The
+// arithmetic per (sample, class) is the same lane-strided sum followed by a warp reduction for every SB, so the results do not
+// depend on the batch size.
+template <int SB>
 __global__ void __launch_bounds__(IBINN_THREADS) head_fwd_kernel(const HeadP p) {
     IBINN_DYN_SMEM(float, smem);
     __shared__ int s_flag;
     const int B = p.B, C = p.C, D = p.D;
-    float* s_z = smem;          // [D]
-    float* s_zz = s_z + D;      // [C]
-    float* s_lw = s_zz + C;     // [C]
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, b = blockIdx.x;
-    for (int d = tid; d < D; d += IBINN_THREADS) s_z[d] = __ldg(p.z + (size_t)b * D + d);
+    float* s_z = smem;               // [SB][D]
+    float* s_zz = s_z + SB * D;      // [SB][C]
+    float* s_lw = s_zz + SB * C;     // [C]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, b0 = blockIdx.x * SB;
+    const int nb = min(SB, B - b0);
+    {
+        const float* zb = p.z + (size_t)b0 * D;
+        const int n = nb * D;
+        if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(p.z) & 15) == 0)
+            for (int e = tid * 4; e < n; e += IBINN_THREADS * 4) st4(s_z + e, __ldg(reinterpret_cast<const float4*>(zb + e)));
+        else
+            for (int e = tid; e < n; e += IBINN_THREADS) s_z[e] = __ldg(zb + e);
+        for (int e = n + tid; e < SB * D; e += IBINN_THREADS) s_z[e] = 0.f;
+    }
     log_softmax_phi(p.phi, C, s_lw);
     __syncthreads();
     for (int k = wid; k < C; k += IBINN_THREADS / 32) {
         const float* mk = p.mu + (size_t)k * D;
-        float acc = 0.f;
+        float acc[SB];
+#pragma unroll
+        for (int s = 0; s < SB; ++s) acc[s] = 0.f;
         for (int d = lane; d < D; d += 32) {
-            const float t = s_z[d] - __ldg(mk + d);
-            acc = fmaf(t, t, acc);
+            const float m = __ldg(mk + d);
+#pragma unroll
+            for (int s = 0; s < SB; ++s) {
+                const float t = s_z[s * D + d] - m;
+                acc[s] = fmaf(t, t, acc[s]);
+            }
         }
-        acc = warp_sum(acc);
-        if (lane == 0) s_zz[k] = acc;
+#pragma unroll
+        for (int s = 0; s < SB; ++s) {
+            const float v = warp_sum(acc[s]);
+            if (lane == 0) s_zz[s * C + k] = v;
+        }
     }
     __syncthreads();
-    if (wid == 0) {
+    for (int s = wid; s < nb; s += IBINN_THREADS / 32) {
+        const int b = b0 + s;
+        const float* zz = s_zz + s * C;
         const float jac = __ldg(p.jac + b);
         float m = -INFINITY;
-        for (int k = lane; k < C; k += 32) m = fmaxf(m, -0.5f * s_zz[k] + s_lw[k]);
+        for (int k = lane; k < C; k += 32) m = fmaxf(m, -0.5f * zz[k] + s_lw[k]);
         m = warp_max(m);
-        float s = 0.f;
-        for (int k = lane; k < C; k += 32) s += expf(-0.5f * s_zz[k] + s_lw[k] - m);
-        s = warp_sum(s);
-        const float ls = logf(s);
+        float se = 0.f;
+        for (int k = lane; k < C; k += 32) se += expf(-0.5f * zz[k] + s_lw[k] - m);
+        se = warp_sum(se);
+        const float ls = logf(se);
         const float lse = m + ls;
         float sl = 0.f;
         for (int k = lane; k < C; k += 32) {
-            const float lg = -0.5f * s_zz[k];
+            const float lg = -0.5f * zz[k];
             p.logits[(size_t)b * C + k] = lg;
             sl += lg;
         }
@@ -80,8 +105,8 @@ __global__ void __launch_bounds__(IBINN_THREADS) head_fwd_kernel(const HeadP p) 
         if (p.y) {
             for (int k = lane; k < C; k += 32) {
                 const float yk = __ldg(p.y + (size_t)b * C + k);
-                const float lg = -0.5f * s_zz[k];
-                lc = fmaf(s_zz[k], rintf(yk), lc);
+                const float lg = -0.5f * zz[k];
+                lc = fmaf(zz[k], rintf(yk), lc);
                 // (log_softmax(l)_k - logw_k) evaluated like the reference: shift by the max first
                 ly = fmaf(yk, ((lg + s_lw[k] - m) - ls) - s_lw[k], ly);
                 if (yk > by) { by = yk; iy = k; }
@@ -113,10 +138,12 @@ __global__ void __launch_bounds__(IBINN_THREADS) head_fwd_kernel(const HeadP p) 
         }
     }
     if (!last_block_ticket(p.counter, gridDim.x, &s_flag)) return;
-    if (tid < 5) {
+    // batch means: warp q sums quantity q over the samples (lane-strided, fp64, fixed order)
+    if (wid < 5) {
         double t = 0.;
-        for (int bb = 0; bb < B; ++bb) t += (double)p.partials[(size_t)bb * 5 + tid];
-        p.means[tid] = (float)(t / (tid == 1 ? (double)B * C : (double)B));
+        for (int bb = lane; bb < B; bb += 32) t += (double)__ldcg(p.partials + (size_t)bb * 5 + wid);
+        t = warp_sum_d(t);
+        if (lane == 0) p.means[wid] = (float)(t / (wid == 1 ? (double)B * C : (double)B));
     }
     if (tid == 0) *p.counter = 0u;
 }
@@ -262,10 +289,21 @@ extern "C" int ibinn_gmm_head_forward(const float* z, const float* jac, const fl
     HeadP p{};
     p.z = z; p.jac = jac; p.mu = mu; p.phi = phi; p.y = y; p.Lx = L_x; p.logits = logits; p.Lc = L_cNLL; p.Ly = L_y;
     p.correct = correct; p.lse = lse; p.means = means; p.partials = partials; p.counter = counter; p.B = B; p.C = C; p.D = D;
-    size_t sm = ((size_t)D + 2 * C + 8) * sizeof(float);
-    e = ibinn_set_smem(head_fwd_kernel, sm);
-    if (e) return e;
-    IBINN_LAUNCH(head_fwd_kernel, dim3(B), dim3(IBINN_THREADS), sm, (cudaStream_t)stream, p);
+    // samples per CTA: as many (up to 8) as still leave two CTAs for each of the 148 SMs
+    const int sb = B >= 148 * 2 * 8 ? 8 : B >= 148 * 2 * 4 ? 4 : B >= 148 * 2 * 2 ? 2 : 1;
+    const size_t sm = ((size_t)sb * D + (size_t)(sb + 1) * C + 8) * sizeof(float);
+    const dim3 grid((B + sb - 1) / sb);
+#define IBINN_HEAD_FWD(SB_)                                                                           \
+    do {                                                                                              \
+        e = ibinn_set_smem(head_fwd_kernel<SB_>, sm);                                                 \
+        if (e) return e;                                                                              \
+        IBINN_LAUNCH(head_fwd_kernel<SB_>, grid, dim3(IBINN_THREADS), sm, (cudaStream_t)stream, p);   \
+    } while (0)
+    if (sb == 8) IBINN_HEAD_FWD(8);
+    else if (sb == 4) IBINN_HEAD_FWD(4);
+    else if (sb == 2) IBINN_HEAD_FWD(2);
+    else IBINN_HEAD_FWD(1);
+#undef IBINN_HEAD_FWD
     return ibinn_launch_status();
 }
 

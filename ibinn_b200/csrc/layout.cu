@@ -10,13 +10,16 @@ namespace {
 __global__ void __launch_bounds__(IBINN_THREADS) dct_fwd_kernel(const float* __restrict__ x, const float* __restrict__ M,
                                                                 float* __restrict__ out, int C, int N, float scale) {
     IBINN_DYN_SMEM(float, smem);
-    const int D = C * N * N, NN = N * N;
+    // NNp: odd per-channel pitch of the intermediate.  The second pass walks channels fastest (the output is channel-fastest), and
+    // with the natural pitch N*N = 64 all 32 lanes of a warp hit one bank (measured: 3.8 % of the HBM peak at batch 8192).
+    const int D = C * N * N, NN = N * N, NNp = NN | 1;
     float* s_x = smem;
     float* s_t = s_x + D;
-    float* s_M = s_t + D;
+    float* s_M = s_t + C * NNp;
     const int tid = threadIdx.x;
     const size_t base = (size_t)blockIdx.x * D;
-    for (int e = tid; e < D; e += IBINN_THREADS) s_x[e] = __ldg(x + base + e);
+    if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) for (int e = tid * 4; e < D; e += IBINN_THREADS * 4) st4(s_x + e, __ldg(reinterpret_cast<const float4*>(x + base + e)));
+    else for (int e = tid; e < D; e += IBINN_THREADS) s_x[e] = __ldg(x + base + e);
     for (int e = tid; e < NN; e += IBINN_THREADS) s_M[e] = __ldg(M + e);
     __syncthreads();
     // t[c][h][kw] = sum_w M[kw][w] x[c][h][w]
@@ -24,14 +27,15 @@ __global__ void __launch_bounds__(IBINN_THREADS) dct_fwd_kernel(const float* __r
         const int kw = e % N, ch = e / N;
         float acc = 0.f;
         for (int w = 0; w < N; ++w) acc = fmaf(s_M[kw * N + w], s_x[ch * N + w], acc);
-        s_t[e] = acc;
+        const int c = e / NN;
+        s_t[c * NNp + (e - c * NN)] = acc;
     }
     __syncthreads();
     for (int e = tid; e < D; e += IBINN_THREADS) {
         const int c = e % C, kk = e / C;
         const int kh = kk % N, kw = kk / N;
         float acc = 0.f;
-        for (int h = 0; h < N; ++h) acc = fmaf(s_M[kh * N + h], s_t[(c * N + h) * N + kw], acc);
+        for (int h = 0; h < N; ++h) acc = fmaf(s_M[kh * N + h], s_t[c * NNp + h * N + kw], acc);
         out[base + e] = acc * scale;
     }
 }
@@ -40,16 +44,16 @@ __global__ void __launch_bounds__(IBINN_THREADS) dct_fwd_kernel(const float* __r
 __global__ void __launch_bounds__(IBINN_THREADS) dct_inv_kernel(const float* __restrict__ t, const float* __restrict__ M,
                                                                 float* __restrict__ x, int C, int N, float scale, int tr) {
     IBINN_DYN_SMEM(float, smem);
-    const int D = C * N * N, NN = N * N;
-    float* s_t = smem;       // [c][kh][kw]
-    float* s_u = s_t + D;    // [c][kh][w]
-    float* s_A = s_u + D;    // A(r,k) row-major
+    const int D = C * N * N, NN = N * N, NNp = NN | 1;      // odd channel pitch: the channel-fastest scatter below is conflict-free
+    float* s_t = smem;            // [c][kh][kw], channel pitch NNp
+    float* s_u = s_t + C * NNp;   // [c][kh][w]
+    float* s_A = s_u + D;         // A(r,k) row-major
     const int tid = threadIdx.x;
     const size_t base = (size_t)blockIdx.x * D;
     for (int e = tid; e < D; e += IBINN_THREADS) {
         const int c = e % C, kk = e / C;
         const int kh = kk % N, kw = kk / N;
-        s_t[(c * N + kh) * N + kw] = __ldg(t + base + e);
+        s_t[c * NNp + kh * N + kw] = __ldg(t + base + e);
     }
     for (int e = tid; e < NN; e += IBINN_THREADS) {
         const int r = e / N, k = e % N;
@@ -57,9 +61,10 @@ __global__ void __launch_bounds__(IBINN_THREADS) dct_inv_kernel(const float* __r
     }
     __syncthreads();
     for (int e = tid; e < D; e += IBINN_THREADS) {
-        const int w = e % N, ck = e / N;
+        const int w = e % N, ck = e / N, c = ck / N;
+        const float* tr_ = s_t + c * NNp + (ck - c * N) * N;
         float acc = 0.f;
-        for (int kw = 0; kw < N; ++kw) acc = fmaf(s_A[w * N + kw], s_t[ck * N + kw], acc);
+        for (int kw = 0; kw < N; ++kw) acc = fmaf(s_A[w * N + kw], tr_[kw], acc);
         s_u[e] = acc;
     }
     __syncthreads();
@@ -97,6 +102,24 @@ __global__ void __launch_bounds__(IBINN_THREADS) haar_kernel(const float* __rest
     }
 }
 
+// One CTA per row when D is a multiple of 4: the row is read with coalesced 128-bit loads into shared memory, gathered there and
+// written with 128-bit stores (the direct gather below reads 32 scattered sectors per warp instruction).
+__global__ void __launch_bounds__(IBINN_THREADS) gather_rows_kernel(const float* __restrict__ x, const int* __restrict__ idx,
+                                                                    float* __restrict__ out, int B, int D) {
+    IBINN_DYN_SMEM(float, s_row);
+    for (int b = blockIdx.x; b < B; b += gridDim.x) {
+        const float* xr = x + (size_t)b * D;
+        float* orow = out + (size_t)b * D;
+        for (int e = threadIdx.x * 4; e < D; e += IBINN_THREADS * 4) st4(s_row + e, __ldg(reinterpret_cast<const float4*>(xr + e)));
+        __syncthreads();
+        for (int e = threadIdx.x * 4; e < D; e += IBINN_THREADS * 4) {
+            const int4 i4 = __ldg(reinterpret_cast<const int4*>(idx + e));
+            st4(orow + e, make_float4(s_row[i4.x], s_row[i4.y], s_row[i4.z], s_row[i4.w]));
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(IBINN_THREADS) gather_kernel(const float* __restrict__ x, const int* __restrict__ idx,
                                                                float* __restrict__ out, long long n, int D) {
     for (long long e = (long long)blockIdx.x * IBINN_THREADS + threadIdx.x; e < n; e += (long long)gridDim.x * IBINN_THREADS) {
@@ -120,7 +143,7 @@ extern "C" int ibinn_dct2d_forward(const float* x, const float* M, float* out, i
     if (e) return e;
     if (!x || !M || !out) return IBINN_ENULL;
     if (B <= 0 || C <= 0 || N <= 0 || N > 64) return IBINN_EINVAL;
-    size_t sm = ((size_t)2 * C * N * N + (size_t)N * N) * sizeof(float);
+    size_t sm = ((size_t)2 * C * N * N + C + 4 + (size_t)N * N) * sizeof(float);
     e = ibinn_set_smem(dct_fwd_kernel, sm);
     if (e) return e;
     IBINN_LAUNCH(dct_fwd_kernel, dim3(B), dim3(IBINN_THREADS), sm, (cudaStream_t)stream, x, M, out, C, N, scale);
@@ -133,7 +156,7 @@ extern "C" int ibinn_dct2d_inverse(const float* t, const float* M, float* x, int
     if (e) return e;
     if (!x || !M || !t) return IBINN_ENULL;
     if (B <= 0 || C <= 0 || N <= 0 || N > 64) return IBINN_EINVAL;
-    size_t sm = ((size_t)2 * C * N * N + (size_t)N * N) * sizeof(float);
+    size_t sm = ((size_t)2 * C * N * N + C + 4 + (size_t)N * N) * sizeof(float);
     e = ibinn_set_smem(dct_inv_kernel, sm);
     if (e) return e;
     IBINN_LAUNCH(dct_inv_kernel, dim3(B), dim3(IBINN_THREADS), sm, (cudaStream_t)stream, t, M, x, C, N, scale, transpose_M);
@@ -166,6 +189,13 @@ extern "C" int ibinn_permute_features(const float* x, const int32_t* index, floa
     if (!x || !index || !out) return IBINN_ENULL;
     if (B <= 0 || D <= 0) return IBINN_EINVAL;
     const long long n = (long long)B * D;
+    if ((D & 3) == 0 && (size_t)D * sizeof(float) <= 160 * 1024 && (((uintptr_t)x | (uintptr_t)out | (uintptr_t)index) & 15) == 0) {
+        const size_t sm = (size_t)D * sizeof(float);
+        e = ibinn_set_smem(gather_rows_kernel, sm);
+        if (e) return e;
+        IBINN_LAUNCH(gather_rows_kernel, dim3(B < 148 * 8 ? B : 148 * 8), dim3(IBINN_THREADS), sm, (cudaStream_t)stream, x, (const int*)index, out, B, D);
+        return ibinn_launch_status();
+    }
     IBINN_LAUNCH(gather_kernel, dim3(grid_for(n)), dim3(IBINN_THREADS), 0, (cudaStream_t)stream, x, (const int*)index, out, n, D);
     return ibinn_launch_status();
 }

@@ -22,6 +22,7 @@ def main():
     ap.add_argument('--batch', type=int, default=8192)
     ap.add_argument('--reps', type=int, default=10)
     ap.add_argument('--out', default=None)
+    ap.add_argument('--only', default=None, help='substring filter on the kernel names')
     a = ap.parse_args()
     import torch
     from scipy.stats import special_ortho_group
@@ -42,6 +43,8 @@ def main():
 
     def run(name, nbytes, make, call, nsets=None):
         """make() -> operand tuple; call(*operands) launches once."""
+        if a.only and a.only not in name:
+            return
         nsets = nsets or max(2, int(160e6 // max(nbytes, 1)) + 1)
         sets = [make() for _ in range(nsets)]
         for i in range(3):
@@ -85,8 +88,10 @@ def main():
             out, _ = ops.aio_coupling_forward(x, a_, w, an, ao, 2.0)
             return rn(B, C, H, H), rn(B), x, a_, out
         gn, go = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+        ops.DEFERRED_AIO = []          # as in engine.TrainStep: the ActNorm-gradient records of all blocks are summed by one launch per step
         run('aio_coupling_backward C=%d %dx%d' % (C, H, H), 4 * HW * (3 * C + 4 * c2) * B, mkb,
             lambda go_, gj, x, a_, out: ops.aio_coupling_backward(go_, gj, x, a_, out, w, an, ao, 2.0, 0.1, gn, go))
+        ops.DEFERRED_AIO = None
         del c1
 
     # ---- space-to-depth coupling (downsampling_coupling_block.py:49-97): DOWN_0 and DOWN_1 input shapes

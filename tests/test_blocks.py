@@ -255,3 +255,57 @@ def test_aio_backward_deferred_record_reduction(dev):
     _lib.check(_lib.lib().ibinn_aio_param_reduce_many(_lib.ptr(table, torch.uint8), len(entries), _lib.stream(table)), 'aio_param_reduce_many')
     assert torch.equal(gx0, gx1) and torch.equal(ga0, ga1)
     assert rel(got_an, ref_an) < 1e-6 and rel(got_off, ref_off) < 1e-6
+
+
+@pytest.mark.parametrize('B,C', [(2500, 10), (1300, 100), (700, 10)])
+def test_head_large_batch_is_batch_size_independent(dev, B, C):
+    """The scoring batches (BASELINE.json configs[3]) take the several-samples-per-CTA variants of head_fwd_kernel (8 / 4 / 2 samples):
+    per-sample results must equal the one-sample-per-CTA results bit for bit and the fp64 restatement of model.py:113-126,144-159
+    within the head tolerance (1e-3 on the loss terms and logits, bit-exact arg-max)."""
+    from ibinn_b200 import ops
+    D = 3072 if dev.type == 'cuda' else 64
+    g = torch.Generator().manual_seed(21)
+    z, jac = torch.randn(B, D, generator=g), torch.randn(B, generator=g)
+    mu, phi = torch.randn(C, D, generator=g), 0.3 * torch.randn(C, generator=g)
+    lab = torch.randint(0, C, (B,), generator=g)
+    y = torch.zeros(B, C).scatter_(1, lab.view(-1, 1), 1.) * 0.98 + 0.02 / C
+    t = lambda v: v.to(dev).contiguous()
+    big = ops.gmm_head_forward(t(z), t(jac), t(mu), t(phi), t(y))
+    n = 100
+    small = ops.gmm_head_forward(t(z[:n]), t(jac[:n]), t(mu), t(phi), t(y[:n]))
+    for k in ('L_x', 'logits', 'lse', 'L_cNLL', 'L_y', 'correct'):
+        assert torch.equal(big[k][:n].cpu(), small[k].cpu()), k
+    zd, mud = z.double(), mu.double()
+    zz = ((zd[:, None, :] - mud[None]) ** 2).sum(-1)
+    lw = torch.log_softmax(phi.double(), 0)
+    lse = torch.logsumexp(-0.5 * zz + lw, 1)
+    L_x = (-lse - jac.double()) / D
+    L_y = (y.double() * (torch.log_softmax(-0.5 * zz + lw, 1) - lw)).sum(1)
+    assert rel(big['logits'], -0.5 * zz) < 1e-5
+    assert rel(big['L_x'], L_x) < 1e-5 and rel(big['L_y'], L_y) < 1e-4
+    assert torch.equal(big['logits'].cpu().argmax(1), (-0.5 * zz).argmax(1))
+    ref_means = torch.stack([L_x.mean(), (-0.5 * zz).mean()])
+    assert rel(big['means'][:2], ref_means) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('C,H', [(3, 32), (12, 16), (48, 8)])
+def test_aio_coupling_large_batch(cuda_dev, C, H):
+    """Scoring-batch launch (B = 1024 samples, vector path of aio_mix_kernel) against the fp64 formula of all_in_one_block.py:61-114."""
+    from scipy.stats import special_ortho_group
+    from ibinn_b200 import ops
+    B, c1, c2 = 1024, C - C // 2, C // 2
+    g = torch.Generator().manual_seed(22)
+    x, a = torch.randn(B, C, H, H, generator=g), 0.7 * torch.randn(B, 2 * c2, H, H, generator=g)
+    w = torch.tensor(special_ortho_group.rvs(C, random_state=3), dtype=torch.float32)
+    an, ao = 0.2 * torch.randn(C, generator=g), 0.2 * torch.randn(C, generator=g)
+    out, jac = ops.aio_coupling_forward(x.to(cuda_dev), a.to(cuda_dev), w.to(cuda_dev), an.to(cuda_dev), ao.to(cuda_dev), 2.0)
+    xd, ad = x.double(), a.double()
+    sig = 2.0 * torch.tanh(0.1 * ad[:, :c2])
+    u = torch.cat([xd[:, :c1], xd[:, c1:] * torch.exp(sig) + ad[:, c2:]], 1)
+    ref = torch.einsum('oi,bihw->bohw', w.double(), u) * an.double().exp().view(1, C, 1, 1) + ao.double().view(1, C, 1, 1)
+    ref_jac = sig.sum((1, 2, 3)) + H * H * an.double().sum()
+    assert rel(out, ref) < 1e-5 and rel(jac, ref_jac) < 2e-6
+    # and the first half of the inverse (MODE 1 of the same kernel) undoes the permutation / ActNorm
+    u32 = ops.aio_unpermute(out, w.t().contiguous().to(cuda_dev), an.to(cuda_dev), ao.to(cuda_dev))
+    assert rel(u32, u) < 1e-5
