@@ -53,32 +53,79 @@ __global__ void __launch_bounds__(IBINN_THREADS) head_fwd_kernel(const HeadP p) 
     {
         const float* zb = p.z + (size_t)b0 * D;
         const int n = nb * D;
-        if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(p.z) & 15) == 0)
-            for (int e = tid * 4; e < n; e += IBINN_THREADS * 4) st4(s_z + e, __ldg(reinterpret_cast<const float4*>(zb + e)));
-        else
+        if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(p.z) & 15) == 0) {
+            constexpr int ZB = 6;                         // 96 bytes in flight per thread before the first shared-memory store
+            const int n4 = n >> 2;
+            const float4* zb4 = reinterpret_cast<const float4*>(zb);
+            for (int i0 = tid; i0 < n4; i0 += IBINN_THREADS * ZB) {
+                float4 v[ZB];
+#pragma unroll
+                for (int u = 0; u < ZB; ++u) if (i0 + u * IBINN_THREADS < n4) v[u] = __ldg(zb4 + i0 + u * IBINN_THREADS);
+#pragma unroll
+                for (int u = 0; u < ZB; ++u) if (i0 + u * IBINN_THREADS < n4) st4(s_z + (size_t)(i0 + u * IBINN_THREADS) * 4, v[u]);
+            }
+        } else
             for (int e = tid; e < n; e += IBINN_THREADS) s_z[e] = __ldg(zb + e);
         for (int e = n + tid; e < SB * D; e += IBINN_THREADS) s_z[e] = 0.f;
     }
     log_softmax_phi(p.phi, C, s_lw);
     __syncthreads();
-    for (int k = wid; k < C; k += IBINN_THREADS / 32) {
-        const float* mk = p.mu + (size_t)k * D;
+    // Work item = (class k, part of the feature axis): with few classes (C = 10 on 8 warps) whole-class items leave most warps idle
+    // in the last round.  Every item is a lane-strided sum (128-bit loads: a lane owns 4 consecutive features per step) followed by
+    // a warp reduction; a class's parts are added in order below.  The split depends on (C, D) only, never on the batch size.
+    const bool vec = (D & 3) == 0 && (reinterpret_cast<uintptr_t>(p.mu) & 15) == 0;
+    const int nsp = (vec && C < 16 && D % 16 == 0) ? 4 : (vec && C < 32 && D % 8 == 0) ? 2 : 1;
+    const int Dp = D / nsp;
+    float* s_part = s_lw + C;        // [SB][C][nsp]
+    for (int item = wid; item < C * nsp; item += IBINN_THREADS / 32) {
+        const int k = item / nsp, part = item - k * nsp;
+        const float* mk = p.mu + (size_t)k * D + part * Dp;
+        const float* zk = s_z + part * Dp;
         float acc[SB];
 #pragma unroll
         for (int s = 0; s < SB; ++s) acc[s] = 0.f;
-        for (int d = lane; d < D; d += 32) {
-            const float m = __ldg(mk + d);
+        if (vec) {
+            constexpr int MU = 3;                         // class-mean loads (L2) in flight per lane
+            for (int d0 = lane * 4; d0 < Dp; d0 += 128 * MU) {
+                float4 mv[MU];
 #pragma unroll
-            for (int s = 0; s < SB; ++s) {
-                const float t = s_z[s * D + d] - m;
-                acc[s] = fmaf(t, t, acc[s]);
+                for (int u = 0; u < MU; ++u) if (d0 + 128 * u < Dp) mv[u] = __ldg(reinterpret_cast<const float4*>(mk + d0 + 128 * u));
+#pragma unroll
+                for (int u = 0; u < MU; ++u) {
+                    const int d = d0 + 128 * u;
+                    if (d >= Dp) break;
+                    const float4 m = mv[u];
+#pragma unroll
+                    for (int s = 0; s < SB; ++s) {
+                        const float4 zv = ld4(zk + s * D + d);
+                        float t = zv.x - m.x; acc[s] = fmaf(t, t, acc[s]);
+                        t = zv.y - m.y; acc[s] = fmaf(t, t, acc[s]);
+                        t = zv.z - m.z; acc[s] = fmaf(t, t, acc[s]);
+                        t = zv.w - m.w; acc[s] = fmaf(t, t, acc[s]);
+                    }
+                }
+            }
+        } else {
+            for (int d = lane; d < Dp; d += 32) {
+                const float m = __ldg(mk + d);
+#pragma unroll
+                for (int s = 0; s < SB; ++s) {
+                    const float t = zk[s * D + d] - m;
+                    acc[s] = fmaf(t, t, acc[s]);
+                }
             }
         }
 #pragma unroll
         for (int s = 0; s < SB; ++s) {
             const float v = warp_sum(acc[s]);
-            if (lane == 0) s_zz[s * C + k] = v;
+            if (lane == 0) s_part[(s * C + k) * nsp + part] = v;
         }
+    }
+    __syncthreads();
+    for (int e = tid; e < SB * C; e += IBINN_THREADS) {
+        float v = 0.f;
+        for (int q = 0; q < nsp; ++q) v += s_part[e * nsp + q];
+        s_zz[e] = v;
     }
     __syncthreads();
     for (int s = wid; s < nb; s += IBINN_THREADS / 32) {
@@ -289,9 +336,10 @@ extern "C" int ibinn_gmm_head_forward(const float* z, const float* jac, const fl
     HeadP p{};
     p.z = z; p.jac = jac; p.mu = mu; p.phi = phi; p.y = y; p.Lx = L_x; p.logits = logits; p.Lc = L_cNLL; p.Ly = L_y;
     p.correct = correct; p.lse = lse; p.means = means; p.partials = partials; p.counter = counter; p.B = B; p.C = C; p.D = D;
-    // samples per CTA: as many (up to 8) as still leave two CTAs for each of the 148 SMs
-    const int sb = B >= 148 * 2 * 8 ? 8 : B >= 148 * 2 * 4 ? 4 : B >= 148 * 2 * 2 ? 2 : 1;
-    const size_t sm = ((size_t)sb * D + (size_t)(sb + 1) * C + 8) * sizeof(float);
+    // samples per CTA: as many as still leave two CTAs for each of the 148 SMs; 8 only where the class means dominate the traffic
+    // (4 samples = 48 KB of z per CTA keeps four CTAs per SM resident, which hides the load latencies better at C = 10)
+    const int sb = (B >= 148 * 2 * 8 && C >= 32) ? 8 : B >= 148 * 2 * 4 ? 4 : B >= 148 * 2 * 2 ? 2 : 1;
+    const size_t sm = ((size_t)sb * D + (size_t)(sb + 1) * C + (size_t)sb * C * 4 + 8) * sizeof(float);
     const dim3 grid((B + sb - 1) / sb);
 #define IBINN_HEAD_FWD(SB_)                                                                           \
     do {                                                                                              \

@@ -40,6 +40,54 @@ __global__ void __launch_bounds__(IBINN_THREADS) dct_fwd_kernel(const float* __r
     }
 }
 
+// N = 8 (every CIFAR configuration: the last stage is 8 x 8) with register blocking: a thread transforms a whole 8-vector, so the
+// operands cost ~3 shared-memory reads per output instead of 16, the index arithmetic is shifts, the input arrives by 128-bit
+// loads and the channel-fastest output is written as full 128-byte lines.  Same summation order as the generic kernel (bit-equal).
+__global__ void __launch_bounds__(IBINN_THREADS, 5) dct8_fwd_kernel(const float* __restrict__ x, const float* __restrict__ M,
+                                                                 float* __restrict__ out, int C, float scale) {
+    IBINN_DYN_SMEM(float, smem);
+    const int D = C * 64;
+    float* s_x = smem;               // [c][h][w]
+    float* s_t = s_x + D;            // [c][h][kw], channel pitch 65
+    float* s_M = smem + ((D + C * 65 + 3) & ~3);      // 16-byte aligned for the 128-bit broadcast reads
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t base = (size_t)blockIdx.x * D;
+    for (int e = tid * 4; e < D; e += IBINN_THREADS * 4) st4(s_x + e, __ldg(reinterpret_cast<const float4*>(x + base + e)));
+    if (tid < 64) s_M[tid] = __ldg(M + tid);
+    __syncthreads();
+    // t[c][h][kw] = sum_w M[kw][w] x[c][h][w]: one (c,h) row per thread
+    for (int r = tid; r < C * 8; r += IBINN_THREADS) {
+        const float4 x0 = ld4(s_x + r * 8), x1 = ld4(s_x + r * 8 + 4);
+        const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        float* tr_ = s_t + (r >> 3) * 65 + (r & 7) * 8;
+#pragma unroll 2
+        for (int kw = 0; kw < 8; ++kw) {          // (not fully unrolled: the compiler would keep all 64 coefficients in registers)
+            const float4 m0 = ld4(s_M + kw * 8), m1 = ld4(s_M + kw * 8 + 4);
+            const float mv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            float acc = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) acc = fmaf(mv[w], xv[w], acc);
+            tr_[kw] = acc;
+        }
+    }
+    __syncthreads();
+    // out[(kw*8 + kh)*C + c] = scale * sum_h M[kh][h] t[c][h][kw]: warp <-> kw, lane <-> c
+    for (int c = lane; c < C; c += 32) {
+        float tv[8];
+#pragma unroll
+        for (int h = 0; h < 8; ++h) tv[h] = s_t[c * 65 + h * 8 + wid];
+#pragma unroll 2
+        for (int kh = 0; kh < 8; ++kh) {
+            const float4 m0 = ld4(s_M + kh * 8), m1 = ld4(s_M + kh * 8 + 4);
+            const float mv[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            float acc = 0.f;
+#pragma unroll
+            for (int h = 0; h < 8; ++h) acc = fmaf(mv[h], tv[h], acc);
+            out[base + (size_t)(wid * 8 + kh) * C + c] = acc * scale;
+        }
+    }
+}
+
 // x[b,c,h,w] = scale * sum_{kh,kw} A(h,kh) A(w,kw) t[b, (kw*N + kh)*C + c],  A(r,k) = tr ? M[k][r] : M[r][k]
 __global__ void __launch_bounds__(IBINN_THREADS) dct_inv_kernel(const float* __restrict__ t, const float* __restrict__ M,
                                                                 float* __restrict__ x, int C, int N, float scale, int tr) {
@@ -143,6 +191,14 @@ extern "C" int ibinn_dct2d_forward(const float* x, const float* M, float* out, i
     if (e) return e;
     if (!x || !M || !out) return IBINN_ENULL;
     if (B <= 0 || C <= 0 || N <= 0 || N > 64) return IBINN_EINVAL;
+    if (N == 8 && ((uintptr_t)x & 15) == 0) {
+        static_assert(IBINN_THREADS == 256, "dct8_fwd_kernel maps its 8 warps to the 8 column frequencies");
+        const size_t sm8 = ((size_t)C * 64 + (size_t)C * 65 + 4 + 64) * sizeof(float);
+        e = ibinn_set_smem(dct8_fwd_kernel, sm8);
+        if (e) return e;
+        IBINN_LAUNCH(dct8_fwd_kernel, dim3(B), dim3(IBINN_THREADS), sm8, (cudaStream_t)stream, x, M, out, C, scale);
+        return ibinn_launch_status();
+    }
     size_t sm = ((size_t)2 * C * N * N + C + 4 + (size_t)N * N) * sizeof(float);
     e = ibinn_set_smem(dct_fwd_kernel, sm);
     if (e) return e;

@@ -17,9 +17,16 @@ __global__ void __launch_bounds__(IBINN_THREADS) sumsq_kernel(const float* __res
     double acc = 0.;
     const long long n4 = n / 4;
     const float4* g4 = reinterpret_cast<const float4*>(g);
-    for (long long i = (long long)blockIdx.x * IBINN_THREADS + tid; i < n4; i += (long long)gridDim.x * IBINN_THREADS) {
-        const float4 v = g4[i];
-        acc += (double)(v.x * v.x + v.y * v.y) + (double)(v.z * v.z + v.w * v.w);
+    {
+        constexpr int U = 4;                              // 64 bytes in flight per thread
+        const long long stride = (long long)gridDim.x * IBINN_THREADS;
+        for (long long i = (long long)blockIdx.x * IBINN_THREADS + tid; i < n4; i += stride * U) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = (i + u * stride < n4) ? __ldg(g4 + i + u * stride) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < U; ++u) acc += (double)(v[u].x * v[u].x + v[u].y * v[u].y) + (double)(v[u].z * v[u].z + v[u].w * v[u].w);
+        }
     }
     if (blockIdx.x == 0)
         for (long long i = n4 * 4 + tid; i < n; i += IBINN_THREADS) acc += (double)g[i] * (double)g[i];
@@ -32,9 +39,11 @@ __global__ void __launch_bounds__(IBINN_THREADS) sumsq_kernel(const float* __res
         partials[blockIdx.x] = t;
     }
     if (!last_block_ticket(counter, gridDim.x, &s_flag)) return;
-    if (tid == 0) {
+    if (tid < 32) {
         double t = 0.;
-        for (unsigned i = 0; i < gridDim.x; ++i) t += partials[i];
+        for (unsigned i = tid; i < gridDim.x; i += 32) t += __ldcg(partials + i);       // lane-strided, then a fixed shuffle tree
+        t = warp_sum_d(t);
+        if (tid != 0) return;
         for (int i = 0; i < n_extra; ++i) t += (double)extra_sumsq[i];
         const double nrm = sqrt(t);
         out[0] = (float)nrm;
