@@ -224,10 +224,8 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
     const size_t ib = (size_t)b * C * HW + qo;
     const float gj = p.g_jac ? __ldg(p.g_jac + b) : 0.f;
 
-    for (int e = tid; e < C * Cp; e += IBINN_THREADS) {
-        const int o = e / Cp, i = e - o * Cp;
-        s_w[e] = (i < C) ? __ldg(p.w + (size_t)o * C + i) : 0.f;
-    }
+    for (int o = wid; o < C; o += IBINN_THREADS / 32)          // warp <-> output channel, lane <-> input channel: no divisions
+        for (int i = lane; i < Cp; i += 32) s_w[o * Cp + i] = (i < C) ? __ldg(p.w + (size_t)o * C + i) : 0.f;
     // phase A: g_v = g_out * exp(an) into shared memory, per-channel sums of g and g (y - off) for the ActNorm gradients
     if (HWl % 32 == 0) {
         // fast path: every load of the sample is in flight at once; a warp's 32 consecutive elements share a channel, so
@@ -239,6 +237,7 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
         __syncthreads();
         constexpr int KB = 12;
         const int n = C * HWl;
+        const int shl = p.hw_shift;        // log2(HWl) when it is a power of two: channel / pixel by shifts instead of two divisions per element
         for (int e0 = 0; e0 < n; e0 += IBINN_THREADS * KB) {
             float g[KB], y[KB];
 #pragma unroll
@@ -246,7 +245,7 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
                 const int e = e0 + tid + IBINN_THREADS * k;
                 g[k] = 0.f; y[k] = 0.f;
                 if (e < n) {
-                    const int o = e / HWl, q = e - o * HWl;
+                    const int o = shl ? (e >> shl) : e / HWl, q = e - o * HWl;
                     g[k] = __ldg(p.g_out + ib + (size_t)o * HW + q); y[k] = __ldg(p.out_saved + ib + (size_t)o * HW + q);
                 }
             }
@@ -254,7 +253,7 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
             for (int k = 0; k < KB; ++k) {
                 const int e = e0 + tid + IBINN_THREADS * k;
                 if (e - lane >= n) continue;                 // whole warp in or out (n is a multiple of 32)
-                const int o = e / HWl, q = e - o * HWl;
+                const int o = shl ? (e >> shl) : e / HWl, q = e - o * HWl;
                 s_u[(size_t)o * HWp + q] = g[k] * s_sc[o];
                 const float so = warp_sum(g[k]), sn = warp_sum(g[k] * (y[k] - s_of[o]));
                 if (lane == 0) { s_part[(e >> 5) * 2] = so; s_part[(e >> 5) * 2 + 1] = sn; }
@@ -665,6 +664,11 @@ extern "C" int ibinn_aio_coupling_backward(const float* g_out, const float* g_ja
     p.g_x = g_x; p.g_a = g_a; p.g_an = g_act_norm; p.g_off = g_act_offset; p.partials = partials; p.counter = counter;
     p.B = B; p.C = C; p.HW = H * W; p.clamp = clamp; p.alpha = alpha;
     p.nsplit = aio_bwd_nsplit(H * W);
+    {
+        const int HWl = H * W / p.nsplit;          // pixels per CTA
+        if (HWl >= 2 && (HWl & (HWl - 1)) == 0)
+            while ((1 << p.hw_shift) < HWl) ++p.hw_shift;
+    }
     p.defer = defer_reduce ? 1 : 0;
     size_t sm = aio_smem(C, H * W / p.nsplit);
     int e = ibinn_set_smem(aio_bwd_kernel, sm);

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(IBINN_THREADS) head_fwd_kernel(const HeadP p) 
 #pragma unroll
         for (int s = 0; s < SB; ++s) acc[s] = 0.f;
         if (vec) {
-            constexpr int MU = 3;                         // class-mean loads (L2) in flight per lane
+            constexpr int MU = 6;                         // class-mean loads (L2) in flight per lane
             for (int d0 = lane * 4; d0 < Dp; d0 += 128 * MU) {
                 float4 mv[MU];
 #pragma unroll
@@ -185,12 +185,34 @@ __global__ void __launch_bounds__(IBINN_THREADS) head_fwd_kernel(const HeadP p) 
         }
     }
     if (!last_block_ticket(p.counter, gridDim.x, &s_flag)) return;
-    // batch means: warp q sums quantity q over the samples (lane-strided, fp64, fixed order)
-    if (wid < 5) {
-        double t = 0.;
-        for (int bb = lane; bb < B; bb += 32) t += (double)__ldcg(p.partials + (size_t)bb * 5 + wid);
-        t = warp_sum_d(t);
-        if (lane == 0) p.means[wid] = (float)(t / (wid == 1 ? (double)B * C : (double)B));
+    // batch means (fp64, fixed order): thread-strided partial sums of the five per-sample records, a shuffle tree per warp, then
+    // warp q adds the eight warp sums of quantity q.  (A single warp per quantity was a 25 us serial tail at B = 8192.)
+    {
+        __shared__ double s_red[5][IBINN_THREADS / 32];
+        double t[5] = {0., 0., 0., 0., 0.};
+        constexpr int UB = 4;
+        for (int b1 = tid; b1 < B; b1 += IBINN_THREADS * UB) {
+            float v[UB][5];
+#pragma unroll
+            for (int u = 0; u < UB; ++u)
+#pragma unroll
+                for (int q = 0; q < 5; ++q) v[u][q] = (b1 + u * IBINN_THREADS < B) ? __ldcg(p.partials + (size_t)(b1 + u * IBINN_THREADS) * 5 + q) : 0.f;
+#pragma unroll
+            for (int u = 0; u < UB; ++u)
+#pragma unroll
+                for (int q = 0; q < 5; ++q) t[q] += (double)v[u][q];
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const double w = warp_sum_d(t[q]);
+            if (lane == 0) s_red[q][wid] = w;
+        }
+        __syncthreads();
+        if (tid < 5) {
+            double tot = 0.;
+            for (int i = 0; i < IBINN_THREADS / 32; ++i) tot += s_red[tid][i];
+            p.means[tid] = (float)(tot / (tid == 1 ? (double)B * C : (double)B));
+        }
     }
     if (tid == 0) *p.counter = 0u;
 }
