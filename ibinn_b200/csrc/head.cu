@@ -5,6 +5,7 @@
 // Distances are evaluated as sum_d (z_d - mu_kd)^2 (not the expanded -2 z.mu + |z|^2 + |mu|^2 the
 // reference uses): same value in exact arithmetic, no cancellation in fp32.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -33,6 +34,106 @@ __device__ __forceinline__ void log_softmax_phi(const float* phi, int C, float* 
         s = warp_sum(s);
         const float l = m + logf(s);
         for (int k = lane; k < C; k += 32) s_lw[k] = __ldg(phi + k) - l;
+    }
+}
+
+// Loss terms of one sample from its C squared distances zz (shared memory) by one warp: model.py:144-159.
+// The five per-sample quantities that feed the batch means go to p.partials[b] (wsum == nullptr) or are added to wsum[0..5) (lane 0).
+__device__ __forceinline__ void head_sample_tail(const HeadP& p, int b, const float* zz, const float* s_lw, int lane, double* wsum = nullptr) {
+    const int C = p.C, D = p.D;
+    const float jac = __ldg(p.jac + b);
+    float m = -INFINITY;
+    for (int k = lane; k < C; k += 32) m = fmaxf(m, -0.5f * zz[k] + s_lw[k]);
+    m = warp_max(m);
+    float se = 0.f;
+    for (int k = lane; k < C; k += 32) se += expf(-0.5f * zz[k] + s_lw[k] - m);
+    se = warp_sum(se);
+    const float ls = logf(se);
+    const float lse = m + ls;
+    float sl = 0.f;
+    for (int k = lane; k < C; k += 32) {
+        const float lg = -0.5f * zz[k];
+        p.logits[(size_t)b * C + k] = lg;
+        sl += lg;
+    }
+    sl = warp_sum(sl);
+    float lc = 0.f, ly = 0.f;
+    float by = -INFINITY, bl = -INFINITY; int iy = 0x7fffffff, il = 0x7fffffff;
+    if (p.y) {
+        for (int k = lane; k < C; k += 32) {
+            const float yk = __ldg(p.y + (size_t)b * C + k);
+            const float lg = -0.5f * zz[k];
+            lc = fmaf(zz[k], rintf(yk), lc);
+            // (log_softmax(l)_k - logw_k) evaluated like the reference: shift by the max first
+            ly = fmaf(yk, ((lg + s_lw[k] - m) - ls) - s_lw[k], ly);
+            if (yk > by) { by = yk; iy = k; }
+            if (lg > bl) { bl = lg; il = k; }
+        }
+        lc = warp_sum(lc);
+        ly = warp_sum(ly);
+        // arg max with first-index tie break (torch.max semantics)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float oy = __shfl_xor_sync(0xffffffffu, by, o); const int oiy = __shfl_xor_sync(0xffffffffu, iy, o);
+            if (oy > by || (oy == by && oiy < iy)) { by = oy; iy = oiy; }
+            const float ol = __shfl_xor_sync(0xffffffffu, bl, o); const int oil = __shfl_xor_sync(0xffffffffu, il, o);
+            if (ol > bl || (ol == bl && oil < il)) { bl = ol; il = oil; }
+        }
+    }
+    if (lane == 0) {
+        const float lx = (-lse - jac) / (float)D;
+        p.Lx[b] = lx;
+        p.lse[b] = lse;
+        float pr[5] = {lx, sl, 0.f, 0.f, 0.f};
+        if (p.y) {
+            const float c = (0.5f * lc - jac) / (float)D;
+            const float ok = (iy == il) ? 1.f : 0.f;
+            p.Lc[b] = c; p.Ly[b] = ly; p.correct[b] = ok;
+            pr[2] = c; pr[3] = ly; pr[4] = ok;
+        }
+        if (wsum) {
+#pragma unroll
+            for (int q = 0; q < 5; ++q) wsum[q] += (double)pr[q];
+        } else {
+            float* dst = p.partials + (size_t)b * 5;
+#pragma unroll
+            for (int q = 0; q < 5; ++q) dst[q] = pr[q];
+        }
+    }
+}
+
+// Executed by the last CTA: the five batch means.
+template <int NT>
+__device__ __forceinline__ void head_batch_means(const HeadP& p) {
+    const int B = p.B, C = p.C, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // batch means (fp64, fixed order): thread-strided partial sums of the five per-sample records, a shuffle tree per warp, then
+    // warp q adds the eight warp sums of quantity q.  (A single warp per quantity was a 25 us serial tail at B = 8192.)
+    {
+        __shared__ double s_red[5][NT / 32];
+        double t[5] = {0., 0., 0., 0., 0.};
+        constexpr int UB = 4;
+        for (int b1 = tid; b1 < B; b1 += NT * UB) {
+            float v[UB][5];
+#pragma unroll
+            for (int u = 0; u < UB; ++u)
+#pragma unroll
+                for (int q = 0; q < 5; ++q) v[u][q] = (b1 + u * NT < B) ? __ldcg(p.partials + (size_t)(b1 + u * NT) * 5 + q) : 0.f;
+#pragma unroll
+            for (int u = 0; u < UB; ++u)
+#pragma unroll
+                for (int q = 0; q < 5; ++q) t[q] += (double)v[u][q];
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const double w = warp_sum_d(t[q]);
+            if (lane == 0) s_red[q][wid] = w;
+        }
+        __syncthreads();
+        if (tid < 5) {
+            double tot = 0.;
+            for (int i = 0; i < NT / 32; ++i) tot += s_red[tid][i];
+            p.means[tid] = (float)(tot / (tid == 1 ? (double)B * C : (double)B));
+        }
     }
 }
 
@@ -128,91 +229,206 @@ __global__ void __launch_bounds__(IBINN_THREADS) head_fwd_kernel(const HeadP p) 
         s_zz[e] = v;
     }
     __syncthreads();
-    for (int s = wid; s < nb; s += IBINN_THREADS / 32) {
-        const int b = b0 + s;
-        const float* zz = s_zz + s * C;
-        const float jac = __ldg(p.jac + b);
-        float m = -INFINITY;
-        for (int k = lane; k < C; k += 32) m = fmaxf(m, -0.5f * zz[k] + s_lw[k]);
-        m = warp_max(m);
-        float se = 0.f;
-        for (int k = lane; k < C; k += 32) se += expf(-0.5f * zz[k] + s_lw[k] - m);
-        se = warp_sum(se);
-        const float ls = logf(se);
-        const float lse = m + ls;
-        float sl = 0.f;
-        for (int k = lane; k < C; k += 32) {
-            const float lg = -0.5f * zz[k];
-            p.logits[(size_t)b * C + k] = lg;
-            sl += lg;
-        }
-        sl = warp_sum(sl);
-        float lc = 0.f, ly = 0.f;
-        float by = -INFINITY, bl = -INFINITY; int iy = 0x7fffffff, il = 0x7fffffff;
-        if (p.y) {
-            for (int k = lane; k < C; k += 32) {
-                const float yk = __ldg(p.y + (size_t)b * C + k);
-                const float lg = -0.5f * zz[k];
-                lc = fmaf(zz[k], rintf(yk), lc);
-                // (log_softmax(l)_k - logw_k) evaluated like the reference: shift by the max first
-                ly = fmaf(yk, ((lg + s_lw[k] - m) - ls) - s_lw[k], ly);
-                if (yk > by) { by = yk; iy = k; }
-                if (lg > bl) { bl = lg; il = k; }
-            }
-            lc = warp_sum(lc);
-            ly = warp_sum(ly);
-            // arg max with first-index tie break (torch.max semantics)
+    for (int s = wid; s < nb; s += IBINN_THREADS / 32) head_sample_tail(p, b0 + s, s_zz + s * C, s_lw, lane);
+    if (!last_block_ticket(p.counter, gridDim.x, &s_flag)) return;
+    head_batch_means<IBINN_THREADS>(p);
+    if (tid == 0) *p.counter = 0u;
+}
+
+// N per-lane partial sums -> N warp totals with 31-ish shuffles per 32 values instead of 5 N: at every butterfly step a lane
+// keeps one half of its values and sends the other half to its partner.  Every total is formed by exactly the tree of
+// `warp_sum` ((l, l^16), then ^8, ...; a + b == b + a), so the value does not depend on the slot it is computed in.  Afterwards
+// the lane holds the totals `base + r` for r < lim (lim <= 2 for N <= 64) in v[r].
+template <int N, int O>
+struct WarpMultiSum {
+    template <int NV>
+    static __device__ __forceinline__ void run(float (&v)[NV], int lane, int& base, int& lim) {
+        constexpr int H = (N + 1) / 2;
+        const bool up = (lane & O) != 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float oy = __shfl_xor_sync(0xffffffffu, by, o); const int oiy = __shfl_xor_sync(0xffffffffu, iy, o);
-                if (oy > by || (oy == by && oiy < iy)) { by = oy; iy = oiy; }
-                const float ol = __shfl_xor_sync(0xffffffffu, bl, o); const int oil = __shfl_xor_sync(0xffffffffu, il, o);
-                if (ol > bl || (ol == bl && oil < il)) { bl = ol; il = oil; }
+        for (int i = 0; i < H; ++i) {
+            const float lo = v[i];
+            const float hi = (i + H < N) ? v[i + H] : 0.f;
+            const float got = __shfl_xor_sync(0xffffffffu, up ? lo : hi, O);
+            v[i] = (up ? hi : lo) + got;
+        }
+        base += up ? H : 0;
+        lim = up ? lim - H : min(lim, H);
+        WarpMultiSum<H, O / 2>::run(v, lane, base, lim);
+    }
+};
+template <int N>
+struct WarpMultiSum<N, 0> {
+    template <int NV>
+    static __device__ __forceinline__ void run(float (&)[NV], int, int&, int&) {}
+};
+template <int N>
+__device__ __forceinline__ void warp_multi_sum(float (&v)[N], int lane, int& base, int& lim) {
+    base = 0;
+    lim = N;
+    WarpMultiSum<N, 16>::run(v, lane, base, lim);
+}
+
+// Two fp32 lanes in one 64-bit register pair: Blackwell's FADD2 / FFMA2 issue two IEEE fp32 operations per instruction slot
+// (each component rounds exactly like the scalar instruction).  The host simulator of tests/emu uses the scalar definition.
+#ifdef IBINN_EMU
+struct f32x2 { float lo, hi; };
+__device__ __forceinline__ f32x2 f2_make(float lo, float hi) { return f32x2{lo, hi}; }
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) { return f32x2{a.lo - b.lo, a.hi - b.hi}; }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { return f32x2{fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)}; }
+__device__ __forceinline__ float f2_lo(f32x2 a) { return a.lo; }
+__device__ __forceinline__ float f2_hi(f32x2 a) { return a.hi; }
+#else
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_make(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float f2_lo(f32x2 a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); return lo; }
+__device__ __forceinline__ float f2_hi(f32x2 a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); return hi; }
+#endif
+
+// Ordered loads for the software pipeline of head_fwd_stream_kernel: ptxas gives a load whose first use is in the NEXT loop
+// iteration the lowest priority and sinks it to the end of the loop body (seen in SASS: all refills after the last FFMA2), which
+// exposes the full HBM latency once per body.  Volatile accesses keep their program order among themselves, so issuing both the
+// z refill (global) and the class-mean reads (shared) as volatile pins each refill between two columns' arithmetic.
+#ifdef IBINN_EMU
+__device__ __forceinline__ float4 ld4_ordered_global(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4_ordered_shared(const float* p) { return *reinterpret_cast<const float4*>(p); }
+#else
+__device__ __forceinline__ float4 ld4_ordered_global(const float* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld4_ordered_shared(const float* p) {
+    float4 v;
+    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+}
+#endif
+
+// Scoring-batch forward for few classes (C = CC, C x D floats of class means fit into shared memory): persistent CTAs of NT / 32 warps keep
+// mu resident in shared memory and stream z from HBM exactly once; a warp owns SW samples at a time, keeps their SW x CC partial
+// distances in registers (one shared-memory read of mu serves SW samples) and never stages z.  The summation order per
+// (sample, class) is that of head_fwd_kernel with nsp = 4 (four feature parts, lane-strided 128-bit steps, warp tree, parts added in
+// order), so the per-sample results are bit-identical to the small-batch kernel.  The class means sit in shared memory interleaved by
+// class PAIRS ([pair][half][D/4][(d, class), 4 floats]) so that one 128-bit read yields two packed (m_2p[d], m_2p+1[d]) operands and the
+// distance update runs as FADD2 / FFMA2 (z broadcast to both halves): half the fp32 issue slots of the scalar form (23 M -> 17 M
+// warp instructions at B = 8192).  Measured limit (profiles/r01_head_stream.md): 2 B C D fp32 operations is what bounds this kernel,
+// not HBM: the packed instructions run on the FMA-heavy pipe only, which is busy 46 % of the active cycles.
+template <int SW, int CC, int NT, int UU>
+__global__ void __launch_bounds__(NT, 1) head_fwd_stream_kernel(const HeadP p) {
+    IBINN_DYN_SMEM(float, smem);
+    __shared__ int s_flag;
+    constexpr int NW = NT / 32, NV = SW * CC;
+    const int B = p.B, D = p.D, Dp = D >> 2, ncol = Dp >> 7;     // host: D % (512 * UU) == 0
+    float* s_mu = smem;                       // [CC / 2][2][D / 4][4]
+    float* s_zz = s_mu + (size_t)CC * D;      // [NW][NV]
+    float* s_lw = s_zz + NW * NV;             // [CC]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    static_assert(CC % 2 == 0, "class pairs");
+    const int Q = D >> 2;                     // 128-bit columns per class
+    for (int i = tid; i < (CC / 2) * Q; i += NT) {
+        const int kp = i / Q, q = i - kp * Q;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p.mu + (size_t)(2 * kp) * D) + q);
+        const float4 c = __ldg(reinterpret_cast<const float4*>(p.mu + (size_t)(2 * kp + 1) * D) + q);
+        st4(s_mu + ((size_t)(2 * kp) * Q + q) * 4, make_float4(a.x, c.x, a.y, c.y));
+        st4(s_mu + ((size_t)(2 * kp + 1) * Q + q) * 4, make_float4(a.z, c.z, a.w, c.w));
+    }
+    __shared__ double s_wred[NW][5];
+    if (tid < NW * 5) (&s_wred[0][0])[tid] = 0.;
+    log_softmax_phi(p.phi, CC, s_lw);
+    __syncthreads();
+    const int ngroups = (B + SW - 1) / SW;
+    float* my_zz = s_zz + wid * NV;
+    double* wsum = s_wred[wid];               // lane 0 only
+    for (int g = blockIdx.x + gridDim.x * wid; g < ngroups; g += gridDim.x * NW) {
+        const int b0 = g * SW, nb = min(SW, B - b0);
+        const float* zs[SW];
+#pragma unroll
+        for (int s = 0; s < SW; ++s) zs[s] = p.z + (size_t)(b0 + min(s, nb - 1)) * D;
+        float tot0 = 0.f, tot1 = 0.f;
+        int base = 0, lim = 0;
+        // Rolling prefetch: a column's registers are refilled with the column UU steps ahead as soon as it has been consumed, so
+        // UU x SW 128-bit loads per lane stay in flight across the whole sample (and across the part boundaries).
+        float4 zv[UU][SW];
+#pragma unroll
+        for (int u = 0; u < UU; ++u)
+#pragma unroll
+            for (int s = 0; s < SW; ++s) zv[u][s] = __ldcs(reinterpret_cast<const float4*>(zs[s] + lane * 4 + 128 * u));
+        int pn = 0, cn = UU;                  // (part, column) of the next load
+        if (cn == ncol) { cn = 0; pn = 1; }
+        int noff = pn * Dp + lane * 4 + 128 * cn;
+#pragma unroll 1
+        for (int part = 0; part < 4; ++part) {
+            f32x2 acc2[SW][CC / 2];
+#pragma unroll
+            for (int s = 0; s < SW; ++s)
+#pragma unroll
+                for (int kp = 0; kp < CC / 2; ++kp) acc2[s][kp] = f2_make(0.f, 0.f);
+#pragma unroll 1
+            for (int c0 = 0; c0 < ncol; c0 += UU) {
+#pragma unroll
+                for (int u = 0; u < UU; ++u) {
+                    const float* mq = s_mu + (size_t)(part * Dp + lane * 4 + 128 * (c0 + u));
+#pragma unroll
+                    for (int kp = 0; kp < CC / 2; ++kp) {
+                        const float4 m01 = ld4_ordered_shared(mq + (size_t)(2 * kp) * D), m23 = ld4_ordered_shared(mq + (size_t)(2 * kp + 1) * D);
+                        const f32x2 m0 = f2_make(m01.x, m01.y), m1 = f2_make(m01.z, m01.w);
+                        const f32x2 m2 = f2_make(m23.x, m23.y), m3 = f2_make(m23.z, m23.w);
+#pragma unroll
+                        for (int s = 0; s < SW; ++s) {
+                            f32x2 a = acc2[s][kp];
+                            f32x2 t = f2_sub(f2_make(zv[u][s].x, zv[u][s].x), m0); a = f2_fma(t, t, a);
+                            t = f2_sub(f2_make(zv[u][s].y, zv[u][s].y), m1); a = f2_fma(t, t, a);
+                            t = f2_sub(f2_make(zv[u][s].z, zv[u][s].z), m2); a = f2_fma(t, t, a);
+                            t = f2_sub(f2_make(zv[u][s].w, zv[u][s].w), m3); a = f2_fma(t, t, a);
+                            acc2[s][kp] = a;
+                        }
+                    }
+                    // (unconditional: past the end the last column is simply read again; a branch here makes the compiler sink
+                    // all the refills below the arithmetic of the whole UU-column body)
+#pragma unroll
+                    for (int s = 0; s < SW; ++s) zv[u][s] = ld4_ordered_global(zs[s] + noff);
+                    ++cn;
+                    const bool wrap = cn == ncol;
+                    cn = wrap ? 0 : cn;
+                    pn = wrap ? pn + 1 : pn;
+                    noff = min(pn, 3) * Dp + lane * 4 + 128 * (pn > 3 ? ncol - 1 : cn);
+                }
             }
+            float acc[NV];
+#pragma unroll
+            for (int s = 0; s < SW; ++s)
+#pragma unroll
+                for (int kp = 0; kp < CC / 2; ++kp) {
+                    acc[s * CC + 2 * kp] = f2_lo(acc2[s][kp]);
+                    acc[s * CC + 2 * kp + 1] = f2_hi(acc2[s][kp]);
+                }
+            warp_multi_sum<NV>(acc, lane, base, lim);
+            tot0 += acc[0];
+            tot1 += acc[1];
         }
-        if (lane == 0) {
-            const float lx = (-lse - jac) / (float)D;
-            p.Lx[b] = lx;
-            p.lse[b] = lse;
-            float* pr = p.partials + (size_t)b * 5;
-            pr[0] = lx; pr[1] = sl;
-            if (p.y) {
-                const float c = (0.5f * lc - jac) / (float)D;
-                const float ok = (iy == il) ? 1.f : 0.f;
-                p.Lc[b] = c; p.Ly[b] = ly; p.correct[b] = ok;
-                pr[2] = c; pr[3] = ly; pr[4] = ok;
-            } else { pr[2] = 0.f; pr[3] = 0.f; pr[4] = 0.f; }
-        }
+        if (lim > 0) my_zz[base] = tot0;
+        if (lim > 1) my_zz[base + 1] = tot1;
+        __syncwarp();
+        for (int s = 0; s < nb; ++s) head_sample_tail(p, b0 + s, my_zz + s * CC, s_lw, lane, wsum);
+        __syncwarp();
+    }
+    // batch means (fp64, fixed order): warp sums -> one record per CTA (front of the partials workspace) -> the last CTA adds the
+    // gridDim.x records.  (Reading back one record per SAMPLE in the last CTA was a ~4 us serial tail at B = 8192.)
+    __syncthreads();
+    double* recs = reinterpret_cast<double*>(p.partials);
+    if (tid < 5) {
+        double t = 0.;
+        for (int w = 0; w < NW; ++w) t += s_wred[w][tid];
+        recs[(size_t)blockIdx.x * 5 + tid] = t;
     }
     if (!last_block_ticket(p.counter, gridDim.x, &s_flag)) return;
-    // batch means (fp64, fixed order): thread-strided partial sums of the five per-sample records, a shuffle tree per warp, then
-    // warp q adds the eight warp sums of quantity q.  (A single warp per quantity was a 25 us serial tail at B = 8192.)
-    {
-        __shared__ double s_red[5][IBINN_THREADS / 32];
-        double t[5] = {0., 0., 0., 0., 0.};
-        constexpr int UB = 4;
-        for (int b1 = tid; b1 < B; b1 += IBINN_THREADS * UB) {
-            float v[UB][5];
-#pragma unroll
-            for (int u = 0; u < UB; ++u)
-#pragma unroll
-                for (int q = 0; q < 5; ++q) v[u][q] = (b1 + u * IBINN_THREADS < B) ? __ldcg(p.partials + (size_t)(b1 + u * IBINN_THREADS) * 5 + q) : 0.f;
-#pragma unroll
-            for (int u = 0; u < UB; ++u)
-#pragma unroll
-                for (int q = 0; q < 5; ++q) t[q] += (double)v[u][q];
-        }
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            const double w = warp_sum_d(t[q]);
-            if (lane == 0) s_red[q][wid] = w;
-        }
-        __syncthreads();
-        if (tid < 5) {
-            double tot = 0.;
-            for (int i = 0; i < IBINN_THREADS / 32; ++i) tot += s_red[tid][i];
-            p.means[tid] = (float)(tot / (tid == 1 ? (double)B * C : (double)B));
-        }
+    if (tid < 5) {
+        double t = 0.;
+        for (unsigned i = 0; i < gridDim.x; ++i) t += __ldcg(recs + (size_t)i * 5 + tid);
+        p.means[tid] = (float)(t / (tid == 1 ? (double)B * CC : (double)B));
     }
     if (tid == 0) *p.counter = 0u;
 }
@@ -358,6 +574,30 @@ extern "C" int ibinn_gmm_head_forward(const float* z, const float* jac, const fl
     HeadP p{};
     p.z = z; p.jac = jac; p.mu = mu; p.phi = phi; p.y = y; p.Lx = L_x; p.logits = logits; p.Lc = L_cNLL; p.Ly = L_y;
     p.correct = correct; p.lse = lse; p.means = means; p.partials = partials; p.counter = counter; p.B = B; p.C = C; p.D = D;
+    // Scoring batches of the 10-class configs: class means resident in shared memory, z streamed once (head_fwd_stream_kernel), from
+    // the batch at which most of its 148 x 16 warps get a pair of samples.  IBINN_HEAD_STREAM = 0 / 2 / 1024 overrides the choice
+    // (A/B measurements only; the per-sample results are bit-identical either way).
+    {
+        static const int force = [] { const char* v = getenv("IBINN_HEAD_STREAM"); return v ? atoi(v) : -1; }();
+        const bool can = C == 10 && D % 512 == 0 && (int64_t)B * 5 * 4 >= 148 * 5 * 8 &&
+                         ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(mu)) & 15) == 0 && (reinterpret_cast<uintptr_t>(partials) & 7) == 0;
+        int sw = !can ? 0 : B >= 3 * 148 * 16 ? 1024 : B >= 2048 ? 2 : 0;
+        if (can && force >= 0) sw = force;
+#define IBINN_HEAD_STREAM(SW_, NT_, UU_)                                                                                      \
+    do {                                                                                                                      \
+        const size_t sms = ((size_t)C * D + (size_t)(NT_ / 32) * SW_ * C + C + 8) * sizeof(float);                            \
+        if (sms > 227 * 1024 || D % (512 * UU_) != 0) break;                                                                                          \
+        const int ngroups = (B + SW_ - 1) / SW_;                                                                              \
+        const dim3 grid(min(148, ngroups));     /* groups go round-robin over (CTA, warp): every SM streams */               \
+        e = ibinn_set_smem(head_fwd_stream_kernel<SW_, 10, NT_, UU_>, sms);                                                   \
+        if (e) return e;                                                                                                      \
+        IBINN_LAUNCH((head_fwd_stream_kernel<SW_, 10, NT_, UU_>), grid, dim3(NT_), sms, (cudaStream_t)stream, p);             \
+        return ibinn_launch_status();                                                                                         \
+    } while (0)
+        if (sw == 2) IBINN_HEAD_STREAM(2, 512, 3);               // 128 registers: three columns of z in flight per lane
+        else if (sw == 1024) IBINN_HEAD_STREAM(2, 1024, 2);      // 64 registers, 32 warps per SM: best at B = 8192 (38.5 vs 40.4 us)
+#undef IBINN_HEAD_STREAM
+    }
     // samples per CTA: as many as still leave two CTAs for each of the 148 SMs; 8 only where the class means dominate the traffic
     // (4 samples = 48 KB of z per CTA keeps four CTAs per SM resident, which hides the load latencies better at C = 10)
     const int sb = (B >= 148 * 2 * 8 && C >= 32) ? 8 : B >= 148 * 2 * 4 ? 4 : B >= 148 * 2 * 2 ? 2 : 1;
