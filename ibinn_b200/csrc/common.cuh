@@ -89,3 +89,21 @@ __device__ __forceinline__ bool last_block_ticket(unsigned* counter, unsigned nb
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// Two fp32 lanes in one 64-bit register pair: Blackwell's FADD2 / FFMA2 issue two IEEE fp32 operations per instruction slot
+// (each component rounds exactly like the scalar instruction).  The host simulator of tests/emu uses the scalar definition.
+#ifdef IBINN_EMU
+struct f32x2 { float lo, hi; };
+__device__ __forceinline__ f32x2 f2_make(float lo, float hi) { return f32x2{lo, hi}; }
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) { return f32x2{a.lo - b.lo, a.hi - b.hi}; }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { return f32x2{fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)}; }
+__device__ __forceinline__ float f2_lo(f32x2 a) { return a.lo; }
+__device__ __forceinline__ float f2_hi(f32x2 a) { return a.hi; }
+#else
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 f2_make(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ float f2_lo(f32x2 a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); return lo; }
+__device__ __forceinline__ float f2_hi(f32x2 a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); return hi; }
+#endif

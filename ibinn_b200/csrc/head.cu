@@ -269,24 +269,6 @@ __device__ __forceinline__ void warp_multi_sum(float (&v)[N], int lane, int& bas
     WarpMultiSum<N, 16>::run(v, lane, base, lim);
 }
 
-// Two fp32 lanes in one 64-bit register pair: Blackwell's FADD2 / FFMA2 issue two IEEE fp32 operations per instruction slot
-// (each component rounds exactly like the scalar instruction).  The host simulator of tests/emu uses the scalar definition.
-#ifdef IBINN_EMU
-struct f32x2 { float lo, hi; };
-__device__ __forceinline__ f32x2 f2_make(float lo, float hi) { return f32x2{lo, hi}; }
-__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) { return f32x2{a.lo - b.lo, a.hi - b.hi}; }
-__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { return f32x2{fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi)}; }
-__device__ __forceinline__ float f2_lo(f32x2 a) { return a.lo; }
-__device__ __forceinline__ float f2_hi(f32x2 a) { return a.hi; }
-#else
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 f2_make(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ f32x2 f2_sub(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 f2_fma(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ float f2_lo(f32x2 a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); return lo; }
-__device__ __forceinline__ float f2_hi(f32x2 a) { float lo, hi; asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a)); return hi; }
-#endif
-
 // Ordered loads for the software pipeline of head_fwd_stream_kernel: ptxas gives a load whose first use is in the NEXT loop
 // iteration the lowest priority and sinks it to the end of the loop body (seen in SASS: all refills after the last FFMA2), which
 // exposes the full HBM latency once per body.  Volatile accesses keep their program order among themselves, so issuing both the
@@ -583,16 +565,16 @@ extern "C" int ibinn_gmm_head_forward(const float* z, const float* jac, const fl
                          ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(mu)) & 15) == 0 && (reinterpret_cast<uintptr_t>(partials) & 7) == 0;
         int sw = !can ? 0 : B >= 3 * 148 * 16 ? 1024 : B >= 2048 ? 2 : 0;
         if (can && force >= 0) sw = force;
-#define IBINN_HEAD_STREAM(SW_, NT_, UU_)                                                                                      \
-    do {                                                                                                                      \
-        const size_t sms = ((size_t)C * D + (size_t)(NT_ / 32) * SW_ * C + C + 8) * sizeof(float);                            \
-        if (sms > 227 * 1024 || D % (512 * UU_) != 0) break;                                                                                          \
-        const int ngroups = (B + SW_ - 1) / SW_;                                                                              \
-        const dim3 grid(min(148, ngroups));     /* groups go round-robin over (CTA, warp): every SM streams */               \
-        e = ibinn_set_smem(head_fwd_stream_kernel<SW_, 10, NT_, UU_>, sms);                                                   \
-        if (e) return e;                                                                                                      \
-        IBINN_LAUNCH((head_fwd_stream_kernel<SW_, 10, NT_, UU_>), grid, dim3(NT_), sms, (cudaStream_t)stream, p);             \
-        return ibinn_launch_status();                                                                                         \
+#define IBINN_HEAD_STREAM(SW_, NT_, UU_)                                                                                                  \
+    do {                                                                                                                                  \
+        const size_t sms = ((size_t)C * D + (size_t)(NT_ / 32) * SW_ * C + C + 8) * sizeof(float);                                        \
+        if (sms > 227 * 1024 || D % (512 * UU_) != 0) break;                                                                              \
+        const int ngroups = (B + SW_ - 1) / SW_;                                                                                          \
+        const dim3 grid(min(148, ngroups));     /* groups go round-robin over (CTA, warp): every SM streams */                            \
+        e = ibinn_set_smem(head_fwd_stream_kernel<SW_, 10, NT_, UU_>, sms);                                                               \
+        if (e) return e;                                                                                                                  \
+        IBINN_LAUNCH((head_fwd_stream_kernel<SW_, 10, NT_, UU_>), grid, dim3(NT_), sms, (cudaStream_t)stream, p);                         \
+        return ibinn_launch_status();                                                                                                     \
     } while (0)
         if (sw == 2) IBINN_HEAD_STREAM(2, 512, 3);               // 128 registers: three columns of z in flight per lane
         else if (sw == 1024) IBINN_HEAD_STREAM(2, 1024, 2);      // 64 registers, 32 warps per SM: best at B = 8192 (38.5 vs 40.4 us)
