@@ -235,7 +235,9 @@ int ibinn_linear_wgrad(const float* g, const float* h, const float* g_mask, int 
 /* ---------------------------------------------------------------- GMM / Information-Bottleneck head
  * Replaces reference model.py:113-126 (`cluster_distances`) and model.py:144-163 (loss dict).
  * z (B,D), jac (B), mu (C,D), phi (C), y (B,C) soft one-hot or NULL.  Per-sample outputs L_x, logits (B,C),
- * L_cNLL, L_y, correct (0/1), lse; means[5] = mean(L_x), mean(logits), mean(L_cNLL), mean(L_y), acc. */
+ * L_cNLL, L_y, correct (0/1), lse; means[5] = mean(L_x), mean(logits), mean(L_cNLL), mean(L_y), acc.
+ * `partials` is scratch of ibinn_gmm_head_partials_floats(B) floats (contents unspecified afterwards: per-sample records, or per-CTA
+ * fp64 records at the scoring batches when it is 8-byte aligned); `counter` one zero-initialised uint32, left at zero. */
 int64_t ibinn_gmm_head_partials_floats(int B);
 int ibinn_gmm_head_forward(const float* z, const float* jac, const float* mu, const float* phi, const float* y, float* L_x,
                            float* logits, float* L_cNLL, float* L_y, float* correct, float* lse, float* means,

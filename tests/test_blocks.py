@@ -264,6 +264,8 @@ def test_head_large_batch_is_batch_size_independent(dev, B, C):
     per-sample results must equal the one-sample-per-CTA results bit for bit and the fp64 restatement of model.py:113-126,144-159
     within the head tolerance (1e-3 on the loss terms and logits, bit-exact arg-max)."""
     from ibinn_b200 import ops
+    if dev.type != 'cuda' and B == 7300:
+        pytest.skip('the 1024-thread variant needs D % 1024 == 0: GPU only (the simulator runs the 512-thread variant at B = 2500)')
     # (host simulator: one case at D = 1536 so that head_fwd_stream_kernel, which needs D % 1536 == 0, runs there too)
     D = 3072 if dev.type == 'cuda' else 1536 if (B, C) == (2500, 10) else 64
     g = torch.Generator().manual_seed(21)
