@@ -72,6 +72,35 @@ class FlatParams:
     def zero_grad(self):
         self.grad.zero_()
 
+    def _momentum_views(self):
+        """(parameter, view of `buf`) for every parameter of an optimiser group with momentum"""
+        for s in self.segments:
+            if s['group'] is None:
+                continue
+            g = self.model.optimizer.param_groups[s['group']]
+            if not float(g.get('momentum', 0.)):
+                continue
+            for p in g['params']:
+                if p.requires_grad:
+                    o = p.data.data_ptr() - self.flat.data_ptr()
+                    yield p, self.buf[o // 4:o // 4 + p.numel()].view(p.shape)
+
+    def export_momentum(self):
+        """Make the torch optimiser's state show the fused step's momentum (views of `buf`), so that
+        `optimizer.state_dict()` -- what the reference checkpoints (model.py:237-241) -- is complete."""
+        for p, v in self._momentum_views():
+            self.model.optimizer.state[p]['momentum_buffer'] = v
+
+    def import_momentum(self, opt_state):
+        """inverse of export_momentum from a `torch.optim.SGD.state_dict()`; entries without a buffer are left at zero"""
+        order = [p for g in self.model.optimizer.param_groups for p in g['params']]
+        ids = [i for g in opt_state.get('param_groups', []) for i in g['params']]
+        by_param = {id(p): opt_state['state'].get(i) for p, i in zip(order, ids)}
+        for p, v in self._momentum_views():
+            st = by_param.get(id(p))
+            if st is not None and st.get('momentum_buffer') is not None:
+                v.copy_(st['momentum_buffer'])
+
     def clip_and_step(self, max_norm, grad_scale=1.0):
         """Fused clip_grad_norm_ + SGD.  Returns the device tensor [total_norm, clip_coef]."""
         # ||grad_scale * g|| <= max_norm  <=>  ||g|| <= max_norm / grad_scale
@@ -186,7 +215,10 @@ class TrainStep:
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
         self.flat = FlatParams(model)
+        model._ibinn_flat = self.flat          # model.save / model.load checkpoint the momentum through it
         dev = model.mu.device
+        if self.world > 1:
+            self._broadcast_replicas()
         self.wprep = WeightPrep(model) if dev.type == 'cuda' else None      # after FlatParams: the filters have their final addresses
         self.masks = MaskPool(model, batch_size)
         self.x = torch.zeros((batch_size,) + tuple(model.dims), dtype=torch.float32, device=dev)
@@ -202,6 +234,40 @@ class TrainStep:
         self._g1 = self._g2 = None
         self.out = None
         self.launches = None
+
+    def _broadcast_replicas(self):
+        """Every rank starts from rank 0's model: trainable tensors (one flat buffer), the frozen soft-permutation
+        matrices (drawn from numpy's global RNG, reference all_in_one_block.py:43) and the BatchNorm buffers."""
+        src = dist.get_global_rank(self.pg, 0) if self.pg is not None else 0
+        dist.broadcast(self.flat.flat, src=src, group=self.pg)
+        with torch.no_grad():
+            for p in self.model.parameters():
+                if not p.requires_grad:
+                    dist.broadcast(p.data, src=src, group=self.pg)
+            for name, b in self.model.named_buffers():
+                if 'tmp_var' not in name and b is not None and b.numel():
+                    dist.broadcast(b, src=src, group=self.pg)
+
+    def _snapshot(self):
+        """everything a training step mutates besides the static input buffers"""
+        bufs = [b for n, b in self.model.named_buffers() if 'tmp_var' not in n and b is not None]
+        snap = dict(flat=self.flat.flat.clone(), buf=self.flat.buf.clone(), bufs=[(b, b.clone()) for b in bufs],
+                    cpu_rng=torch.get_rng_state())
+        if self.flat.flat.is_cuda:
+            snap['cuda_rng'] = torch.cuda.get_rng_state(self.flat.flat.device)
+        return snap
+
+    def _restore(self, snap):
+        with torch.no_grad():
+            self.flat.flat.copy_(snap['flat'])
+            self.flat.buf.copy_(snap['buf'])
+            for b, v in snap['bufs']:
+                b.copy_(v)
+        torch.set_rng_state(snap['cpu_rng'])
+        if 'cuda_rng' in snap:
+            torch.cuda.set_rng_state(snap['cuda_rng'], self.flat.flat.device)
+        if self.wprep is not None:
+            self.wprep.invalidate()
 
     # -- pieces ---------------------------------------------------------------------------------
     def _fwd_bwd(self):
@@ -258,8 +324,11 @@ class TrainStep:
 
     def capture(self, warmup=3):
         """Warm up eagerly (lazy inits, allocator), then capture.  The all-reduce stays outside the
-        graphs (two graphs around one NCCL call) so that capture never depends on the NCCL build."""
+        graphs (two graphs around one NCCL call) so that capture never depends on the NCCL build.
+        The warm-up steps are real optimisation steps on whatever batch is loaded, so parameters, momentum, BatchNorm
+        buffers and the RNG state are put back afterwards: capturing has no training side effect."""
         L = _lib.lib()
+        snap = self._snapshot()
         # Warm up and capture on ONE side stream: autograd remembers the stream on which a parameter's
         # gradient accumulator was created and syncs it with the backward's stream, which is illegal
         # across a capture boundary.
@@ -272,6 +341,8 @@ class TrainStep:
             for _ in range(warmup):
                 self._eager()
         torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._restore(snap)
         torch.cuda.synchronize()
         n0 = L.ibinn_launch_count()
         self._g1 = torch.cuda.CUDAGraph()

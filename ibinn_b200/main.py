@@ -23,7 +23,7 @@ def main(argv=None):
         args.write(f)
     if mode == 'train':
         from . import train
-        train.train(args)
+        train.train(args, synthetic=os.environ.get('IBINN_SYNTHETIC_DATA', '0') == '1')   # opt-in only; otherwise the reference's data.py
     elif mode == 'test':
         raise SystemExit('`test` runs the reference\'s evaluation/ package (plots, OoD, calibration), which is outside the '
                          'ibinn_b200 hot path: point it at ibinn_b200.model.GenerativeClassifier (see INTEGRATION.md)')

@@ -91,8 +91,9 @@ class GenerativeClassifier(nn.Module):
     def _update_empirical_mu(self, z, y):
         mu = torch.mm(z.t().detach(), y.round())
         mu = mu / torch.sum(y, dim=0, keepdim=True)
-        mu = mu.t().view(1, self.n_classes, -1)
-        self.mu.data = (0.005 * mu + 0.995 * self.mu.data).data
+        # In place (the reference rebinds `.data`, model.py:115-120): engine.FlatParams keeps mu as a view of its flat buffer
+        # and a captured CUDA graph reads that address, so the tensor must never move.
+        self.mu.data.mul_(0.995).add_(mu.t().contiguous().view_as(self.mu), alpha=0.005)
 
     def mu_pairwise_dist(self):
         m = self.mu.squeeze()
@@ -142,7 +143,7 @@ class GenerativeClassifier(nn.Module):
                 mu += mu_batch.t().view(1, self.n_classes, -1)
                 counter += 1
             mu /= counter
-        self.mu.data = mu.data
+        self.mu.data.copy_(mu)          # in place: see _update_empirical_mu
 
     def sample(self, y, temperature=1., temperature_class=1.):
         z = temperature * torch.randn(y.shape[0], self.ndim_tot, device=self.mu.device)
@@ -150,11 +151,26 @@ class GenerativeClassifier(nn.Module):
         return self.inn(z + mu, rev=True)
 
     def save(self, fname):
+        """reference model.py:237-241.  The fused step keeps the SGD momentum in engine.FlatParams.buf rather than in
+        the torch optimiser; `_ibinn_flat` (set by engine.TrainStep) exposes it as the optimiser's `momentum_buffer`
+        entries first, so the `opt` entry is what torch.optim.SGD would have written."""
+        flat = getattr(self, '_ibinn_flat', None)
+        if flat is not None:
+            flat.export_momentum()
         torch.save({'inn': self.inn.state_dict(), 'mu': self.mu, 'phi': self.phi, 'opt': self.optimizer.state_dict()}, fname)
 
     def load(self, fname):
+        """reference model.py:243-248: strict on everything but the `tmp_var` scratch buffers."""
         data = torch.load(fname, weights_only=False)
-        data['inn'] = {k: v for k, v in data['inn'].items() if 'tmp_var' not in k}
-        self.inn.load_state_dict(data['inn'], strict=False)
+        inn_state = {k: v for k, v in data['inn'].items() if 'tmp_var' not in k}
+        own = {k for k in self.inn.state_dict() if 'tmp_var' not in k}
+        missing, unexpected = sorted(own - set(inn_state)), sorted(set(inn_state) - own)
+        if missing or unexpected:
+            raise RuntimeError('Error(s) in loading state_dict for %s: missing keys %s, unexpected keys %s'
+                               % (type(self.inn).__name__, missing[:8], unexpected[:8]))
+        self.inn.load_state_dict(inn_state, strict=False)          # only the tmp_var buffers may be absent
         self.mu.data.copy_(data['mu'].data)
         self.phi.data.copy_(data['phi'].data)
+        flat = getattr(self, '_ibinn_flat', None)
+        if flat is not None and data.get('opt') is not None:
+            flat.import_momentum(data['opt'])

@@ -43,7 +43,7 @@ class SyntheticDataset:
         return y
 
 
-def train(args, dataset=None, device='cuda', use_graph=True, max_iterations=None):
+def train(args, dataset=None, device='cuda', use_graph=True, max_iterations=None, synthetic=False):
     t, c = args['training'], args['checkpoints']
     N_epochs = eval(t['n_epochs'])
     label_smoothing = eval(args['data']['label_smoothing'])
@@ -59,11 +59,17 @@ def train(args, dataset=None, device='cuda', use_graph=True, max_iterations=None
     dev = torch.device(device)
     inn = GenerativeClassifier(args).to(dev)
     if dataset is None:
-        try:
-            import data                      # the reference's data.py, if the caller has it on sys.path
-            dataset = data.Dataset(args)
-        except ImportError:
+        if synthetic:
+            print('ibinn_b200.train: training on SYNTHETIC N(0,1) images with random labels (throughput / smoke run only)', flush=True)
             dataset = SyntheticDataset(args, device=device)
+        else:
+            # the reference's own loader (reference data.py:93-191; outside the hot path, not restated here) must be importable
+            try:
+                import data
+                dataset = data.Dataset(args)
+            except (ImportError, AttributeError) as e:
+                raise RuntimeError('ibinn_b200.train: no dataset given and the reference data.py is not importable (%s); put the '
+                                   'reference on sys.path, pass dataset=..., or opt in to noise with synthetic=True' % e) from e
     if resume:
         inn.load(resume)
     step = TrainStep(inn, batch_size=eval(args['data']['batch_size']), use_graph=use_graph)

@@ -103,13 +103,13 @@ def _ddp_worker(rank, world, port, lib_path, tmp):
     _lib._use_library_for_tests(lib_path, True)
     dist.init_process_group('gloo', rank=rank, world_size=world)
     dev = torch.device('cpu')
-    m = _model(dev)
+    m = _model(dev, seed=rank)          # replicas are seeded differently on purpose: TrainStep broadcasts rank 0's model
     step = TrainStep(m, batch_size=3, beta=1.0, clip=8., use_graph=False)
     gen = torch.Generator().manual_seed(5)
     for it in range(2):
         xs, ys = _batch(3 * world, 10, gen)
         step.step(xs[rank * 3:(rank + 1) * 3], ys[rank * 3:(rank + 1) * 3])
-    torch.save({k: v for k, v in m.state_dict().items() if 'running' not in k and 'num_batches' not in k}, os.path.join(tmp, 'r%d.pt' % rank))
+    torch.save({k: v for k, v in m.state_dict().items() if 'running' not in k and 'num_batches' not in k and 'tmp_var' not in k}, os.path.join(tmp, 'r%d.pt' % rank))
     dist.destroy_process_group()
 
 
@@ -172,11 +172,7 @@ def test_train_step_schedules_agree():
             step = TrainStep(m, batch_size=8, beta=1.0, clip=8., use_graph=graph)
             if graph:
                 step.load(*[t.to(dev) for t in batches[0]])
-                snap = copy.deepcopy({k: v.clone() for k, v in m.state_dict().items()})
-                mom = step.flat.buf.clone()
-                step.capture()                         # warm-up steps move the parameters: restore them
-                m.load_state_dict(snap)
-                step.flat.buf.copy_(mom)
+                step.capture()                         # side-effect free (test_capture_has_no_training_side_effects)
             for x, y in batches:
                 step.step(x.to(dev), y.to(dev))
             torch.cuda.synchronize()
@@ -192,3 +188,94 @@ def test_train_step_schedules_agree():
         assert float((flat(other) - flat(results[0])).norm() / flat(results[0]).norm()) < 1e-4
         for k in results[0]:
             assert rel(other[k], results[0][k].double()) < 2e-2, k
+
+
+EMP = {'model': dict(SMALL['model']), 'training': {'empirical_mu': 'True'}}
+
+
+def test_empirical_mu_updates_in_place(dev):
+    """`empirical_mu = True` (reference experiments_configs/cifar10/misc/empiric_mu.ini, model.py:115-120): the running
+    class means are blended into `mu` IN PLACE, so mu stays a view of the flat parameter buffer and the step runs."""
+    m = _model(dev, overrides=EMP)
+    assert m.mu_empirical
+    step = TrainStep(m, batch_size=4, beta=1.0, use_graph=False)
+    gen = torch.Generator().manual_seed(3)
+    ptr0 = m.mu.data_ptr()
+    mu0 = m.mu.detach().clone()
+    x, y = _batch(4, 10, gen)
+    z = m.inn(x.to(dev)).detach()
+    emp = (z.t().double() @ y.to(dev).round().double() / y.to(dev).double().sum(0, keepdim=True)).t().reshape(1, 10, -1)
+    out = step.step(x.to(dev), y.to(dev))
+    assert m.mu.data_ptr() == ptr0 and m.mu.is_contiguous()
+    assert np.isfinite(float(out['L_x_tr']))
+    # the blend happened before the optimiser touched mu: undo the SGD update (mu group: momentum 0, weight decay 0)
+    o = (m.mu.data_ptr() - step.flat.flat.data_ptr()) // 4
+    lr_mu = m.optimizer.param_groups[1]['lr']
+    coef = min(1., 8. / (float(out['grad_norm']) + 1e-6))
+    blended = m.mu.detach().double() + lr_mu * coef * step.flat.grad[o:o + m.mu.numel()].view_as(m.mu).double()
+    assert rel(blended, 0.995 * mu0.double() + 0.005 * emp) < 1e-5
+
+
+@pytest.mark.gpu
+def test_empirical_mu_under_cuda_graph(cuda_dev):
+    dev = cuda_dev
+    gen = torch.Generator().manual_seed(3)
+    batches = [_batch(4, 10, gen) for _ in range(3)]
+    res = []
+    for graph in (False, True):
+        m = _model(dev, overrides=EMP)
+        m.eval()
+        step = TrainStep(m, batch_size=4, beta=1.0, use_graph=graph)
+        for x, y in batches:
+            step.step(x.to(dev), y.to(dev))
+        torch.cuda.synchronize()
+        res.append(m.mu.detach().clone())
+    assert rel(res[1], res[0]) < 1e-4
+
+
+@pytest.mark.gpu
+def test_capture_has_no_training_side_effects(cuda_dev):
+    """TrainStep.capture() warms up with real steps; parameters, momentum, BatchNorm buffers and the RNG state must come
+    back, so the first replayed batch gets exactly ONE update (the reference trajectory)."""
+    dev = cuda_dev
+    m = _model(dev, overrides={'model': {'n_coupling_blocks_conv': '[1, 1, 1]', 'fc_width': '8'}})     # dropout live
+    step = TrainStep(m, batch_size=4, beta=1.0, use_graph=True)
+    gen = torch.Generator().manual_seed(4)
+    x, y = _batch(4, 10, gen)
+    step.load(x.to(dev), y.to(dev))
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    buf0, rng0 = step.flat.buf.clone(), torch.cuda.get_rng_state(dev)
+    step.capture()
+    torch.cuda.synchronize()
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, sd0[k]), k
+    assert torch.equal(step.flat.buf, buf0)
+    assert torch.equal(torch.cuda.get_rng_state(dev), rng0)
+    step.run()
+    torch.cuda.synchronize()
+    nbt = [v for k, v in m.state_dict().items() if k.endswith('num_batches_tracked')]
+    assert all(int(v) == 1 for v in nbt)
+
+
+def test_checkpoint_carries_momentum_and_load_is_strict(dev, tmp_path):
+    m = _model(dev)
+    step = TrainStep(m, batch_size=2, use_graph=False)
+    gen = torch.Generator().manual_seed(6)
+    x, y = _batch(2, 10, gen)
+    step.step(x.to(dev), y.to(dev))
+    f = str(tmp_path / 'ck.pt')
+    m.save(f)
+    ck = torch.load(f, weights_only=False)
+    st = ck['opt']['state']
+    n_inn = len(m.optimizer.param_groups[0]['params'])
+    assert len(st) >= n_inn and all(st[i]['momentum_buffer'] is not None for i in range(n_inn))
+    p0 = m.optimizer.param_groups[0]['params'][0]
+    assert rel(st[0]['momentum_buffer'], step.flat.buf[:p0.numel()].view(p0.shape)) == 0.
+    m2 = _model(dev, seed=1)
+    step2 = TrainStep(m2, batch_size=2, use_graph=False)
+    m2.load(f)
+    assert torch.equal(step2.flat.buf.cpu(), step.flat.buf.cpu()) and torch.equal(step2.flat.flat.cpu(), step.flat.flat.cpu())
+    # a checkpoint of another architecture is refused (reference model.py:246 loads strictly)
+    other = _model(dev, overrides={'model': dict(SMALL['model'], n_coupling_blocks_conv='[1, 2, 1]')})
+    with pytest.raises(RuntimeError):
+        other.load(f)

@@ -32,3 +32,12 @@ def test_train_driver_and_checkpoint(dev, tmp_path):
     with torch.no_grad():
         a, b = inn(x, ds.val_y, loss_mean=False), m2(x, ds.val_y, loss_mean=False)
     assert torch.equal(a['L_x_tr'], b['L_x_tr'])
+
+
+def test_train_refuses_to_fall_back_to_noise(tmp_path):
+    """no dataset and no reference data.py on sys.path: raise instead of silently training on N(0,1) noise"""
+    import pytest
+    args = config.make_args(overrides=OV)
+    args['checkpoints']['output_dir'] = str(tmp_path)
+    with pytest.raises(RuntimeError, match='synthetic=True'):
+        train.train(args, dataset=None, device='cpu', use_graph=False)
