@@ -175,9 +175,12 @@ def depth_to_space(x):
 class _State:
     """Per-call scratch: BN mode, dropout masks, running-stat updates, activations."""
 
-    def __init__(self, train, masks, collect):
+    def __init__(self, train, masks, collect, relu_masks=None):
         self.train = train
         self.masks = masks or {}
+        # optional {'<subnet key>.relu<i>': 0/1 tensor}: the ReLU decisions are taken from the caller instead of from the
+        # sign of the pre-activation (flip-free gradient parity, tests/test_blocks.py::test_*_injected_relu_masks)
+        self.relu_masks = relu_masks
         self.new_stats: Dict[str, torch.Tensor] = {}
         self.collect = collect
         self.records: Dict[str, torch.Tensor] = {}
@@ -207,16 +210,23 @@ def _dropout(h, key, p, st: _State):
     return h * m.to(h.dtype).view(*m.shape, *([1] * (h.dim() - m.dim())))
 
 
+def _relu(h, key, st: _State):
+    m = st.relu_masks.get(key) if st.relu_masks is not None else None
+    if m is None:
+        return F.relu(h)
+    return h * m.to(h.dtype)
+
+
 def conv_subnet(h, P, key, relu_first, strided, st: _State):
     """basic_residual_block / strided_residual_block, inn_architecture.py:68-110."""
     j = 0
     if relu_first:
-        h = F.relu(h)
+        h = _relu(h, key + '.relu0', st)
         j = 1
     h = F.conv2d(h, P['%s.%d.weight' % (key, j)], padding=1)
-    h = F.relu(_bn(h, P, '%s.%d' % (key, j + 1), st))
+    h = _relu(_bn(h, P, '%s.%d' % (key, j + 1), st), key + '.relu1', st)
     h = F.conv2d(h, P['%s.%d.weight' % (key, j + 3)], padding=1, stride=2 if strided else 1)
-    h = F.relu(_bn(h, P, '%s.%d' % (key, j + 4), st))
+    h = _relu(_bn(h, P, '%s.%d' % (key, j + 4), st), key + '.relu2', st)
     if strided:
         last = j + 6
     else:
@@ -227,7 +237,7 @@ def conv_subnet(h, P, key, relu_first, strided, st: _State):
 
 def fc_subnet(h, P, key, st: _State):
     """fc_constr, inn_architecture.py:112-120."""
-    h = F.relu(F.linear(h, P[key + '.0.weight'], P[key + '.0.bias']))
+    h = _relu(F.linear(h, P[key + '.0.weight'], P[key + '.0.bias']), key + '.relu1', st)
     h = _dropout(h, key + '.2', None, st)
     return F.linear(h, P[key + '.3.weight'], P[key + '.3.bias'])
 

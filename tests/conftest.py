@@ -38,6 +38,10 @@ def dev(request):
 @pytest.fixture
 def cuda_dev():
     from ibinn_b200 import _lib
+    if os.environ.get('IBINN_TEST_EMU_AS_CUDA') == '1' and not torch.cuda.is_available():
+        # dry run of the GPU-only tests' host logic on the simulator (developer aid; shrink sizes with IBINN_TEST_BENCH_B)
+        _lib._use_library_for_tests(_emu_library(), True)
+        return torch.device('cpu')
     if not torch.cuda.is_available():
         pytest.skip('no GPU')
     _lib._use_library_for_tests(None, False)

@@ -12,6 +12,7 @@ import torch
 from util import O, randomize_, rel, state_of
 
 from ibinn_b200 import functions as Fn
+from ibinn_b200 import ops
 from ibinn_b200.all_in_one_block import AIO_Block
 from ibinn_b200.dct_transform import DCTPooling2d
 from ibinn_b200.downsampling_coupling_block import DownsampleCouplingBlock
@@ -57,14 +58,14 @@ def run_node(blk, spec, x, dev, train, masks_ours=None, masks_oracle=None, check
                 raise
 
 
-def _run_node_once(blk, spec, x, dev, train, masks_ours=None, masks_oracle=None, check_inverse=True, seed=0):
+def _run_node_once(blk, spec, x, dev, train, masks_ours=None, masks_oracle=None, check_inverse=True, seed=0, relu_masks=None):
     g = torch.Generator().manual_seed(100 + seed)
     P = state_of(blk, spec.key + '.')
     keys = [k for k in O.trainable_keys(P)]
     for k in keys:
         P[k].requires_grad_()
     x64 = x.double().requires_grad_()
-    st = O._State(train, masks_oracle, False)
+    st = O._State(train, masks_oracle, False, relu_masks)
     out64, jac64 = O.node_forward(x64, P, spec, st)
     gout = torch.randn(out64.shape, generator=g)
     gjac = torch.randn(x.shape[0], generator=g) * 0.01
@@ -115,6 +116,54 @@ def _run_node_once(blk, spec, x, dev, train, masks_ours=None, masks_oracle=None,
             assert rel(-jr, jf) < 1e-5
 
 
+def _bn_pre(h, r):
+    """BatchNorm output exactly as the kernels form it while staging: fma(h, gamma*invstd, beta - mean*gamma*invstd)"""
+    inv = torch.rsqrt(r.scale + r.eps) if r.is_var else r.scale
+    A = r.gamma * inv
+    return torch.addcmul((r.beta - r.mean * A).view(1, -1, 1, 1), h, A.view(1, -1, 1, 1))
+
+
+def subnet_relu_masks(net, xin, key, train):
+    """The ReLU decisions OUR kernels take in conv subnet `net` on input `xin`, as {oracle key: 0/1 fp64 tensor}."""
+    import copy
+    net = copy.deepcopy(net)                  # the probe must not advance the BatchNorm running statistics
+    net.train(train)
+    with torch.no_grad():
+        _, (h1, h2, r1, r2, _, _) = Fn.conv_subnet_forward(net, xin, train)
+        m = {key + '.relu1': _bn_pre(h1, r1) > 0, key + '.relu2': _bn_pre(h2, r2) > 0}
+        if net.relu_first:
+            m[key + '.relu0'] = xin > 0
+    return {k: v.double().cpu() for k, v in m.items()}
+
+
+def run_node_flip_free(blk, spec, x, dev, train, seed=0):
+    """run_node WITHOUT the retry: the oracle takes its ReLU decisions from our kernels' own pre-activations, so both sides
+    differentiate the same piecewise-linear branch and an fp32 rounding difference cannot flip a unit.  One draw, strict
+    tolerances: a defect that bites one draw in three cannot hide here."""
+    import copy
+    blk = copy.deepcopy(blk).to(dev)
+    blk.train(train)
+    xd = x.to(dev)
+    masks = {}
+    if spec.kind == 'aio':
+        masks.update(subnet_relu_masks(blk.s, xd[:, :blk.split_len1], spec.key + '.s', train))
+    elif spec.kind == 'down':
+        c1 = blk.split_len1
+        masks.update(subnet_relu_masks(blk.s_hi, xd[:, :c1], spec.key + '.s_hi', train))
+        with torch.no_grad():
+            out = copy.deepcopy(blk)([xd])[0]
+        masks.update(subnet_relu_masks(blk.s_lo, out[:, 4 * c1:], spec.key + '.s_lo', train))
+    elif spec.kind == 'glow':
+        l1 = blk.split_len1
+        with torch.no_grad():
+            out = copy.deepcopy(blk)([xd])[0]
+            h2 = ops.linear_forward(xd[:, l1:], blk.s2.lin1.weight, blk.s2.lin1.bias)
+            h1 = ops.linear_forward(out[:, :l1], blk.s1.lin1.weight, blk.s1.lin1.bias)
+        masks[spec.key + '.s1.relu1'] = (h1 > 0).double().cpu()
+        masks[spec.key + '.s2.relu1'] = (h2 > 0).double().cpu()
+    _run_node_once(blk.cpu(), spec, x, dev, train, check_inverse=False, seed=seed, relu_masks=masks)
+
+
 AIO_CASES = [  # C, H, width, relu_first, B
     (3, 32, 16, False, 3), (3, 32, 16, True, 2), (12, 16, 32, True, 3), (48, 8, 64, True, 2),
     (4, 14, 32, True, 2), (16, 7, 64, True, 3), (8, 32, 16, True, 2),
@@ -133,6 +182,38 @@ def test_aio_block(dev, C, H, width, relu_first, B, train):
     spec = O.NodeSpec('aio', 1, 'aio', (C, H, H), (C, H, H), dict(width=width, dropout=0., relu_first=relu_first, clamp=0.7))
     x = torch.randn(B, C, H, H, generator=g)
     run_node(blk, spec, x, dev, train)
+
+
+@pytest.mark.parametrize('C,H,width,relu_first,B', [(3, 32, 16, True, 2), (12, 16, 32, True, 3), (48, 8, 64, True, 2), (16, 7, 64, True, 3)])
+def test_aio_block_injected_relu_masks(dev, C, H, width, relu_first, B):
+    torch.manual_seed(C * 100 + H)
+    np.random.seed(C + H)
+    g = torch.Generator().manual_seed(7)
+    blk = AIO_Block([(C, H, H)], subnet_constructor=partial(conv_constr, width, 0., relu_first, False), clamp=0.7,
+                    act_norm=0.75, permute_soft=True)
+    randomize_(blk, g)
+    spec = O.NodeSpec('aio', 1, 'aio', (C, H, H), (C, H, H), dict(width=width, dropout=0., relu_first=relu_first, clamp=0.7))
+    run_node_flip_free(blk, spec, torch.randn(B, C, H, H, generator=g), dev, True)
+
+
+@pytest.mark.parametrize('C,H,width,B', [(3, 32, 32, 2), (12, 16, 64, 2)])
+def test_down_block_injected_relu_masks(dev, C, H, width, B):
+    torch.manual_seed(C * 10 + H)
+    g = torch.Generator().manual_seed(9)
+    blk = DownsampleCouplingBlock([(C, H, H)], subnet_constructor_strided=partial(conv_constr, width, 0., False, True),
+                                  subnet_constructor_low_res=partial(conv_constr, width, 0., False, False), clamp=0.7)
+    randomize_(blk, g)
+    spec = O.NodeSpec('down', 1, 'down', (C, H, H), (4 * C, H // 2, H // 2), dict(width=width, dropout=0., clamp=0.7))
+    run_node_flip_free(blk, spec, torch.randn(B, C, H, H, generator=g), dev, True)
+
+
+def test_glow_block_injected_relu_masks(dev):
+    torch.manual_seed(3072)
+    g = torch.Generator().manual_seed(10)
+    blk = GLOWCouplingBlock([(3072,)], subnet_constructor=partial(fc_constr, 16, 0.), clamp=2.0)
+    randomize_(blk, g)
+    spec = O.NodeSpec('glow', 1, 'glow', (3072,), (3072,), dict(clamp=2.0, width=16, dropout=0.))
+    run_node_flip_free(blk, spec, torch.randn(3, 3072, generator=g), dev, True)
 
 
 def test_aio_block_dropout_mask(dev):
