@@ -1,15 +1,19 @@
 #!/usr/bin/env python
-"""bench.py -- IB-INN hot-path throughput on B200 (contract: see the task statement / DESIGN.md).
+"""bench.py -- IB-INN hot-path throughput on B200 (contract: see the task statement / DESIGN.md section 4).
 
-  python bench.py --gpus N --steps K --warmup W            # ibinn_b200 (CUDA, one rank per GPU under torchrun)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU (oracle port)
+  python bench.py --gpus N --steps K --warmup W                  # ibinn_b200 (CUDA, one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...        # the reference's own files on the host CPU cores
+  python bench.py --workload {cifar10_train|cifar100_train|mnist_fwd|cifar10_infer|cifar10_beta_sweep}
 
-A step = one CIFAR-10 IB-INN (beta = 1) training step (forward, IB loss, backward, clip 8.0, SGD) on a
-synthetic batch of 128 images per GPU (BASELINE.json configs[1]).  Prints ONE JSON line on rank 0.
+Default workload = BASELINE.json configs[1]: one CIFAR-10 IB-INN (beta = 1) training step (forward, IB loss, backward,
+clip 8.0, SGD) on a synthetic batch of 128 images per GPU.  The other workloads are configs[2] (CIFAR-100, 100-class head),
+configs[0] (MNIST forward + IB loss, batch 64), configs[3] (eval-mode scoring at batch 2048) and configs[4] (the beta ramp:
+independent replicas, one process per GPU, no collective).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -18,9 +22,28 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = 'CIFAR-10 IB-INN beta_ramp beta_1.0000 training step (fwd + IB loss + bwd + clip 8.0 + SGD), fp32, synthetic 32x32x3'
-PER_GPU_BATCH = 128
-TRAIN_FLOP_PER_IMG = 1.175e9      # BASELINE.md section 2 (fwd + dgrad + wgrad, 2 x MAC)
+BETA_RAMP = [0.6002, 0.8435, 1.0000, 1.1855, 1.6662, 2.3419, 3.2915, 4.6261, 6.5019]   # reference gen_beta_ramp.sh:11-19
+
+# name -> description, ini overrides, per-GPU batch, kind, algorithmic FLOPs per image (2 x MAC; BASELINE.md section 2 / SURVEY 8d)
+WORKLOADS = {
+    'cifar10_train': dict(
+        text='CIFAR-10 IB-INN beta_ramp beta_1.0000 training step (fwd + IB loss + bwd + clip 8.0 + SGD), fp32, synthetic 32x32x3',
+        overrides={}, batch=128, kind='train', flop_per_img=1.175e9, classes=10),
+    'cifar100_train': dict(
+        text='CIFAR-100 IB-INN (100-class GMM head) training step (fwd + IB loss + bwd + clip 8.0 + SGD), fp32, synthetic 32x32x3, batch-sharded',
+        overrides={'data': {'dataset': 'CIFAR100'}}, batch=128, kind='train', flop_per_img=1.175e9 + 3 * 2 * 3072 * 100, classes=100),
+    'mnist_fwd': dict(
+        text='MNIST IB-INN (experiments_configs/mnist, beta=1) forward + IB loss, batch 64, fp32, synthetic 28x28',
+        overrides={'data': {'dataset': 'MNIST', 'label_smoothing': '0.01'}, 'model': {'act_norm': '0.80'}}, batch=64, kind='fwd',
+        flop_per_img=0.2064e9, classes=10),
+    'cifar10_infer': dict(
+        text='CIFAR-10 IB-INN inference log-likelihood / OoD scoring (eval mode, no backward), fp32, synthetic 32x32x3, batch 2048',
+        overrides={}, batch=2048, kind='infer', flop_per_img=0.3916e9, classes=10),
+    'cifar10_beta_sweep': dict(
+        text='CIFAR-10 beta sweep (9 betas 0.6-6.5 of beta_ramp) independent training replicas, fp32, synthetic 32x32x3, batch 128 each',
+        overrides={}, batch=128, kind='sweep', flop_per_img=1.175e9, classes=10),
+}
+METRIC = {'train': 'train_images_per_sec', 'sweep': 'train_images_per_sec', 'fwd': 'forward_images_per_sec', 'infer': 'inference_images_per_sec'}
 
 
 def peaks():
@@ -30,6 +53,38 @@ def peaks():
                     source='measured')
     except Exception:
         return dict(hbm=6650., bf16=1590., bf16_sustained=1400., source='fallback')
+
+
+def measure_tf32_peak(torch, dev, seconds=1.0):
+    """Dense TF32 tensor throughput of this GPU: cuBLAS `torch.matmul` 8192^3 with TF32 allowed (2 N^3 FLOP), best of 10 (burst)
+    and back to back for `seconds` (sustained).  MEASURED_PEAKS.json only records bf16."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a, b = torch.randn(n, n, device=dev), torch.randn(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(5, int(seconds * 1e3 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        sustained = e0.elapsed_time(e1) / reps
+        del a, b
+        return dict(burst=2. * n ** 3 / (best * 1e-3) / 1e12, sustained=2. * n ** 3 / (sustained * 1e-3) / 1e12)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
 
 
 class ClockSampler:
@@ -66,20 +121,90 @@ class ClockSampler:
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons, 'samples': len(sm)}
 
 
-def cpu_reference(steps, warmup, budget_s=None):
-    """The reference's training step restated by the oracle, fp32, all host threads."""
+def config_of(wname, batch, world):
+    """identical for both arms (the driver compares the two dicts)"""
+    w = WORKLOADS[wname]
+    n_cfg = len(BETA_RAMP) if w['kind'] == 'sweep' else 1
+    return {'workload': w['text'], 'per_gpu_batch': batch, 'global_batch': batch * world,
+            'parallelism': ('replicas%d' if w['kind'] == 'sweep' else 'dp%d') % world, 'configs': n_cfg}
+
+
+# --------------------------------------------------------------------------------------------- reference arm (host CPU)
+
+def reference_run(wname, batch, device, steps, warmup, budget_s=None):
+    """the reference's own files (baseline/_ref, see baseline/ref_arm.py) on `device`; falls back to the oracle port when the
+    files did not travel.  Returns dict(value img/s, sec_per_step, steps, cores, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, 'baseline'))
+    import ref_arm
+    w = WORKLOADS[wname]
+    if ref_arm.available() or ref_arm.install():
+        r = ref_arm.RefRunner(wname, device, batch=batch)
+        sec, n = r.time(steps, warmup, budget_s)
+        return dict(value=batch / sec, sec_per_step=sec, steps=n, cores=r.threads, kind='reference')
+    if device != 'cpu':
+        raise RuntimeError('baseline/_ref is missing: no stock-PyTorch GPU baseline')
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     import cpu_train_step as C
     import ibinn_oracle as O
-    tr = C.CpuTrainer(O.Cfg(), PER_GPU_BATCH, beta=1.0)
+    from ibinn_b200 import config
+    cfg = O.cfg_from_args(config.make_args(overrides=w['overrides']))
+    tr = C.CpuTrainer(cfg, batch, beta=1.0)
+    fn = 'step' if w['kind'] in ('train', 'sweep') else 'forward_only'
     if budget_s is not None:
         t0 = time.perf_counter()
-        tr.step()
+        getattr(tr, fn)()
         first = time.perf_counter() - t0
-        steps = max(2, min(steps, int(budget_s / max(first, 1e-3))))
-        warmup = 0
-    sec = C.time_steps(tr, steps, warmup)
-    return dict(value=PER_GPU_BATCH / sec, sec_per_step=sec, cores=tr.threads, steps=steps)
+        steps, warmup = max(2, min(steps, int(budget_s / max(first, 1e-3)))), 0
+    sec = C.time_steps(tr, steps, warmup, fn)
+    return dict(value=batch / sec, sec_per_step=sec, steps=steps, cores=tr.threads, kind='port')
+
+
+def reference_main(a, rank, world, warmup):
+    if rank != 0:
+        return
+    w = WORKLOADS[a.workload]
+    batch = a.batch or w['batch']
+    dev = a.ref_device
+    # every step is one full batch of the workload; the number of steps is bounded so the run ends within a few minutes
+    r = reference_run(a.workload, batch, dev, a.steps, warmup, budget_s=a.budget if a.budget > 0 else None)
+    sample = '%d full %s of batch %d on %s' % (r['steps'], 'training steps' if w['kind'] in ('train', 'sweep') else 'forward passes', batch,
+                                               'the host CPU cores' if dev == 'cpu' else 'cuda:0 with stock PyTorch (cuDNN / cuBLAS, TF32 off)')
+    line = {'impl': 'reference', 'metric': METRIC[w['kind']], 'value': r['value'], 'unit': 'img/s', 'n_gpus': a.gpus,
+            'steps': r['steps'], 'warmup': warmup if a.budget <= 0 else min(warmup, 1), 'ms_per_step': r['sec_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic', 'config': config_of(a.workload, batch, world),
+            'device': dev,
+            'cpu_baseline': {'value': r['value'], 'unit': 'img/s', 'cores': r['cores'], 'kind': r['kind'], 'sample': sample},
+            'e2e': {'value': r['value'], 'unit': 'img/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'note': 'the unmodified reference files (baseline/_ref) through oracle/ref_shims; one process, rank 0 only' if r['kind'] == 'reference'
+                    else 'oracle port of the reference (baseline/_ref did not travel)'}
+    print(json.dumps(line), flush=True)
+
+
+def sub_reference(wname, batch, device, steps, warmup, budget):
+    """run the reference arm in a fresh process (its shims monkey-patch torch) and parse its JSON line"""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--workload', wname, '--batch', str(batch),
+           '--ref-device', device, '--steps', str(steps), '--warmup', str(warmup), '--budget', str(budget)]
+    env = dict(os.environ)
+    for k in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK'):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith('{'):
+                return json.loads(ln)
+        return {'error': (out.stderr or out.stdout)[-400:]}
+    except Exception as e:       # noqa: BLE001
+        return {'error': repr(e)}
+
+
+# --------------------------------------------------------------------------------------------- our arm
+
+def tag_flops(key, B):
+    m = re.search(r'\[k(\d) s(\d) (?:[NT] )?(\d+)->(\d+) @(\d+)x(\d+)', key)
+    if not m:
+        return 0.
+    k, _, ci, co, h, w = (int(v) for v in m.groups())
+    return 2. * B * h * w * ci * co * k * k
 
 
 def main():
@@ -88,8 +213,13 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cifar10_train', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=0, help='per-GPU batch (default: the workload\'s)')
+    ap.add_argument('--ref-device', default='cpu', choices=['cpu', 'cuda'], help='--impl reference: host cores (the arm) or stock PyTorch on the GPU')
+    ap.add_argument('--budget', type=float, default=0., help='--impl reference: clip the number of steps so the run ends within about this many seconds (0 = exactly --steps)')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-torch-baseline', action='store_true')
     ap.add_argument('--profile-out', default=None, help='write the per-kernel-class device-time table here (json)')
     a = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
@@ -98,18 +228,7 @@ def main():
     warmup = max(a.warmup, 3)
 
     if a.impl == 'reference':
-        if rank != 0:
-            return
-        r = cpu_reference(a.steps, warmup)
-        line = {'impl': 'reference', 'metric': 'train_images_per_sec', 'value': r['value'], 'unit': 'img/s', 'n_gpus': a.gpus,
-                'steps': a.steps, 'warmup': warmup, 'ms_per_step': r['sec_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
-                'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-                'config': {'workload': WORKLOAD, 'per_gpu_batch': PER_GPU_BATCH, 'global_batch': PER_GPU_BATCH,
-                           'note': 'reference algorithm (oracle port of the pure-PyTorch reference) on host CPU cores; one step = one full batch of 128'},
-                'cpu_baseline': {'value': r['value'], 'unit': 'img/s', 'cores': r['cores'], 'kind': 'port',
-                                 'sample': '%d full training steps of batch %d' % (a.steps, PER_GPU_BATCH)},
-                'e2e': {'value': r['value'], 'unit': 'img/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(line), flush=True)
+        reference_main(a, rank, world, warmup)
         return
 
     import numpy as np
@@ -119,45 +238,88 @@ def main():
     if not os.path.exists(os.path.join(ROOT, 'ibinn_b200', 'csrc', 'libibinn_b200.so')):
         ge.build()
     from ibinn_b200 import _lib, config
-    from ibinn_b200.engine import TrainStep
+    from ibinn_b200.engine import ScoreStep, TrainStep
     from ibinn_b200.model import GenerativeClassifier
     if not torch.cuda.is_available():
         raise SystemExit('bench.py (impl ours) needs a B200: there is no CPU path')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    W = WORKLOADS[a.workload]
+    kind = W['kind']
+    B = a.batch or W['batch']
+    C = W['classes']
     if world > 1:
         if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
             os.environ['NCCL_DEBUG'] = 'WARN'          # NCCL prints its version banner on stdout: keep stdout to the one JSON line
         dist.init_process_group('nccl', device_id=dev)
-    torch.manual_seed(0)
-    np.random.seed(0)
-    args = config.make_args()                      # the reference's default CIFAR-10 config, beta_IB = 1.0
-    model = GenerativeClassifier(args).to(dev)
-    model.train()
-    B = PER_GPU_BATCH
-    g = torch.Generator().manual_seed(1 + rank)
-    xh = torch.randn(B, 3, 32, 32, generator=g).pin_memory()
-    lab = torch.randint(0, 10, (B,), generator=g)
-    yh = (torch.zeros(B, 10).scatter_(1, lab.view(-1, 1), 1.) * 0.98 + 0.002).pin_memory()
-    step = TrainStep(model, batch_size=B, beta=1.0, use_graph=not a.no_graph)
-    step.load(xh, yh)
+    args = config.make_args(overrides=W['overrides'])     # the reference's default.ini (+ the workload's keys)
 
-    # ---- per-kernel-class device times: one eager step bracketed with CUDA events (after a warm step)
-    side, step.side_streams = step.side_streams, None      # serialised on one stream: every launch gets its own event pair
-    step._eager()
+    def make_model():
+        torch.manual_seed(0)
+        np.random.seed(0)
+        return GenerativeClassifier(args).to(dev)
+
+    g = torch.Generator().manual_seed(1 + rank)
+    model = make_model()
+    xh = torch.randn(B, *model.dims, generator=g).pin_memory()
+    lab = torch.randint(0, C, (B,), generator=g)
+    eps = float(args['data']['label_smoothing'])
+    yh = (torch.zeros(B, C).scatter_(1, lab.view(-1, 1), 1.) * (1 - eps) + eps / C).pin_memory()
+
+    # ---- the engines of this workload
+    if kind == 'train':
+        model.train()
+        engines = [TrainStep(model, batch_size=B, beta=1.0, use_graph=not a.no_graph)]
+    elif kind == 'sweep':
+        # replicas only: rank r trains the configurations r, r + world, ... of the ramp, each its own model; no data-path collective
+        mine = BETA_RAMP[rank::world]
+        engines = []
+        for i, beta in enumerate(mine):
+            m = model if i == 0 else make_model()
+            m.train()
+            engines.append(TrainStep(m, batch_size=B, beta=beta, use_graph=not a.no_graph, process_group=None, replicas_only=True))
+    elif kind == 'fwd':
+        model.train()
+        engines = [ScoreStep(model, batch_size=B, with_labels=True, loss_mean=True, train_mode=True, use_graph=not a.no_graph)]
+    else:
+        model.eval()
+        engines = [ScoreStep(model, batch_size=B, with_labels=False, loss_mean=False, train_mode=False, use_graph=not a.no_graph)]
+    for e in engines:
+        e.load(xh, yh) if kind != 'infer' else e.load(xh)
+    main_e = engines[0]
+    n_cfg_total = len(BETA_RAMP) if kind == 'sweep' else 1
+    imgs_per_step_global = B * (n_cfg_total if kind == 'sweep' else world)
+
+    # ---- per-kernel-class device times: one eager pass bracketed with CUDA events (after a warm pass)
+    def eager(e):
+        if isinstance(e, TrainStep):
+            e._eager()
+        else:
+            e._forward()
+    side = getattr(main_e, 'side_streams', None)
+    if side is not None:
+        main_e.side_streams = None                        # serialised on one stream: every launch gets its own event pair
+    eager(main_e)
     torch.cuda.synchronize()
     _lib.profile(True)
     n0 = _lib.lib().ibinn_launch_count()
-    step._eager()
+    eager(main_e)
     prof = _lib.profile(False)
-    step.side_streams = side
+    if side is not None:
+        main_e.side_streams = side
     table = prof.summary()
     eager_launches = int(_lib.lib().ibinn_launch_count() - n0)
     total_ms = sum(t for t, _ in table.values())
+    if kind in ('fwd', 'infer'):
+        main_e.refresh()
+
+    def run_all():
+        for e in engines:
+            e.run()
 
     # ---- timed region: K steps, inputs resident in HBM
     for _ in range(warmup):
-        step.run()
+        run_all()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -168,22 +330,39 @@ def main():
     torch.cuda.synchronize()
     e0.record()
     for _ in range(a.steps):
-        step.run()
+        run_all()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
-    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the logged scalars, every step
-    res_h = torch.zeros(4).pin_memory()
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the step's result, every step, through the public engine API
+    if kind in ('train', 'sweep'):
+        res_h = torch.zeros(len(engines), 4).pin_memory()
+        d2h = 16 * len(engines)
+    elif kind == 'fwd':
+        res_h = torch.zeros(1, 5).pin_memory()
+        d2h = 20
+    else:
+        res_h = torch.zeros(B, 1 + C).pin_memory()           # per-sample score L_x and the class log-likelihoods (ood.py:43-46)
+        d2h = B * (1 + C) * 4
+    h2d = int(xh.numel() * 4 + (yh.numel() * 4 if kind != 'infer' else 0)) * len(engines)
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     f0.record()
     for _ in range(a.steps):
-        out = step.step(xh, yh)
-        res_h.copy_(torch.stack([out['L_x_tr'], out['L_y_tr'], out['acc_tr'], out['grad_norm']]))   # synchronous read, like train.py:120-121
+        for i, e in enumerate(engines):
+            if kind in ('train', 'sweep'):
+                out = e.step(xh, yh)
+                res_h[i].copy_(torch.stack([out['L_x_tr'], out['L_y_tr'], out['acc_tr'], out['grad_norm']]))   # synchronous read, like train.py:120-121
+            elif kind == 'fwd':
+                out = e.step(xh, yh)
+                res_h[0].copy_(torch.stack([out['L_x_tr'], out['logits_tr'], out['L_cNLL_tr'], out['L_y_tr'], out['acc_tr']]))
+            else:
+                out = e.step(xh)
+                res_h.copy_(torch.cat([out['L_x_tr'].view(-1, 1), out['logits_tr']], 1))
     f1.record()
     torch.cuda.synchronize()
     ms_e2e = f0.elapsed_time(f1)
@@ -193,84 +372,91 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.tolist()
     loss_ok = bool(np.isfinite(res_h.numpy()).all())
+    launches = sum((e.launches if e.launches is not None else eager_launches) for e in engines)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     pk = peaks()
+    tf32 = measure_tf32_peak(torch, dev)
     ms_step = ms / a.steps
-    value = world * B / (ms_step * 1e-3)
+    value = imgs_per_step_global / (ms_step * 1e-3)
     # ---- roofline of the dominant kernel.  The profiler keys carry the launch shapes
     # ('ibinn_conv_forward[k3 s1 N 32->32 @16x16 pre2 epi1]'), so the algorithmic FLOPs (2 x MAC, counted once although the
-    # 3xTF32 arithmetic issues 2-3 MMAs per product) are exact per launch; the duration is the CUDA-event time of the same launches.
-    import re
-
-    def tag_flops(key):
-        m = re.search(r'\[k(\d) s(\d) (?:[NT] )?(\d+)->(\d+) @(\d+)x(\d+)', key)
-        if not m:
-            return 0.
-        k, _, ci, co, h, w = (int(v) for v in m.groups())
-        return 2. * B * h * w * ci * co * k * k
+    # 3xTF32 arithmetic issues 3 MMAs per product) are exact per launch; the duration is the CUDA-event time of the same launches.
     fam = {'conv_tc_kernel (subnet conv forward + dgrad)': lambda k: k.startswith('ibinn_conv_forward[') and ' s1 ' in k,
-           'wgrad_tc_kernel (subnet conv weight gradient)': lambda k: k.startswith('ibinn_conv_wgrad[') and ' s1 ' in k}
+           'wgrad_tc_kernel (subnet conv weight gradient)': lambda k: k.startswith('ibinn_conv_wgrad[') and ' s1 ' in k,
+           'block_fused_kernel (whole coupling block)': lambda k: k.startswith('ibinn_block_')}
     stats = {}
     for name, pred in fam.items():
         keys = [k for k in table if pred(k)]
-        stats[name] = dict(ms=sum(table[k][0] for k in keys), n=sum(table[k][1] for k in keys), flops=sum(tag_flops(k) * table[k][1] for k in keys))
+        if keys:
+            stats[name] = dict(ms=sum(table[k][0] for k in keys), n=sum(table[k][1] for k in keys),
+                               flops=sum(tag_flops(k, B) * table[k][1] for k in keys))
     top = max(stats, key=lambda n: stats[n]['ms'])
     st = stats[top]
     ach = st['flops'] / (st['ms'] * 1e-3) / 1e12 if st['ms'] > 0 else 0.
     traffic = None
     try:
-        ncu = json.load(open(os.path.join(ROOT, 'profiles', 'r01_ncu_full.json')))
+        ncu = json.load(open(os.path.join(ROOT, 'profiles', 'r02_ncu_full.json' if os.path.exists(os.path.join(ROOT, 'profiles', 'r02_ncu_full.json')) else 'r01_ncu_full.json')))
         traffic = ncu[top.split(' ')[0]]['dram_bytes_per_launch']
     except Exception:
         pass
-    # HBM-bound kernel families at the training batch: algorithmic bytes / CUDA-event time of the same
-    # launches.  At batch 128 a launch moves 3-8 MB (L2-resident), so these are latency-bound; scripts/hbm_ops_bench.py measures the
-    # same kernels at the scoring batch (profiles/r01_hbm_ops.json).
+    # HBM-bound kernel families at this batch: algorithmic bytes / CUDA-event time of the same launches
     n_param = sum(q.numel() for q in model.parameters() if q.requires_grad)
-    hbm_bytes = {'ibinn_aio_coupling_forward': 8 * 32768 * B + 48 * 36864 * B,      # 8 blocks of 32 768 B + 48 of 36 864 B per image
-                 'ibinn_aio_coupling_backward': 8 * 53248 * B + 48 * 61440 * B,
-                 'ibinn_sgd_step': 20. * n_param, 'ibinn_grad_norm_clip': 4. * n_param}
+    hbm_bytes = {'ibinn_sgd_step': 20. * n_param, 'ibinn_grad_norm_clip': 4. * n_param}
+    if a.workload.startswith('cifar'):
+        hbm_bytes.update({'ibinn_aio_coupling_forward': 8 * 32768 * B + 48 * 36864 * B,      # 8 blocks of 32 768 B + 48 of 36 864 B per image
+                          'ibinn_aio_coupling_backward': 8 * 53248 * B + 48 * 61440 * B,
+                          'ibinn_gmm_head_forward': (12288 + 4 * (C + 3)) * B + 4 * C * 3072})
     hbm_fam = {}
     for k, nbytes in hbm_bytes.items():
         if k in table and table[k][0] > 0:
             gbs = nbytes / (table[k][0] * 1e-3) / 1e9
             hbm_fam[k] = {'ms_per_step': table[k][0], 'launches': table[k][1], 'bytes_per_step': nbytes, 'gbs': gbs, 'frac_of_hbm_peak': gbs / pk['hbm']}
-    roofline = {'bound': 'tensor', 'kernel': top, 'hbm_families': hbm_fam, 'launches_per_step': st['n'], 'avg_launch_us': st['ms'] * 1e3 / max(st['n'], 1),
-                'flops_per_launch': st['flops'] / max(st['n'], 1), 'achieved': ach, 'peak': pk['bf16_sustained'], 'unit': 'TFLOP/s',
-                'frac': ach / pk['bf16_sustained'], 'traffic': traffic,
-                'peak_source': pk['source'] + ' bf16 dense sustained (MEASURED_PEAKS.json has no TF32 figure; nominal TF32 dense is half of it)',
+    roofline = {'bound': 'tensor', 'kernel': top, 'achieved': ach, 'peak': tf32['sustained'], 'unit': 'TFLOP/s', 'frac': ach / tf32['sustained'],
+                'traffic': traffic,
+                'peak_source': 'measured in this run: cuBLAS TF32 matmul 8192^3 back to back for 1 s (burst %.0f, sustained %.0f TFLOP/s); '
+                               'MEASURED_PEAKS.json (%s) bf16 dense sustained = %.0f' % (tf32['burst'], tf32['sustained'], pk['source'], pk['bf16_sustained']),
+                'frac_of_bf16_peak': ach / pk['bf16_sustained'],
+                'issued_over_algorithmic': 3.0, 'frac_issued': 3.0 * ach / tf32['sustained'],
+                'launches_per_step': st['n'], 'avg_launch_us': st['ms'] * 1e3 / max(st['n'], 1), 'flops_per_launch': st['flops'] / max(st['n'], 1),
                 'share_of_step': st['ms'] / total_ms if total_ms else None,
+                'whole_step_tflops': W['flop_per_img'] * imgs_per_step_global / world / (ms_step * 1e-3) / 1e12,
+                'hbm_families': hbm_fam,
                 'families': {n: {'ms_per_step': v['ms'], 'launches': v['n'], 'tflops': (v['flops'] / (v['ms'] * 1e-3) / 1e12 if v['ms'] > 0 else 0.)}
                              for n, v in stats.items()},
-                'note': 'fp32-accurate 3xTF32 on tcgen05; channel widths are 16/32/64, so one MMA uses N <= 128 of 256 columns and the kernels are '
-                        'latency- rather than throughput-bound (DESIGN.md section 7); time = CUDA-event durations of these launches in one eager '
-                        'step, traffic = ncu dram bytes per launch (profiles/)'}
-    line = {'metric': 'train_images_per_sec', 'value': value, 'unit': 'img/s', 'n_gpus': world, 'steps': a.steps, 'warmup': warmup,
+                'note': 'fp32-accurate 3xTF32 on tcgen05 (3 MMAs issued per algorithmic product: frac_issued = 3 x frac); time = CUDA-event '
+                        'durations of these launches in one eager step, traffic = ncu dram bytes per launch (profiles/)'}
+    line = {'metric': METRIC[kind], 'value': value, 'unit': 'img/s', 'n_gpus': world, 'steps': a.steps, 'warmup': warmup,
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'per_gpu_batch': B, 'global_batch': B * world, 'parallelism': 'dp%d' % world,
-                       'cuda_graph': step.use_graph, 'dropout': 'as shipped (Dropout2d 0.25 stage 2, Dropout 0.5 fc)',
-                       'l2': 'no explicit flush: one step streams %.0f MB of saved activations + 3 x 45 MB of parameter state, larger than the 126 MB L2'
-                             % (torch.cuda.max_memory_allocated() / 2 ** 20)},
+            'config': config_of(a.workload, B, world),
+            'notes': {'cuda_graph': main_e.use_graph, 'dropout': 'as shipped (Dropout2d 0.25 stage 2, Dropout 0.5 fc)' if kind in ('train', 'sweep', 'fwd') else 'eval mode',
+                      'l2': 'no explicit flush: one step streams %.0f MB of activations + parameter state, larger than the 126 MB L2'
+                            % (torch.cuda.max_memory_allocated() / 2 ** 20)},
             'clocks': clocks,
-            'e2e': {'value': world * B / (ms_e2e / a.steps * 1e-3), 'unit': 'img/s', 'h2d_bytes_per_step': int(xh.numel() * 4 + yh.numel() * 4),
-                    'd2h_bytes_per_step': 16},
-            'gpu_launches': (step.launches if step.launches is not None else eager_launches) * a.steps,
-            'gpu_launches_per_step': step.launches if step.launches is not None else eager_launches,
+            'e2e': {'value': imgs_per_step_global / (ms_e2e / a.steps * 1e-3), 'unit': 'img/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': launches * a.steps, 'gpu_launches_per_step': launches,
             'roofline': roofline, 'finite': loss_ok}
-    if not a.no_cpu_baseline and world == 1:
-        r = cpu_reference(10, 1, budget_s=15.)
-        line['cpu_baseline'] = {'value': r['value'], 'unit': 'img/s', 'cores': r['cores'], 'kind': 'port',
-                                'sample': '%d full training steps of batch %d (oracle fp32 port of the reference step)' % (r['steps'], B)}
-    if a.profile_out:
-        rows = sorted(((k, t, n) for k, (t, n) in table.items()), key=lambda r: -r[1])
-        json.dump({'total_ms': total_ms, 'launch_calls': eager_launches, 'rows': rows}, open(a.profile_out, 'w'), indent=1)
-    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    del engines, main_e, model
+    torch.cuda.empty_cache()
+    if world == 1:
+        if not a.no_cpu_baseline:
+            r = sub_reference(a.workload, B, 'cpu', 10, 1, 20.)
+            line['cpu_baseline'] = r.get('cpu_baseline', r)
+        if not a.no_torch_baseline:
+            # informational: the reference's own deployment (train.py:45 `.cuda()`): the same unmodified files with stock PyTorch
+            # kernels (cuDNN / cuBLAS, TF32 off) on this B200
+            r = sub_reference(a.workload, B, 'cuda', 20, 3, 60.)
+            line['torch_gpu_baseline'] = ({'value': r['value'], 'unit': 'img/s', 'ms_per_step': r['ms_per_step'], 'sample': r['cpu_baseline']['sample']}
+                                          if 'value' in r else r)
+    if a.profile_out:
+        rows = sorted(((k, v[0], v[1]) for k, v in table.items()), key=lambda r: -r[1])
+        json.dump({'total_ms': total_ms, 'launch_calls': eager_launches, 'rows': rows}, open(a.profile_out, 'w'), indent=1)
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == '__main__':

@@ -202,7 +202,7 @@ class TrainStep:
     step's stream) and returns the dict of device scalars the reference logs (no host sync).  With
     `use_graph` the whole step is captured once into CUDA graphs and replayed."""
 
-    def __init__(self, model, batch_size, beta=None, clip=None, use_graph=True, process_group=None, class_nll=None):
+    def __init__(self, model, batch_size, beta=None, clip=None, use_graph=True, process_group=None, class_nll=None, replicas_only=False):
         if not isinstance(model.optimizer, torch.optim.SGD):
             raise NotImplementedError('the fused step implements the reference default (SGD); use the plain torch loop otherwise')
         t = model.args['training']
@@ -213,7 +213,8 @@ class TrainStep:
         self.class_nll = eval(ab['class_NLL']) if class_nll is None else class_nll
         self.bx, self.by = beta_weights(self.beta, not eval(ab['no_NLL_term']))
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
+        # replicas_only: an independent training run per process (the beta sweep, BASELINE.json configs[4]): no gradient exchange
+        self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) and not replicas_only else 1
         self.flat = FlatParams(model)
         model._ibinn_flat = self.flat          # model.save / model.load checkpoint the momentum through it
         dev = model.mu.device
@@ -374,5 +375,74 @@ class TrainStep:
         return self.out
 
     def step(self, x, y):
+        self.load(x, y)
+        return self.run()
+
+
+class ScoreStep:
+    """Forward-only pass through the public model API under `torch.no_grad()`: log-likelihood / OoD scoring at large batch
+    (reference evaluation/ood.py:43: `inn(x, y=None, loss_mean=False)` in eval mode) or the forward + IB loss of a training
+    batch (`train_mode=True`, `with_labels=True`).  Static input buffers, tensor-core filter images prepared once, and the
+    whole pass captured into one CUDA graph; `step(x[, y])` returns the model's dict of device tensors (no host sync)."""
+
+    def __init__(self, model, batch_size, with_labels=False, loss_mean=False, train_mode=False, use_graph=True):
+        self.model = model
+        dev = model.mu.device
+        self.with_labels, self.loss_mean, self.train_mode = with_labels, loss_mean, train_mode
+        self.x = torch.zeros((batch_size,) + tuple(model.dims), dtype=torch.float32, device=dev)
+        self.y = torch.zeros((batch_size, model.n_classes), dtype=torch.float32, device=dev) if with_labels else None
+        self.use_graph = bool(use_graph) and dev.type == 'cuda'
+        self.wprep = WeightPrep(model) if dev.type == 'cuda' else None
+        self._graph, self.out, self.launches = None, None, None
+        self.refresh()
+
+    def refresh(self):
+        """call after the parameters changed: the captured graph reads the filter images, not the raw filters"""
+        if self.wprep is not None:
+            self.wprep.refresh()
+
+    def _forward(self):
+        was_training = self.model.inn.training
+        self.model.inn.train(self.train_mode)
+        try:
+            with torch.no_grad():
+                out = self.model(self.x, self.y, loss_mean=self.loss_mean)
+        finally:
+            self.model.inn.train(was_training)
+        if hasattr(self.model.inn, 'release_graph'):
+            self.model.inn.release_graph()
+        self.out = out
+
+    def capture(self, warmup=2):
+        L = _lib.lib()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                self._forward()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        n0 = L.ibinn_launch_count()
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph, stream=s):
+            self._forward()
+        self.launches = int(L.ibinn_launch_count() - n0)
+        torch.cuda.synchronize()
+
+    def load(self, x, y=None):
+        self.x.copy_(x, non_blocking=True)
+        if self.with_labels:
+            self.y.copy_(y, non_blocking=True)
+
+    def run(self):
+        if self.use_graph:
+            if self._graph is None:
+                self.capture()
+            self._graph.replay()
+        else:
+            self._forward()
+        return self.out
+
+    def step(self, x, y=None):
         self.load(x, y)
         return self.run()

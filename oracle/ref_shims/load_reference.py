@@ -23,12 +23,12 @@ def available():
     return os.path.isfile(os.path.join(REFERENCE_DIR, 'model.py'))
 
 
-def _install_shims():
+def _install_shims(force_cpu=False):
     if not hasattr(torch, 'rfft'):
         torch.rfft = lambda v, nd, onesided=False: torch.view_as_real(torch.fft.fft(v, dim=1))
         torch.irfft = lambda V, nd, onesided=False: torch.fft.ifft(
             torch.view_as_complex(V.contiguous()), dim=1).real
-    if not torch.cuda.is_available():
+    if force_cpu or not torch.cuda.is_available():
         torch.cuda.is_available = lambda: True
         torch.Tensor.cuda = lambda self, *a, **k: self
         torch.nn.Module.cuda = lambda self, *a, **k: self
@@ -39,15 +39,16 @@ def _install_shims():
     sys.path.insert(0, _HERE)      # FrEIA / matplotlib stand-ins shadow nothing real
 
 
-def load():
-    """Returns the reference's `model` module (GenerativeClassifier lives there)."""
+def load(force_cpu=False):
+    """Returns the reference's `model` module (GenerativeClassifier lives there).  force_cpu: neutralise `.cuda()` even on
+    a box that has a GPU (the CPU arm of bench.py)."""
     if not available():
         raise FileNotFoundError(REFERENCE_DIR)
-    _install_shims()
+    _install_shims(force_cpu)
     for name in ('model', 'inn_architecture', 'all_in_one_block',
                  'downsampling_coupling_block', 'dct_transform'):
         mod = sys.modules.get(name)
-        if mod is not None and not getattr(mod, '__file__', '').startswith(REFERENCE_DIR):
+        if mod is not None and not (getattr(mod, '__file__', '') or '').startswith(REFERENCE_DIR):
             del sys.modules[name]
     return importlib.import_module('model')
 
