@@ -71,7 +71,9 @@ def test_engine_full_depth_conditioned(cuda_dev, mode):
     assert ez < gate_z
     assert rel(jac, ref['jac']) < 1e-4
     for k in ('L_x_tr', 'L_cNLL_tr', 'L_y_tr', 'logits_tr'):
-        assert rel(out[k], ref[k]) < 1e-3, k
+        # train-mode BN at full depth: the reference's own fp32 L_y is 8.4e-4 from its fp64 value, so that mode is gated relative to it
+        gate = 1e-3 if mode == 'eval' else max(1e-3, 3. * rel(r32[k], ref[k]))
+        assert rel(out[k], ref[k]) < gate, (k, rel(out[k], ref[k]), rel(r32[k], ref[k]))
     assert torch.equal(out['logits_tr'].argmax(1).cpu(), ref['logits_tr'].argmax(1))
     assert float(out['acc_tr']) == float(ref['acc_tr'])
     if mode == 'train':
