@@ -60,8 +60,29 @@ class WgradArgs(Structure):
                 ('Wout', c_int32), ('ksize', c_int32), ('stride', c_int32), ('workspace', c_void_p), ('defer_reduce', c_int32)]
 
 
+class AioBlockDesc(Structure):
+    _fields_ = [('wprep1', c_void_p), ('wprep2', c_void_p), ('wprep3', c_void_p), ('wprep_perm', c_void_p), ('bias3', c_void_p),
+                ('bn1', BnRef), ('bn2', BnRef), ('act_norm', c_void_p), ('act_offset', c_void_p), ('drop_mask', c_void_p),
+                ('out', c_void_p), ('h1', c_void_p), ('h2', c_void_p), ('a', c_void_p), ('save', c_void_p),
+                ('running_mean1', c_void_p), ('running_var1', c_void_p), ('nbt1', c_void_p),
+                ('running_mean2', c_void_p), ('running_var2', c_void_p), ('nbt2', c_void_p),
+                ('relu_first', c_int32), ('reserved', c_int32)]
+
+
+class AioStageArgs(Structure):
+    _fields_ = [('x', c_void_p), ('jac', c_void_p), ('blocks', c_void_p),
+                ('nblk', c_int32), ('B', c_int32), ('C', c_int32), ('H', c_int32), ('W', c_int32), ('width', c_int32), ('train', c_int32),
+                ('clamp', c_float), ('alpha', c_float), ('momentum', c_float),
+                ('stat_records', c_void_p), ('barrier', c_void_p)]
+
+
 P, I, F, L = c_void_p, c_int, c_float, c_int64
 _SIGNATURES = {
+    'ibinn_sizeof_aio_block_desc': ([], c_size_t),
+    'ibinn_sizeof_aio_stage_args': ([], c_size_t),
+    'ibinn_aio_stage_supported': ([POINTER(AioStageArgs)], c_int),
+    'ibinn_aio_stage_workspace_floats': ([POINTER(AioStageArgs)], c_int64),
+    'ibinn_aio_stage_forward': ([POINTER(AioStageArgs), P], c_int),
     'ibinn_abi_version': ([], c_int),
     'ibinn_launch_count': ([], c_int64),
     'ibinn_last_error': ([], ctypes.c_char_p),
@@ -111,7 +132,8 @@ def _declare(lib):
         fn = getattr(lib, name)       # AttributeError if the library does not export it
         fn.argtypes = argtypes
         fn.restype = restype
-    if lib.ibinn_sizeof_conv_args() != ctypes.sizeof(ConvArgs) or lib.ibinn_sizeof_wgrad_args() != ctypes.sizeof(WgradArgs):
+    if lib.ibinn_sizeof_conv_args() != ctypes.sizeof(ConvArgs) or lib.ibinn_sizeof_wgrad_args() != ctypes.sizeof(WgradArgs) \
+            or lib.ibinn_sizeof_aio_block_desc() != ctypes.sizeof(AioBlockDesc) or lib.ibinn_sizeof_aio_stage_args() != ctypes.sizeof(AioStageArgs):
         raise RuntimeError('ibinn_b200: ctypes structure layout does not match include/ibinn_b200.h')
     return lib
 

@@ -1,0 +1,762 @@
+// Fused forward of a RUN of AIO_Blocks (reference all_in_one_block.py:83-114 with the subnet of inn_architecture.py:68-92):
+// one CTA owns one image and carries it through every block of the run with the activations resident in shared memory.
+//
+// Per block and image, four contractions run on tcgen05 as 3xTF32 (fp32-accurate) MMAs, all into ONE TMEM region (the column
+// group of a 128-position tile is handed from one contraction to the next as its epilogue drains it):
+//   conv1  3x3  c1    -> width     A = X1 image  (relu?(x1), hi / lo split, whole image + halo, K-major 16-byte rows)
+//   conv2  3x3  width -> width     A = H1 image  (relu(bn1(conv1)), written by conv1's epilogue straight into operand layout)
+//   conv3  1x1  width -> 2 c2      A = H2 tile   (relu(bn2(conv2)) [* dropout mask]) in a two-slot ring
+//   perm   1x1  C     -> C         A = U tile    ([x1 | x2 exp(clamp tanh(alpha s)) + t], the coupling output) in the same slot
+// The 3x3 taps are nine shifted descriptors onto the same image (one padded 1-D pixel sequence per image: pitch W+1, one zero
+// row below), exactly as in conv_tc.cu; filters arrive as the operand images of ibinn_wprep_many through a ring of TMA bulk copies.
+// Epilogues (warps 0-3, thread <-> TMEM lane <-> position): BatchNorm + ReLU + split -> next operand image; coupling + log-det;
+// ActNorm + store + the next block's X1 image.  The block input itself stays in shared memory as fp32 ([C][HW]) for the coupling.
+//
+// train = 0: running statistics; nothing couples CTAs; persistent over images.
+// train = 1: batch statistics: per-image (mean, M2) records -> grid barrier -> every CTA combines the records in fixed order
+//            (deterministic) -> BN coefficients; two barriers per block; raw conv outputs / subnet output / block output saved.
+#include "common.cuh"
+#include "tc.cuh"
+
+#ifndef IBINN_EMU
+namespace {
+
+constexpr int TM = 128;
+constexpr int BT_THREADS = 192;      // warps 0-3 epilogue, warp 4 MMA issuer, warp 5 filter producer
+constexpr int MAXT = 4;              // tiles of 128 positions per image
+constexpr int MAXSLOT = 8;           // filter ring
+constexpr int MAXW = 64;             // subnet width
+constexpr int MAXCH = 64;            // block channels
+
+struct BG {
+    int C, c1, c2, H, W, HW, width, P, S, halo, ntile, rows;
+    int cin_p, np3, npC, kC;
+    int lbo_img;                     // bytes between k-chunks of the X1 / H1 images (rows * 16)
+    int x_bytes, h_bytes, hu_bytes;  // ONE of hi / lo
+    int nhu, nslot, slot_bytes;
+    int tap1_bytes, tap2_bytes, w3_bytes, wp_bytes;
+    int tile_cols, tmem_cols;
+    int off_x, off_h, off_hu, off_ring, off_xs, off_tab;
+    int smem_bytes;
+};
+
+__host__ __device__ inline int pad_to(int v, int m) { return (v + m - 1) / m * m; }
+
+static bool bt_geometry(const ibinn_aio_stage_args& a, BG& g) {
+    if (a.C < 2 || a.C > MAXCH || (a.width != 32 && a.width != 64)) return false;      // the statistics passes work on groups of 32 channels
+    g.C = a.C; g.c2 = a.C / 2; g.c1 = a.C - g.c2; g.H = a.H; g.W = a.W; g.HW = a.H * a.W; g.width = a.width;
+    g.P = a.W + 1;
+    g.S = (a.H + 1) * g.P;
+    g.halo = g.P + 1;
+    g.ntile = (g.S + TM - 1) / TM;
+    if (g.ntile > MAXT) return false;
+    g.rows = g.halo + g.S;
+    g.cin_p = pad_to(g.c1, 8);
+    g.np3 = pad_to(2 * g.c2, 16);
+    g.npC = pad_to(g.C, 16);
+    g.kC = pad_to(g.C, 8);
+    if (g.kC > g.width) return false;                 // U shares the H2 slot
+    g.lbo_img = g.rows * 16;
+    g.x_bytes = (g.cin_p / 4) * g.lbo_img;
+    g.h_bytes = (g.width / 4) * g.lbo_img;
+    g.hu_bytes = (g.width / 4) * TM * 16;
+    g.nhu = g.ntile < 2 ? 1 : 2;
+    g.tap1_bytes = (g.cin_p / 4) * 2 * g.width * 16;
+    g.tap2_bytes = (g.width / 4) * 2 * g.width * 16;
+    g.w3_bytes = (g.width / 4) * 2 * g.np3 * 16;
+    g.wp_bytes = (g.kC / 4) * 2 * g.npC * 16;
+    g.slot_bytes = g.tap2_bytes;
+    if (g.w3_bytes > g.slot_bytes) g.slot_bytes = g.w3_bytes;
+    if (g.wp_bytes > g.slot_bytes) g.slot_bytes = g.wp_bytes;
+    if (g.tap1_bytes > g.slot_bytes) g.slot_bytes = g.tap1_bytes;
+    int cols = 2 * g.width;
+    if (2 * g.np3 > cols) cols = 2 * g.np3;
+    if (2 * g.npC > cols) cols = 2 * g.npC;
+    g.tile_cols = cols;
+    const int need = g.ntile * cols;
+    if (need > 512) return false;
+    g.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512;
+    // shared memory: A-operand over-reads (garbage rows of discarded positions) must land inside the allocation, so the images
+    // come first and the filter ring last
+    int off = 0;
+    g.off_x = off;  off += 2 * g.x_bytes;
+    g.off_h = off;  off += 2 * g.h_bytes;
+    g.off_hu = off; off += g.nhu * 2 * g.hu_bytes;
+    g.off_ring = off;
+    const int tab_bytes = (4 * MAXW + 3 * MAXCH + 8 * MAXW + 64) * 4;
+    const int xs_bytes = pad_to(g.C * g.HW * 4, 16);
+    const int budget = 225 * 1024 - tab_bytes - xs_bytes - off;
+    int nslot = budget / g.slot_bytes;
+    if (nslot > MAXSLOT) nslot = MAXSLOT;
+    if (nslot < 2) return false;
+    g.nslot = nslot;
+    off += nslot * g.slot_bytes;
+    g.off_xs = off;  off += xs_bytes;
+    g.off_tab = off; off += tab_bytes;
+    g.smem_bytes = off;
+    // the last tile's shifted views read up to (ntile*TM + 2*halo) rows of the last k-chunk of an image
+    const int over = (g.ntile * TM + 2 * g.halo - g.rows) * 16;
+    if (g.off_h + 2 * g.h_bytes + over > g.off_ring + nslot * g.slot_bytes) return false;
+    if (g.lbo_img >= (1 << 18)) return false;
+    return true;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ float ldcg(const float* p) { return __ldcg(p); }
+
+// Column sums over the 32 lanes of a warp for 32 values per lane: lane l ends up with sum over lanes of v[l] (31 shuffles,
+// fixed order).
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = up ? v[i] : v[i + off];
+            const float keep = up ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+// grid-wide barrier of the 128 epilogue threads of every CTA (train mode; all CTAs are co-resident: cooperative launch)
+// `episode` = 1, 2, ... counts this launch's barriers: the counter starts at zero (the last CTA to leave the kernel resets it)
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned nblk, unsigned episode, int tid) {
+    epi_sync();
+    if (tid == 0) {
+        unsigned long long old, cur;
+        asm volatile("atom.add.release.gpu.global.u64 %0, [%1], 1;" : "=l"(old) : "l"(bar) : "memory");
+        const unsigned long long target = (unsigned long long)episode * nblk;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(cur) : "l"(bar) : "memory");
+        } while (cur < target);
+    }
+    epi_sync();
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_aio_stage_args p, const BG g) {
+    extern __shared__ __align__(128) unsigned char sm[];
+    __shared__ __align__(8) uint64_t x1_full, acc_full[MAXT], h1_done[MAXT], hu_full[2], u_full[2], w_full[MAXSLOT], w_empty[MAXSLOT];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ uint32_t s_tapoff[9];
+
+    unsigned char* x_hi = sm + g.off_x;
+    unsigned char* x_lo = x_hi + g.x_bytes;
+    unsigned char* h_hi = sm + g.off_h;
+    unsigned char* h_lo = h_hi + g.h_bytes;
+    unsigned char* hu = sm + g.off_hu;
+    unsigned char* ring = sm + g.off_ring;
+    float* xs = reinterpret_cast<float*>(sm + g.off_xs);          // [C][HW] fp32 block input
+    float* tab = reinterpret_cast<float*>(sm + g.off_tab);
+    float* s_A1 = tab;                  // [MAXW] BN1 scale
+    float* s_B1 = s_A1 + MAXW;
+    float* s_A2 = s_B1 + MAXW;
+    float* s_B2 = s_A2 + MAXW;
+    float* s_sc = s_B2 + MAXW;          // [MAXCH] exp(act_norm)
+    float* s_of = s_sc + MAXCH;         // [MAXCH] act_offset
+    float* s_b3 = s_of + MAXCH;         // [MAXCH] conv3 bias
+    float* s_red = s_b3 + MAXCH;        // [8][MAXW] reduction scratch
+    float* s_misc = s_red + 8 * MAXW;   // [64]
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int nt = g.ntile;
+
+    if (tid < 9) s_tapoff[tid] = (uint32_t)(g.halo + (tid / 3 - 1) * g.P + (tid % 3 - 1));
+    if (tid == 0) {
+        tc::mbar_init(&x1_full, 128);
+        for (int i = 0; i < MAXT; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&h1_done[i], 128); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&hu_full[i], 128); tc::mbar_init(&u_full[i], 128); }
+        for (int i = 0; i < MAXSLOT; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
+        tc::mbar_fence_init();
+    }
+    if (warp == 4) tc::tmem_alloc(&tmem_base_s, g.tmem_cols);
+    // zero the top halo rows of both images once (positions < 0 = the zero padding above the first image row); everything
+    // else is rewritten per image
+    {
+        const int nx = (g.cin_p / 4) * g.halo, nh = (g.width / 4) * g.halo;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = tid; i < nx; i += BT_THREADS) {
+            const int k = i / g.halo, r = i - k * g.halo;
+            *reinterpret_cast<float4*>(x_hi + (size_t)k * g.lbo_img + r * 16) = z;
+            *reinterpret_cast<float4*>(x_lo + (size_t)k * g.lbo_img + r * 16) = z;
+        }
+        for (int i = tid; i < nh; i += BT_THREADS) {
+            const int k = i / g.halo, r = i - k * g.halo;
+            *reinterpret_cast<float4*>(h_hi + (size_t)k * g.lbo_img + r * 16) = z;
+            *reinterpret_cast<float4*>(h_lo + (size_t)k * g.lbo_img + r * 16) = z;
+        }
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_d = tmem_base_s;
+
+    const int nimg = TRAIN ? 1 : (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+    if (warp == 5) {
+        // ================= filter producer: chunks in consumption order through the ring =================
+        if (lane == 0) {
+            uint32_t ci = 0;
+            auto push = [&](const float* src, int bytes) {
+                const uint32_t s = ci % g.nslot;
+                if (ci >= (uint32_t)g.nslot) tc::mbar_wait(&w_empty[s], ((ci / g.nslot) - 1) & 1);
+                tc::mbar_arrive_expect_tx(&w_full[s], (uint32_t)bytes);
+                tc::bulk_g2s(ring + (size_t)s * g.slot_bytes, src, (uint32_t)bytes, &w_full[s]);
+                ++ci;
+            };
+            for (int im = 0; im < nimg; ++im)
+                for (int k = 0; k < p.nblk; ++k) {
+                    const ibinn_aio_block_desc* d = p.blocks + k;
+                    const float* w1 = d->wprep1; const float* w2 = d->wprep2; const float* w3 = d->wprep3; const float* wp = d->wprep_perm;
+                    for (int t = 0; t < nt; ++t)
+                        for (int tap = 0; tap < 9; ++tap) push(w1 + (size_t)tap * (g.tap1_bytes / 4), g.tap1_bytes);
+                    for (int t = 0; t < nt; ++t)
+                        for (int tap = 0; tap < 9; ++tap) push(w2 + (size_t)tap * (g.tap2_bytes / 4), g.tap2_bytes);
+                    for (int s = 0; s <= nt; ++s) {
+                        if (s < nt) push(w3, g.w3_bytes);
+                        if (s >= 1) push(wp, g.wp_bytes);
+                    }
+                }
+        }
+        __syncwarp();
+    } else if (warp == 4) {
+        // ================= MMA issuer =================
+        if (tc::elect_one()) {
+            uint32_t ci = 0, nblk_seen = 0, hu_cnt[2] = {0, 0}, u_cnt[2] = {0, 0};
+            const uint32_t idW2 = tc::idesc_tf32(TM, 2 * g.width), idW1 = tc::idesc_tf32(TM, g.width);
+            const uint32_t id32 = tc::idesc_tf32(TM, 2 * g.np3), id31 = tc::idesc_tf32(TM, g.np3);
+            const uint32_t idC2 = tc::idesc_tf32(TM, 2 * g.npC), idC1 = tc::idesc_tf32(TM, g.npC);
+            // one contraction of one tile: A (hi, lo images with `lbo_a`), nks k-steps, B chunk in ring slot with `lbo_b`
+            auto gemm = [&](uint32_t acc_addr, uint32_t a_hi_addr, uint32_t a_lo_addr, uint32_t lbo_a, uint32_t b_addr, uint32_t lbo_b,
+                            int nks, uint32_t id2, uint32_t id1, bool first) {
+                const uint64_t dah = tc::smem_desc(a_hi_addr, lbo_a), dal = tc::smem_desc(a_lo_addr, lbo_a), db = tc::smem_desc(b_addr, lbo_b);
+                const uint32_t hA = (uint32_t)(dah >> 32), hB = (uint32_t)(db >> 32);
+                uint32_t ah = (uint32_t)dah, al = (uint32_t)dal, b = (uint32_t)db;
+                const uint32_t a_step = (2 * lbo_a) >> 4, b_step = (2 * lbo_b) >> 4;
+                uint32_t acc = first ? 0u : 1u;
+                for (int ks = 0; ks < nks; ++ks) {
+                    tc::mma_tf32(acc_addr, ((uint64_t)hA << 32) | ah, ((uint64_t)hB << 32) | b, id2, acc);
+                    tc::mma_tf32(acc_addr, ((uint64_t)hA << 32) | al, ((uint64_t)hB << 32) | b, id1, 1);
+                    acc = 1;
+                    ah += a_step; al += a_step; b += b_step;
+                }
+            };
+            auto ring_wait = [&]() -> uint32_t {
+                const uint32_t s = ci % g.nslot;
+                tc::mbar_wait(&w_full[s], (ci / g.nslot) & 1);
+                tc::fence_after_sync();
+                return s;
+            };
+            auto ring_release = [&](uint32_t s) { tc::mma_commit(&w_empty[s]); ++ci; };
+            const uint32_t xh = tc::smem_u32(x_hi), xl = tc::smem_u32(x_lo), hh = tc::smem_u32(h_hi), hl = tc::smem_u32(h_lo);
+            const uint32_t ring_a = tc::smem_u32(ring), hu_a = tc::smem_u32(hu);
+            for (int im = 0; im < nimg; ++im)
+                for (int k = 0; k < p.nblk; ++k, ++nblk_seen) {
+                    // ---- conv1
+                    tc::mbar_wait(&x1_full, nblk_seen & 1);
+                    tc::fence_after_sync();
+                    for (int t = 0; t < nt; ++t) {
+                        const uint32_t acc_addr = tmem_d + t * g.tile_cols;
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint32_t s = ring_wait();
+                            const uint32_t ro = (uint32_t)(t * TM) + s_tapoff[tap];
+                            gemm(acc_addr, xh + ro * 16, xl + ro * 16, g.lbo_img, ring_a + s * g.slot_bytes, 2 * g.width * 16, g.cin_p / 8, idW2, idW1, tap == 0);
+                            ring_release(s);
+                        }
+                        tc::mma_commit(&acc_full[t]);
+                    }
+                    // ---- conv2 (tile t needs the H1 rows of tiles t-1 .. t+1)
+                    for (int t = 0; t < nt; ++t) {
+                        const int need = t + 1 < nt ? t + 1 : nt - 1;
+                        tc::mbar_wait(&h1_done[need], nblk_seen & 1);
+                        tc::fence_after_sync();
+                        const uint32_t acc_addr = tmem_d + t * g.tile_cols;
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint32_t s = ring_wait();
+                            const uint32_t ro = (uint32_t)(t * TM) + s_tapoff[tap];
+                            gemm(acc_addr, hh + ro * 16, hl + ro * 16, g.lbo_img, ring_a + s * g.slot_bytes, 2 * g.width * 16, g.width / 8, idW2, idW1, tap == 0);
+                            ring_release(s);
+                        }
+                        tc::mma_commit(&acc_full[t]);
+                    }
+                    // ---- conv3 (tile s) and soft permutation (tile s-1), software-pipelined against the epilogue
+                    for (int s = 0; s <= nt; ++s) {
+                        if (s < nt) {
+                            const int sl = s % g.nhu;
+                            tc::mbar_wait(&hu_full[sl], hu_cnt[sl] & 1); ++hu_cnt[sl];
+                            tc::fence_after_sync();
+                            const uint32_t rs = ring_wait();
+                            const uint32_t a0 = hu_a + sl * 2 * g.hu_bytes;
+                            gemm(tmem_d + s * g.tile_cols, a0, a0 + g.hu_bytes, TM * 16, ring_a + rs * g.slot_bytes, 2 * g.np3 * 16, g.width / 8, id32, id31, true);
+                            ring_release(rs);
+                            tc::mma_commit(&acc_full[s]);
+                        }
+                        if (s >= 1) {
+                            const int t = s - 1, sl = t % g.nhu;
+                            tc::mbar_wait(&u_full[sl], u_cnt[sl] & 1); ++u_cnt[sl];
+                            tc::fence_after_sync();
+                            const uint32_t rs = ring_wait();
+                            const uint32_t a0 = hu_a + sl * 2 * g.hu_bytes;
+                            gemm(tmem_d + t * g.tile_cols, a0, a0 + g.hu_bytes, TM * 16, ring_a + rs * g.slot_bytes, 2 * g.npC * 16, g.kC / 8, idC2, idC1, true);
+                            ring_release(rs);
+                            tc::mma_commit(&acc_full[t]);
+                        }
+                    }
+                }
+        }
+        __syncwarp();
+    } else {
+        // ================= warps 0-3: staging + every epilogue; thread <-> position (TMEM lane) =================
+        const int row = tid;                                  // 0..127
+        const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);
+        const float inv_n = 1.0f / (float)g.HW;
+        // position decode of this thread's row in every tile
+        int pixs[MAXT];                                       // pixel index inside the image or -1
+#pragma unroll
+        for (int t = 0; t < MAXT; ++t) {
+            const int q = t * TM + row;
+            const int yy = q / g.P, xx = q - yy * g.P;
+            pixs[t] = (t < nt && q < g.S && yy < g.H && xx < g.W) ? yy * g.W + xx : -1;
+        }
+
+        // BatchNorm coefficients of block k from given statistics (eval) -> s_A*, s_B*
+        auto load_bn_eval = [&](const ibinn_bn_ref& r, float* sA, float* sB) {
+            for (int c = tid; c < g.width; c += 128) {
+                const float sc = r.scale[c];
+                const float is = r.scale_is_variance ? rsqrtf(sc + r.eps) : sc;
+                const float A = r.gamma[c] * is;
+                sA[c] = A;
+                sB[c] = r.beta[c] - r.mean[c] * A;
+            }
+        };
+
+        unsigned n_episodes = 0;
+        // ---- train: per-image statistics of the accumulators of all tiles (+ save the raw conv output), grid-wide combine
+        auto batch_stats = [&](int kphase, const ibinn_bn_ref& r, float* sA, float* sB, float* raw_out, float* save, float* rmean, float* rvar,
+                               int64_t* nbt, int b, int rec_slot) {
+            const int W2 = g.width;
+            // pass 1a: per-channel sums over the image (invalid rows masked by selection); the raw values are stored on the way
+            float csum[2] = {0.f, 0.f};                        // lane <-> channel (group of 32)
+            for (int t = 0; t < nt; ++t) {
+                tc::mbar_wait(&acc_full[t], kphase & 1);
+                tc::fence_after_sync();
+                const bool valid = pixs[t] >= 0;
+                for (int c0 = 0; c0 < W2; c0 += 32) {
+                    float v[32];
+#pragma unroll
+                    for (int c8 = 0; c8 < 32; c8 += 8) {
+                        float a8[8], b8[8];
+                        tc::tmem_ld8(lane_base + t * g.tile_cols + c0 + c8, a8);
+                        tc::tmem_ld8(lane_base + t * g.tile_cols + W2 + c0 + c8, b8);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[c8 + i] = valid ? a8[i] + b8[i] : 0.f;
+                    }
+                    if (valid && raw_out) {
+                        float* dst = raw_out + ((size_t)b * W2 + c0) * g.HW + pixs[t];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) dst[(size_t)i * g.HW] = v[i];
+                    }
+                    csum[c0 >> 5] += warp_colsum32(v, lane);
+                }
+            }
+            for (int c0 = 0; c0 < W2; c0 += 32) s_red[warp * MAXW + c0 + lane] = csum[c0 >> 5];
+            epi_sync();
+            if (tid < W2) s_red[4 * MAXW + tid] = ((s_red[tid] + s_red[MAXW + tid]) + (s_red[2 * MAXW + tid] + s_red[3 * MAXW + tid])) * inv_n;
+            epi_sync();
+            // pass 1b: M2 about the image mean
+            float csq[2] = {0.f, 0.f};
+            for (int t = 0; t < nt; ++t) {
+                const bool valid = pixs[t] >= 0;
+                for (int c0 = 0; c0 < W2; c0 += 32) {
+                    float v[32];
+#pragma unroll
+                    for (int c8 = 0; c8 < 32; c8 += 8) {
+                        float a8[8], b8[8];
+                        tc::tmem_ld8(lane_base + t * g.tile_cols + c0 + c8, a8);
+                        tc::tmem_ld8(lane_base + t * g.tile_cols + W2 + c0 + c8, b8);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float dlt = (a8[i] + b8[i]) - s_red[4 * MAXW + c0 + c8 + i];
+                            v[c8 + i] = valid ? dlt * dlt : 0.f;
+                        }
+                    }
+                    csq[c0 >> 5] += warp_colsum32(v, lane);
+                }
+            }
+            for (int c0 = 0; c0 < W2; c0 += 32) s_red[warp * MAXW + c0 + lane] = csq[c0 >> 5];
+            epi_sync();
+            float* rec = p.stat_records + ((size_t)rec_slot * p.B + b) * 2 * W2;
+            if (tid < W2) {
+                rec[tid] = s_red[4 * MAXW + tid];
+                rec[W2 + tid] = (s_red[tid] + s_red[MAXW + tid]) + (s_red[2 * MAXW + tid] + s_red[3 * MAXW + tid]);
+            }
+            grid_barrier(p.barrier, gridDim.x, ++n_episodes, tid);
+            // combine the B records in fixed order: with K = mean of record 0, d_b = mean_b - K:
+            //   mean = K + sum d_b / B,   M2 = sum M2_b + n (sum d_b^2 - (sum d_b)^2 / B)
+            {
+                const int c = tid % W2, part = tid / W2, nparts = 128 / W2;
+                const float* base = p.stat_records + (size_t)rec_slot * p.B * 2 * W2;
+                const float K = ldcg(base + c);
+                float s1 = 0.f, s2 = 0.f, m2 = 0.f;
+                for (int b0 = part; b0 < p.B; b0 += nparts * 8) {
+                    float mb[8], qb[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int bb = b0 + u * nparts;
+                        mb[u] = bb < p.B ? ldcg(base + (size_t)bb * 2 * W2 + c) : K;
+                        qb[u] = bb < p.B ? ldcg(base + (size_t)bb * 2 * W2 + W2 + c) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float dlt = mb[u] - K;
+                        s1 += dlt;
+                        s2 = fmaf(dlt, dlt, s2);
+                        m2 += qb[u];
+                    }
+                }
+                epi_sync();                                   // s_red is free again
+                s_red[(part * 3 + 0) * W2 + c] = s1;        // [nparts][3][W2]: 128 / W2 * 3 * W2 = 384 floats
+                s_red[(part * 3 + 1) * W2 + c] = s2;
+                s_red[(part * 3 + 2) * W2 + c] = m2;
+                epi_sync();
+                if (tid < W2) {
+                    float S1 = 0.f, S2 = 0.f, M2 = 0.f;
+                    for (int q = 0; q < nparts; ++q) { S1 += s_red[(q * 3 + 0) * W2 + c]; S2 += s_red[(q * 3 + 1) * W2 + c]; M2 += s_red[(q * 3 + 2) * W2 + c]; }
+                    const float Bf = (float)p.B, nimgpix = (float)g.HW, N = Bf * nimgpix;
+                    const float dm = S1 / Bf, mean = K + dm;
+                    float tot = M2 + nimgpix * (S2 - S1 * dm);
+                    if (tot < 0.f) tot = 0.f;
+                    const float var_b = tot / N;
+                    const float is = 1.0f / sqrtf(var_b + r.eps);
+                    const float A = r.gamma[c] * is;
+                    sA[c] = A;
+                    sB[c] = r.beta[c] - mean * A;
+                    if (blockIdx.x == 0) {
+                        save[c] = mean;
+                        save[W2 + c] = is;
+                        if (rmean) {
+                            const long long nb = nbt ? *nbt : 0;
+                            const float f = p.momentum >= 0.f ? p.momentum : 1.0f / (float)(nb + 1);
+                            const float var_u = N > 1.f ? tot / (N - 1.f) : var_b;
+                            rmean[c] = (1.0f - f) * rmean[c] + f * mean;
+                            rvar[c] = (1.0f - f) * rvar[c] + f * var_u;
+                        }
+                    }
+                }
+                epi_sync();
+                if (blockIdx.x == 0 && tid == 0 && nbt) *nbt = *nbt + 1;
+            }
+        };
+
+        // BN + ReLU (+ dropout mask) + hi/lo split of tile t's accumulator -> operand rows starting at (dst_hi, dst_lo) with
+        // k-chunk stride `lbo`; invalid positions are written as zeros (they are the zero padding of the next 3x3 conv)
+        // (`store` = false: the row lies beyond the image; the TMEM loads are warp-collective and must still be executed)
+        auto bn_relu_to_operand = [&](int t, const float* sA, const float* sB, const float* dmask, unsigned char* dst_hi, unsigned char* dst_lo, int lbo,
+                                      bool store) {
+            const bool valid = pixs[t] >= 0;
+            const int W2 = g.width;
+            for (int c8 = 0; c8 < W2; c8 += 8) {
+                float a8[8], b8[8], hi[8], lo[8];
+                tc::tmem_ld8(lane_base + t * g.tile_cols + c8, a8);
+                tc::tmem_ld8(lane_base + t * g.tile_cols + W2 + c8, b8);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float v = fmaxf(fmaf(a8[i] + b8[i], sA[c8 + i], sB[c8 + i]), 0.f);
+                    if (dmask) v *= dmask[c8 + i];
+                    v = valid ? v : 0.f;
+                    tc::split_tf32(v, hi[i], lo[i]);
+                }
+                if (store) {
+                    *reinterpret_cast<float4*>(dst_hi + (size_t)(c8 / 4) * lbo) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(dst_hi + (size_t)(c8 / 4 + 1) * lbo) = make_float4(hi[4], hi[5], hi[6], hi[7]);
+                    *reinterpret_cast<float4*>(dst_lo + (size_t)(c8 / 4) * lbo) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    *reinterpret_cast<float4*>(dst_lo + (size_t)(c8 / 4 + 1) * lbo) = make_float4(lo[4], lo[5], lo[6], lo[7]);
+                }
+            }
+        };
+
+        uint32_t blk_seen = 0;
+        for (int im = 0; im < nimg; ++im) {
+            const int b = (int)blockIdx.x + im * (int)gridDim.x;
+            float jsum = 0.f, san_tot = 0.f;
+            // ---- stage the first block's input: fp32 copy for the coupling + X1 operand image
+            {
+                const float* xb = p.x + (size_t)b * g.C * g.HW;
+                for (int i = tid; i < g.C * g.HW; i += 128) xs[i] = __ldg(xb + i);
+                epi_sync();
+            }
+            for (int k = 0; k < p.nblk; ++k, ++blk_seen) {
+                const ibinn_aio_block_desc* d = p.blocks + k;
+                const bool last = (k == p.nblk - 1);
+                epi_sync();                                   // every thread is done with the previous block's tables
+                // X1 image of this block from xs (the previous block's epilogue has already written it for k > 0)
+                if (k == 0) {
+                    const int nk4 = g.cin_p / 4;
+                    const bool rf = d->relu_first != 0;
+                    for (int i = tid; i < nk4 * g.S; i += 128) {
+                        const int k4 = i / g.S, q = i - k4 * g.S;
+                        const int yy = q / g.P, xx = q - yy * g.P;
+                        float hi[4], lo[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int ch = k4 * 4 + j;
+                            float v = 0.f;
+                            if (ch < g.c1 && yy < g.H && xx < g.W) {
+                                v = xs[ch * g.HW + yy * g.W + xx];
+                                if (rf) v = fmaxf(v, 0.f);
+                            }
+                            tc::split_tf32(v, hi[j], lo[j]);
+                        }
+                        *reinterpret_cast<float4*>(x_hi + (size_t)k4 * g.lbo_img + (g.halo + q) * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<float4*>(x_lo + (size_t)k4 * g.lbo_img + (g.halo + q) * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+                // per-block tables
+                for (int c = tid; c < g.C; c += 128) { s_sc[c] = expf(d->act_norm[c]); s_of[c] = d->act_offset[c]; }
+                for (int c = tid; c < 2 * g.c2; c += 128) s_b3[c] = d->bias3[c];
+                if (!TRAIN) { load_bn_eval(d->bn1, s_A1, s_B1); load_bn_eval(d->bn2, s_A2, s_B2); }
+                if (warp == 3) {
+                    float v = 0.f;
+                    for (int c = lane; c < g.C; c += 32) v += d->act_norm[c];
+                    v = warp_sum(v);
+                    san_tot += v;                            // the same value in every lane of warp 3
+                }
+                tc::fence_async_smem();
+                mbar_arrive(&x1_full);
+                epi_sync();                                   // tables visible to all epilogue threads
+
+                const float* dmask = (TRAIN && d->drop_mask) ? d->drop_mask + (size_t)b * g.width : nullptr;
+                // ---- B: conv1 accumulators -> H1 image
+                if (TRAIN) batch_stats(0, d->bn1, s_A1, s_B1, d->h1, d->save, d->running_mean1, d->running_var1, d->nbt1, b, 0);
+                for (int t = 0; t < nt; ++t) {
+                    if (!TRAIN) { tc::mbar_wait(&acc_full[t], 0); tc::fence_after_sync(); }
+                    const int q = t * TM + row;
+                    bn_relu_to_operand(t, s_A1, s_B1, nullptr, h_hi + (g.halo + q) * 16, h_lo + (g.halo + q) * 16, g.lbo_img, q < g.S);
+                    tc::fence_before_sync();
+                    tc::fence_async_smem();
+                    mbar_arrive(&h1_done[t]);
+                }
+                // ---- train: statistics of conv2 need all of its tiles before any of them can be normalised
+                if (TRAIN) batch_stats(1, d->bn2, s_A2, s_B2, d->h2, d->save + 2 * g.width, d->running_mean2, d->running_var2, d->nbt2, b, 1);
+                // ---- pipelined tail: H(s-2), D(s), F(s-1)
+                for (int s = 0; s < nt + 2; ++s) {
+                    if (s >= 2) {
+                        // H: ActNorm on the permuted tile, store, and the next block's inputs
+                        const int t = s - 2;
+                        tc::mbar_wait(&acc_full[t], 1);
+                        tc::fence_after_sync();
+                        const int pix = pixs[t];
+                        const int q = t * TM + row;
+                        float* og = (d->out && pix >= 0) ? d->out + (size_t)b * g.C * g.HW + pix : nullptr;
+                        const int nk4 = g.cin_p / 4;
+                        for (int c8 = 0; c8 < g.npC; c8 += 8) {
+                            float a8[8], b8[8], o8[8];
+                            tc::tmem_ld8(lane_base + t * g.tile_cols + c8, a8);
+                            tc::tmem_ld8(lane_base + t * g.tile_cols + g.npC + c8, b8);
+                            tc::tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int c = c8 + i;
+                                o8[i] = 0.f;
+                                if (c < g.C) {
+                                    o8[i] = fmaf(a8[i] + b8[i], s_sc[c], s_of[c]);
+                                    if (pix >= 0) {
+                                        if (og) og[(size_t)c * g.HW] = o8[i];
+                                        if (!last) xs[c * g.HW + pix] = o8[i];
+                                    }
+                                }
+                            }
+                            if (!last && q < g.S) {
+                                // next block's X1 image: relu(out[:c1]) (every block after the first of the network has the leading ReLU;
+                                // the flag of the NEXT block decides)
+                                const bool rf = (d + 1)->relu_first != 0;
+#pragma unroll
+                                for (int h4 = 0; h4 < 2; ++h4) {
+                                    const int k4 = c8 / 4 + h4;
+                                    if (k4 < nk4) {
+                                        float hi[4], lo[4];
+#pragma unroll
+                                        for (int j = 0; j < 4; ++j) {
+                                            const int c = k4 * 4 + j;
+                                            float v = (c < g.c1 && pix >= 0) ? o8[h4 * 4 + j] : 0.f;
+                                            if (rf) v = fmaxf(v, 0.f);
+                                            tc::split_tf32(v, hi[j], lo[j]);
+                                        }
+                                        *reinterpret_cast<float4*>(x_hi + (size_t)k4 * g.lbo_img + (g.halo + q) * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                                        *reinterpret_cast<float4*>(x_lo + (size_t)k4 * g.lbo_img + (g.halo + q) * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                                    }
+                                }
+                            }
+                        }
+                        tc::fence_before_sync();
+                    }
+                    if (s < nt) {
+                        // D: conv2 accumulators -> H2 tile in slot s % nhu
+                        const int t = s, sl = t % g.nhu;
+                        tc::mbar_wait(&acc_full[t], 1);
+                        tc::fence_after_sync();
+                        unsigned char* dh = hu + (size_t)sl * 2 * g.hu_bytes + row * 16;
+                        bn_relu_to_operand(t, s_A2, s_B2, dmask, dh, dh + g.hu_bytes, TM * 16, true);
+                        tc::fence_before_sync();
+                        tc::fence_async_smem();
+                        mbar_arrive(&hu_full[sl]);
+                    }
+                    if (s >= 1 && s - 1 < nt) {
+                        // F: subnet output -> affine coupling -> U tile (same slot), log-det
+                        const int t = s - 1, sl = t % g.nhu;
+                        tc::mbar_wait(&acc_full[t], 0);
+                        tc::fence_after_sync();
+                        const int pix = pixs[t];
+                        const uint32_t tb = lane_base + t * g.tile_cols;
+                        unsigned char* uh = hu + (size_t)sl * 2 * g.hu_bytes + row * 16;
+                        float* ag = (TRAIN && d->a && pix >= 0) ? d->a + (size_t)b * 2 * g.c2 * g.HW + pix : nullptr;
+                        for (int k4 = 0; k4 < g.kC / 4; ++k4) {
+                            float sv[4], tv[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int c = k4 * 4 + j, jj = c - g.c1;
+                                sv[j] = 0.f; tv[j] = 0.f;
+                                if (jj >= 0 && c < g.C) {
+                                    sv[j] = tmem_ld1(tb + jj) + tmem_ld1(tb + g.np3 + jj);
+                                    tv[j] = tmem_ld1(tb + g.c2 + jj) + tmem_ld1(tb + g.np3 + g.c2 + jj);
+                                }
+                            }
+                            tc::tmem_ld_wait();
+                            float hi[4], lo[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int c = k4 * 4 + j, jj = c - g.c1;
+                                float u = 0.f;
+                                if (c < g.C && pix >= 0) {
+                                    u = xs[c * g.HW + pix];
+                                    if (jj >= 0) {
+                                        const float sa = sv[j] + s_b3[jj], ta = tv[j] + s_b3[g.c2 + jj];
+                                        if (ag) { ag[(size_t)jj * g.HW] = sa; ag[(size_t)(g.c2 + jj) * g.HW] = ta; }
+                                        const float sig = p.clamp * tanhf(p.alpha * sa);
+                                        u = fmaf(u, expf(sig), ta);
+                                        jsum += sig;
+                                    }
+                                }
+                                tc::split_tf32(u, hi[j], lo[j]);
+                            }
+                            *reinterpret_cast<float4*>(uh + (size_t)k4 * TM * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<float4*>(uh + g.hu_bytes + (size_t)k4 * TM * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                        }
+                        tc::fence_before_sync();
+                        tc::fence_async_smem();
+                        mbar_arrive(&u_full[sl]);
+                    }
+                }
+                // xs / X1 of the next block are complete in shared memory; the arrive on x1_full at the top of the next
+                // iteration (after its epi_sync) publishes them to the MMA issuer
+            }
+            // ---- log-det of the run for this image: sum of the coupling log-scales + HW * sum of the ActNorm log-scales
+            {
+                const float w = warp_sum(jsum);
+                epi_sync();
+                if (lane == 0) s_misc[warp] = w;
+                if (warp == 3 && lane == 0) s_misc[8] = san_tot;
+                epi_sync();
+                if (tid == 0) p.jac[b] = ((s_misc[0] + s_misc[1]) + (s_misc[2] + s_misc[3])) + (float)g.HW * s_misc[8];
+                epi_sync();
+            }
+        }
+    }
+
+    if (TRAIN && tid == 0) {
+        // every CTA is past its last barrier when it gets here: the last one out returns both counters to zero for the next launch
+        const unsigned long long old = atomicAdd(p.barrier + 1, 1ull);
+        if (old == (unsigned long long)gridDim.x - 1ull) {
+            p.barrier[0] = 0ull;
+            p.barrier[1] = 0ull;
+            __threadfence();
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 4) tc::tmem_dealloc(tmem_d, g.tmem_cols);
+}
+
+}  // namespace
+
+extern "C" size_t ibinn_sizeof_aio_block_desc(void) { return sizeof(ibinn_aio_block_desc); }
+extern "C" size_t ibinn_sizeof_aio_stage_args(void) { return sizeof(ibinn_aio_stage_args); }
+
+extern "C" int ibinn_aio_stage_supported(const ibinn_aio_stage_args* a) {
+    if (!a) return 0;
+    BG g;
+    if (!bt_geometry(*a, g)) return 0;
+    if (a->nblk < 1 || a->B < 1) return 0;
+    if (a->train && a->B > 148) return 0;          // one co-resident CTA per image (grid barrier)
+    return 1;
+}
+
+extern "C" int64_t ibinn_aio_stage_workspace_floats(const ibinn_aio_stage_args* a) {
+    if (!a) return IBINN_ENULL;
+    return a->train ? (int64_t)2 * a->B * 2 * a->width : 0;
+}
+
+extern "C" int ibinn_aio_stage_forward(const ibinn_aio_stage_args* ap, ibinn_stream_t stream) {
+    int e = ibinn_check_device();
+    if (e) return e;
+    if (!ap) return IBINN_ENULL;
+    const ibinn_aio_stage_args& a = *ap;
+    if (!a.x || !a.jac || !a.blocks) return IBINN_ENULL;
+    if (a.train && (!a.stat_records || !a.barrier)) return IBINN_ENULL;
+    BG g;
+    if (!ibinn_aio_stage_supported(ap) || !bt_geometry(a, g)) return IBINN_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = a.train ? a.B : (a.B < 148 ? a.B : 148);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(BT_THREADS);
+    cfg.dynamicSmemBytes = (size_t)g.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = a.train ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ++ibinn_launch_counter;
+    cudaError_t ce;
+    if (a.train) {
+        auto kfn = aio_stage_kernel<true>;
+        e = ibinn_set_smem(kfn, g.smem_bytes);
+        if (e) return e;
+        ce = cudaLaunchKernelEx(&cfg, kfn, a, g);
+    } else {
+        auto kfn = aio_stage_kernel<false>;
+        e = ibinn_set_smem(kfn, g.smem_bytes);
+        if (e) return e;
+        ce = cudaLaunchKernelEx(&cfg, kfn, a, g);
+    }
+    if (ce != cudaSuccess) {
+        snprintf(ibinn_errbuf, sizeof(ibinn_errbuf), "%s:%d launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(ce));
+        cudaGetLastError();
+        return (int)ce;
+    }
+    return ibinn_launch_status();
+}
+
+#else  // IBINN_EMU: no tensor cores in the simulator build; callers use the per-op entry points
+extern "C" size_t ibinn_sizeof_aio_block_desc(void) { return sizeof(ibinn_aio_block_desc); }
+extern "C" size_t ibinn_sizeof_aio_stage_args(void) { return sizeof(ibinn_aio_stage_args); }
+extern "C" int ibinn_aio_stage_supported(const ibinn_aio_stage_args*) { return 0; }
+extern "C" int64_t ibinn_aio_stage_workspace_floats(const ibinn_aio_stage_args*) { return 0; }
+extern "C" int ibinn_aio_stage_forward(const ibinn_aio_stage_args*, ibinn_stream_t) { return IBINN_EINVAL; }
+#endif

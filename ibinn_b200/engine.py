@@ -142,6 +142,18 @@ class WeightPrep:
                 if False in entry and True in entry:
                     w._ibinn_wprep = entry
                     self.params.append(w)
+        from .all_in_one_block import AIO_Block
+        for m in model.inn.modules():
+            # the frozen soft-permutation matrices as 1x1 filters: operand of the fused block kernel (block_tc.cu)
+            if isinstance(m, AIO_Block):
+                w = m.w
+                n = ops.conv_wprep_floats(w, False, 8, 8)
+                if n > 0:
+                    buf = torch.empty(n, dtype=torch.float32, device=dev)
+                    co, ci, ks, _ = w.shape
+                    descs.append(bytes(_lib.WprepDesc(w.data_ptr(), buf.data_ptr(), ci, co, ks, 0)))
+                    w._ibinn_wprep = {'valid': False, False: buf}
+                    self.params.append(w)
         self.n = len(descs)
         raw = np.frombuffer(b''.join(descs), dtype=np.uint8).copy() if descs else np.zeros(1, np.uint8)
         self.table = torch.from_numpy(raw).to(dev)

@@ -4,6 +4,8 @@ model.py:141-142,235, train.py:161-163).  Every graph the reference builds is a 
 container is a sequential interpreter; node modules keep the FrEIA protocol
 `__init__(dims_in, **kw)`, `forward([x], rev) -> [y]`, `jacobian([x], rev)`, `output_dims(dims)`.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -67,23 +69,71 @@ class ReversibleGraphNet(nn.Module):
         for k in range(len(node_list)):
             self.register_buffer('tmp_var_%d' % k, torch.zeros(1))
         self._jacs, self._rev = [], False
+        # runs of consecutive AIO_Blocks of one resolution stage go through ONE fused launch when the kernel supports the
+        # geometry (functions.AIOStageFn); `fused_stages = False` (or IBINN_FUSED=0) keeps one node = one autograd function
+        self.fused_stages = os.environ.get('IBINN_FUSED', '1') != '0'
+        self._runs = None
         if verbose:
             for n in node_list:
                 print(n.name, n.output_dims)
 
+    def _find_runs(self):
+        """{first index: AioStagePlan} for every maximal run (>= 1) of consecutive AIO_Blocks with the same geometry"""
+        from . import ops
+        from .all_in_one_block import AIO_Block
+        runs, k, n = {}, 0, len(self.module_list)
+        while k < n:
+            m = self.module_list[k]
+            if isinstance(m, AIO_Block) and not m.act_norm_trigger:
+                j = k + 1
+                dims = self.node_list[k].output_dims
+                while (j < n and isinstance(self.module_list[j], AIO_Block) and self.node_list[j].output_dims == dims
+                       and not self.module_list[j].act_norm_trigger and self.module_list[j].clamp == m.clamp
+                       and self.module_list[j].s.conv1.weight.shape == m.s.conv1.weight.shape):
+                    j += 1
+                runs[k] = ops.AioStagePlan([self.module_list[i] for i in range(k, j)])
+                k = j
+            else:
+                k += 1
+        return runs
+
     def forward(self, x, c=None, rev=False, intermediate_outputs=False):
-        order = range(len(self.node_list))
-        if rev:
-            order = reversed(order)
+        from . import functions as Fn
+        n = len(self.node_list)
         self._node_inputs, self._jacs, self._rev = {}, [], rev
         h = x
-        for k in order:
+        if rev:
+            for k in reversed(range(n)):
+                m = self.module_list[k]
+                if m is None:
+                    continue
+                self._node_inputs[k] = h
+                h = m([h], rev=True)[0]
+                self._jacs.append((k, h))
+            return h
+        if self.fused_stages and self._runs is None:
+            self._runs = self._find_runs()
+        k = 0
+        while k < n:
             m = self.module_list[k]
             if m is None:
+                k += 1
+                continue
+            plan = self._runs.get(k) if self.fused_stages else None
+            if plan is not None and (m.training or not torch.is_grad_enabled()) and plan.supported(h, m.training):
+                # the whole run in one launch; its log-det is reported by the first block of the run
+                self._node_inputs[k] = h
+                h, jac = Fn.AIOStageFn.apply(h, plan, *Fn.aio_stage_params(plan))
+                m.last_jac = jac
+                for blk in plan.blocks[1:]:
+                    blk.last_jac = None
+                k += len(plan.blocks)
+                self._jacs.append((k - 1, h))
                 continue
             self._node_inputs[k] = h
-            h = m([h], rev=rev)[0]
+            h = m([h], rev=False)[0]
             self._jacs.append((k, h))
+            k += 1
         return h
 
     def release_graph(self):

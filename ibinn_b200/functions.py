@@ -172,6 +172,59 @@ class AIOBlockFn(torch.autograd.Function):
         return (g_x, None, None) + tuple(sink.returns())
 
 
+class AIOStageFn(torch.autograd.Function):
+    """A run of consecutive AIO_Blocks as ONE launch (ops.aio_stage_forward).  The backward walks the run's blocks in
+    reverse with the per-block backward kernels, on the tensors the fused forward saved."""
+
+    @staticmethod
+    def forward(ctx, x, plan, *params):
+        x = x.contiguous()
+        blocks = plan.blocks
+        train = blocks[0].training
+        B = x.shape[0]
+        masks = None
+        if train:
+            masks = [pooled_mask(blk.s, (B, plan.width), blk.s.p_drop, x) if blk.s.p_drop > 0. else None for blk in blocks]
+        res = ops.aio_stage_forward(plan, x, train, masks)
+        ctx.plan, ctx.masks, ctx.train = plan, masks, train
+        if train:
+            ctx.save_for_backward(x, res['outs'], res['h1'], res['h2'], res['a'], res['save'])
+        ctx.res = res if train else None
+        out = res['out']
+        return out, res['jac']
+
+    @staticmethod
+    def backward(ctx, g_out, g_jac):
+        if not ctx.train:
+            raise RuntimeError('ibinn_b200: the fused eval-mode run keeps no activations; it is only used under torch.no_grad()')
+        x, outs, h1, h2, a, save = ctx.saved_tensors
+        blocks = ctx.plan.blocks
+        if g_out is None:
+            g_out = torch.zeros_like(outs[-1])
+        g = g_out.contiguous()
+        g_jac = None if g_jac is None else g_jac.contiguous()
+        grads = [None] * len(blocks)
+        for k in range(len(blocks) - 1, -1, -1):
+            blk = blocks[k]
+            net = blk.s
+            c1 = blk.split_len1
+            xk = x if k == 0 else outs[k - 1]
+            sink = GradSink(conv_subnet_params(net) + [blk.act_norm, blk.act_offset])
+            g_x, g_a = ops.aio_coupling_backward(g, g_jac, xk, a[k], outs[k], blk.w, blk.act_norm, blk.act_offset, blk.clamp, 0.1,
+                                                 sink[8], sink[9])
+            r1 = BN(save[k][0], save[k][1], net.bn1.weight, net.bn1.bias, net.bn1.eps, False)
+            r2 = BN(save[k][2], save[k][3], net.bn2.weight, net.bn2.bias, net.bn2.eps, False)
+            conv_subnet_backward(net, (h1[k], h2[k], r1, r2, ctx.masks[k], True), xk[:, :c1], g_a, sink, 0, g_x[:, :c1], g_x[:, :c1])
+            grads[k] = sink.returns()
+            g = g_x
+        ctx.res = None
+        return (g, None) + tuple(t for gk in grads for t in gk)
+
+
+def aio_stage_params(plan):
+    return [p for blk in plan.blocks for p in conv_subnet_params(blk.s) + [blk.act_norm, blk.act_offset]]
+
+
 def aio_block_reverse(blk, y):
     """AIO_Block.forward, rev=True (reference all_in_one_block.py:93-103).  No autograd."""
     u = ops.aio_unpermute(y, blk.w_inv, blk.act_norm, blk.act_offset)

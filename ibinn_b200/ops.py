@@ -264,6 +264,138 @@ def conv_wgrad(g, x, dw, ksize, stride=1, *, g_pre=PRE_NONE, gh=None, g_bn=None,
         flush_wgrad_group()
 
 
+# ------------------------------------------------------------------------------------ fused run of AIO blocks
+
+_BARRIERS = {}
+
+
+def _grid_barrier_counter(ref):
+    """one zero-initialised 64-bit counter per device for the grid-wide barriers of ibinn_aio_stage_forward (monotonic)"""
+    key = (ref.device.type, ref.device.index)
+    t = _BARRIERS.get(key)
+    if t is None:
+        t = _BARRIERS[key] = torch.zeros(2, dtype=torch.int64, device=ref.device)
+    return t
+
+
+class AioStagePlan:
+    """A run of consecutive AIO_Blocks of one resolution stage that ONE ibinn_aio_stage_forward launch covers (see
+    include/ibinn_b200.h).  Holds what does not change between calls: the blocks, the geometry, a pinned staging buffer for
+    the descriptor table and -- when no engine manages the tensor-core filter images -- its own images."""
+
+    def __init__(self, blocks):
+        self.blocks = list(blocks)
+        b0 = self.blocks[0]
+        self.C = b0.in_channels
+        self.width = b0.s.conv1.weight.shape[0]
+        self.clamp = float(b0.clamp)
+        self._pinned = {}
+        self._own = None
+        self._ok = {}
+
+    def __deepcopy__(self, memo):
+        import copy
+        return AioStagePlan([copy.deepcopy(b, memo) for b in self.blocks])      # staging buffers / CUDA events are per instance
+
+    def weights(self):
+        return [w for blk in self.blocks for w in (blk.s.conv1.weight, blk.s.conv2.weight, blk.s.conv3.weight, blk.w)]
+
+    def supported(self, x, train):
+        if not x.is_cuda or x.dim() != 4 or x.dtype != torch.float32:
+            return False
+        B, C, H, W = x.shape
+        key = (B, H, W, bool(train))
+        ok = self._ok.get(key)
+        if ok is None:
+            a = _lib.AioStageArgs()
+            a.nblk, a.B, a.C, a.H, a.W, a.width, a.train = len(self.blocks), B, C, H, W, self.width, int(train)
+            ok = self._ok[key] = bool(_lib.lib().ibinn_aio_stage_supported(ctypes.byref(a)))
+        return ok
+
+    def weight_images(self, ref):
+        """operand images (forward orientation) of conv1 / conv2 / conv3 / w of every block, as a flat list of tensors"""
+        ws = self.weights()
+        if all(getattr(w, '_ibinn_wprep', None) is not None and w._ibinn_wprep['valid'] for w in ws):
+            return [w._ibinn_wprep[False] for w in ws]          # engine.WeightPrep refreshed them for this step
+        if self._own is None or self._own['dev'] != ref.device:
+            import numpy as np
+            bufs, descs = [], []
+            for w in ws:
+                co, ci, ks, _ = w.shape
+                n = conv_wprep_floats(w, False, 8, 8)
+                if n <= 0:
+                    raise RuntimeError('ibinn_b200: no tensor-core operand image for a filter of shape %s' % (tuple(w.shape),))
+                buf = torch.empty(n, dtype=torch.float32, device=ref.device)
+                bufs.append(buf)
+                descs.append(bytes(_lib.WprepDesc(w.data_ptr(), buf.data_ptr(), ci, co, ks, 0)))
+            raw = np.frombuffer(b''.join(descs), dtype=np.uint8).copy()
+            self._own = dict(dev=ref.device, bufs=bufs, table=torch.from_numpy(raw).to(ref.device), n=len(descs),
+                             ptrs=[w.data_ptr() for w in ws])
+        if self._own['ptrs'] != [w.data_ptr() for w in ws]:
+            self._own = None                                    # the parameters moved (e.g. engine.FlatParams): rebuild
+            return self.weight_images(ref)
+        wprep_many(self._own['table'], self._own['n'], ref)     # one launch; the filters may have changed since the last call
+        return self._own['bufs']
+
+
+def aio_stage_forward(plan, x, train, masks=None):
+    """One launch for the whole run.  Returns dict(out, jac[, outs, h1, h2, a, save]) -- in train mode the per-block tensors
+    the backward entry points need (outs[k] = output of block k)."""
+    B, C, H, W = x.shape
+    nblk, width, c2 = len(plan.blocks), plan.width, C // 2
+    dev = x.device
+    f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+    res = dict(jac=f(B))
+    if train:
+        res.update(outs=f(nblk, B, C, H, W), h1=f(nblk, B, width, H, W), h2=f(nblk, B, width, H, W), a=f(nblk, B, 2 * c2, H, W),
+                   save=f(nblk, 4, width))
+        res['out'] = res['outs'][nblk - 1]
+    else:
+        res['out'] = f(B, C, H, W)
+    imgs = plan.weight_images(x)
+    entries = []
+    for k, blk in enumerate(plan.blocks):
+        net = blk.s
+        d = _lib.AioBlockDesc()
+        d.wprep1, d.wprep2, d.wprep3, d.wprep_perm = (ptr(t) for t in imgs[4 * k:4 * k + 4])
+        d.bias3 = ptr(net.conv3.bias)
+        for name, bn in (('bn1', net.bn1), ('bn2', net.bn2)):
+            if train:
+                setattr(d, name, BnRef(None, None, ptr(bn.weight), ptr(bn.bias), float(bn.eps), 0))
+            else:
+                setattr(d, name, bn_ref(bn.running_mean, bn.running_var, bn.weight, bn.bias, bn.eps, True))
+        d.act_norm, d.act_offset = ptr(blk.act_norm), ptr(blk.act_offset)
+        d.relu_first = int(net.relu_first)
+        if train:
+            m = masks[k] if masks is not None else None
+            d.drop_mask = ptr(m)
+            d.out, d.h1, d.h2, d.a, d.save = ptr(res['outs'][k]), ptr(res['h1'][k]), ptr(res['h2'][k]), ptr(res['a'][k]), ptr(res['save'][k])
+            d.running_mean1, d.running_var1, d.nbt1 = ptr(net.bn1.running_mean), ptr(net.bn1.running_var), ptr(net.bn1.num_batches_tracked, torch.int64)
+            d.running_mean2, d.running_var2, d.nbt2 = ptr(net.bn2.running_mean), ptr(net.bn2.running_var), ptr(net.bn2.num_batches_tracked, torch.int64)
+        elif k == nblk - 1:
+            d.out = ptr(res['out'])
+        entries.append((None, d))
+    table = _reduce_table(entries, dev, plan._pinned)
+    a = _lib.AioStageArgs()
+    a.x, a.jac, a.blocks = ptr(x), ptr(res['jac']), ptr(table, torch.uint8)
+    a.nblk, a.B, a.C, a.H, a.W, a.width, a.train = nblk, B, C, H, W, width, int(train)
+    a.clamp, a.alpha = plan.clamp, 0.1
+    mom = plan.blocks[0].s.bn1.momentum
+    a.momentum = -1.0 if mom is None else float(mom)
+    keep = [table, imgs]
+    if train:
+        L = _lib.lib()
+        rec = f(max(int(L.ibinn_aio_stage_workspace_floats(ctypes.byref(a))), 1))
+        a.stat_records, a.barrier = ptr(rec), ptr(_grid_barrier_counter(x), torch.int64)
+        keep.append(rec)
+    if _lib._profiler is not None:
+        _lib.set_tag('%s x%d C%d w%d @%dx%d' % ('train' if train else 'eval', nblk, C, width, H, W))
+    check(_lib.lib().ibinn_aio_stage_forward(ctypes.byref(a), stream(x)), 'aio_stage_forward')
+    _lib.set_tag('')
+    res['_keep'] = keep
+    return res
+
+
 # ------------------------------------------------------------------------------------ couplings
 
 def aio_coupling_forward(x, a, w, act_norm, act_offset, clamp, alpha=0.1):

@@ -176,6 +176,48 @@ typedef struct {
 /* g_act_offset[c] += sum_r partials[r][c],  g_act_norm[c] += sum_r partials[r][C + c]  for every entry of the table
  * (device memory, n entries), records summed in index order. */
 int ibinn_aio_param_reduce_many(const ibinn_aio_reduce_desc* table, int n, ibinn_stream_t stream);
+/* ---------------------------------------------------------------- fused AIO_Block forward (one launch for a RUN of blocks)
+ * Replaces, for a run of `nblk` consecutive AIO_Blocks of one resolution stage, everything the entry points above do in
+ * 4 launches per block (reference all_in_one_block.py:83-114 + inn_architecture.py:68-92): conv3x3 -> BN -> ReLU -> conv3x3 ->
+ * BN -> ReLU -> [Dropout2d] -> conv1x1 -> affine coupling -> soft permutation -> ActNorm.  One CTA owns one image and walks the
+ * whole run with the activations resident in shared memory; the four contractions of a block (incl. the soft permutation) are
+ * 3xTF32 tcgen05 MMAs into one TMEM region.  train = 0 (running statistics): no inter-CTA dependency, persistent over images.
+ * train = 1 (batch statistics): two grid-wide barriers per block (cooperative launch, B <= number of SMs), the raw conv
+ * outputs, subnet output, block output and batch statistics are saved for the backward entry points.
+ * `blocks` is a DEVICE array of nblk descriptors; filter images come from ibinn_wprep_many (conv3: the (2c2,width,1,1) filter;
+ * perm: the (C,C,1,1) matrix w as a 1x1 filter). */
+typedef struct ibinn_aio_block_desc {
+    const float* wprep1; const float* wprep2; const float* wprep3; const float* wprep_perm;
+    const float* bias3;                 /* (2*(C/2)) */
+    ibinn_bn_ref bn1, bn2;              /* train = 0: running mean / variance (scale_is_variance = 1); train = 1: gamma, beta, eps */
+    const float* act_norm; const float* act_offset;   /* (C) */
+    const float* drop_mask;             /* train: (B,width) Dropout2d mask (0 or 1/(1-p)) or NULL */
+    float* out;                         /* (B,C,H,W) block output, or NULL (train = 0: only needed for the last block of the run) */
+    float* h1; float* h2; float* a;     /* train: (B,width,H,W) x2 raw conv outputs, (B,2*(C/2),H,W) subnet output */
+    float* save;                        /* train: (4,width) = batch mean1, inv-std1, mean2, inv-std2 */
+    float* running_mean1; float* running_var1; int64_t* nbt1;   /* train: updated in place (may be NULL) */
+    float* running_mean2; float* running_var2; int64_t* nbt2;
+    int32_t relu_first;                 /* leading ReLU of the subnet (inn_architecture.py:72) */
+    int32_t reserved;
+} ibinn_aio_block_desc;
+
+typedef struct ibinn_aio_stage_args {
+    const float* x;                     /* (B,C,H,W) contiguous: input of the first block of the run */
+    float* jac;                         /* (B): sum of the log-dets of the run's blocks */
+    const ibinn_aio_block_desc* blocks; /* device memory */
+    int32_t nblk, B, C, H, W, width, train;
+    float clamp, alpha, momentum;       /* momentum < 0: cumulative average */
+    float* stat_records;                /* train: ibinn_aio_stage_workspace_floats() floats */
+    unsigned long long* barrier;        /* train: TWO zero-initialised 64-bit counters (arrivals, exits); the kernel leaves them at zero */
+} ibinn_aio_stage_args;
+
+size_t ibinn_sizeof_aio_block_desc(void);
+size_t ibinn_sizeof_aio_stage_args(void);
+/* 1 if this geometry / mode runs on the fused kernel, 0 if the caller must use the per-op entry points */
+int ibinn_aio_stage_supported(const ibinn_aio_stage_args* a);
+int64_t ibinn_aio_stage_workspace_floats(const ibinn_aio_stage_args* a);
+int ibinn_aio_stage_forward(const ibinn_aio_stage_args* a, ibinn_stream_t stream);
+
 /* inverse direction (all_in_one_block.py:69,93-103): u = w_inv . ((y - act_offset) * exp(-act_norm)),
  * then, with a = subnet(u[:, :C-C/2]):  u[:, C-C/2:] <- (u2 - t) * exp(-sig) in place; jac = -(...) */
 int ibinn_aio_unpermute(const float* y, const float* w_inv, const float* act_norm, const float* act_offset, float* u,

