@@ -200,6 +200,11 @@ def sub_reference(wname, batch, device, steps, warmup, budget):
 # --------------------------------------------------------------------------------------------- our arm
 
 def tag_flops(key, B):
+    m = re.search(r'\[(?:train|eval) x(\d+) C(\d+) w(\d+) @(\d+)x(\d+)', key)       # fused run of AIO blocks: 4 contractions per block
+    if m:
+        nblk, C, w, h, wd = (int(v) for v in m.groups())
+        c1, c2 = C - C // 2, C // 2
+        return 2. * B * nblk * h * wd * (9 * c1 * w + 9 * w * w + w * 2 * c2 + C * C)
     m = re.search(r'\[k(\d) s(\d) (?:[NT] )?(\d+)->(\d+) @(\d+)x(\d+)', key)
     if not m:
         return 0.
@@ -387,7 +392,7 @@ def main():
     # 3xTF32 arithmetic issues 3 MMAs per product) are exact per launch; the duration is the CUDA-event time of the same launches.
     fam = {'conv_tc_kernel (subnet conv forward + dgrad)': lambda k: k.startswith('ibinn_conv_forward[') and ' s1 ' in k,
            'wgrad_tc_kernel (subnet conv weight gradient)': lambda k: k.startswith('ibinn_conv_wgrad[') and ' s1 ' in k,
-           'block_fused_kernel (whole coupling block)': lambda k: k.startswith('ibinn_block_')}
+           'aio_stage_kernel (fused run of coupling blocks: conv1, conv2, conv3, soft permutation)': lambda k: k.startswith('ibinn_aio_stage_forward[')}
     stats = {}
     for name, pred in fam.items():
         keys = [k for k in table if pred(k)]

@@ -19,10 +19,23 @@
 #include "tc.cuh"
 
 #ifndef IBINN_EMU
+#ifdef IBINN_BLK_DBG
+// -DIBINN_BLK_DBG: globaltimer stamps of CTA 0's first image (phase boundaries of the first two blocks), read with ibinn_blk_debug_read
+__device__ unsigned long long ibinn_blk_dbg[256];
+__device__ __forceinline__ unsigned long long bgtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define BDBG(cond, i) do { if ((cond) && blockIdx.x == 0) ibinn_blk_dbg[i] = bgtime(); } while (0)
+#define BDBG_ADD(cond, i, v) do { if ((cond) && blockIdx.x == 0) ibinn_blk_dbg[i] += (v); } while (0)
+extern "C" int ibinn_blk_debug_read(unsigned long long* out) { return (int)cudaMemcpyFromSymbol(out, ibinn_blk_dbg, sizeof(unsigned long long) * 256); }
+extern "C" int ibinn_blk_debug_clear() { unsigned long long z[256] = {0}; return (int)cudaMemcpyToSymbol(ibinn_blk_dbg, z, sizeof(z)); }
+#else
+#define BDBG(cond, i)
+#define BDBG_ADD(cond, i, v)
+#endif
 namespace {
 
 constexpr int TM = 128;
-constexpr int BT_THREADS = 192;      // warps 0-3 epilogue, warp 4 MMA issuer, warp 5 filter producer
+constexpr int NEPI = 256;            // epilogue threads: warps 0-7, two warps per TMEM lane quadrant (they split the channels)
+constexpr int BT_THREADS = 320;      // warps 0-7 epilogue, warp 8 MMA issuer, warp 9 filter producer
 constexpr int MAXT = 4;              // tiles of 128 positions per image
 constexpr int MAXSLOT = 8;           // filter ring
 constexpr int MAXW = 64;             // subnet width
@@ -34,6 +47,7 @@ struct BG {
     int lbo_img;                     // bytes between k-chunks of the X1 / H1 images (rows * 16)
     int x_bytes, h_bytes, hu_bytes;  // ONE of hi / lo
     int nhu, nslot, slot_bytes;
+    int tpc1, tpc2, nch1, nch2;      // filter taps per ring chunk and chunks per 3x3 convolution
     int tap1_bytes, tap2_bytes, w3_bytes, wp_bytes;
     int tile_cols, tmem_cols;
     int off_x, off_h, off_hu, off_ring, off_xs, off_tab;
@@ -69,6 +83,12 @@ static bool bt_geometry(const ibinn_aio_stage_args& a, BG& g) {
     if (g.w3_bytes > g.slot_bytes) g.slot_bytes = g.w3_bytes;
     if (g.wp_bytes > g.slot_bytes) g.slot_bytes = g.wp_bytes;
     if (g.tap1_bytes > g.slot_bytes) g.slot_bytes = g.tap1_bytes;
+    // a ring chunk carries as many consecutive taps as fit: every tap is streamed ONCE per convolution and image (the MMA
+    // loops run tap-outer, tile-inner)
+    g.tpc1 = g.slot_bytes / g.tap1_bytes; if (g.tpc1 > 9) g.tpc1 = 9;
+    g.tpc2 = g.slot_bytes / g.tap2_bytes; if (g.tpc2 > 9) g.tpc2 = 9;
+    g.nch1 = (9 + g.tpc1 - 1) / g.tpc1;
+    g.nch2 = (9 + g.tpc2 - 1) / g.tpc2;
     int cols = 2 * g.width;
     if (2 * g.np3 > cols) cols = 2 * g.np3;
     if (2 * g.npC > cols) cols = 2 * g.npC;
@@ -83,7 +103,7 @@ static bool bt_geometry(const ibinn_aio_stage_args& a, BG& g) {
     g.off_h = off;  off += 2 * g.h_bytes;
     g.off_hu = off; off += g.nhu * 2 * g.hu_bytes;
     g.off_ring = off;
-    const int tab_bytes = (4 * MAXW + 3 * MAXCH + 8 * MAXW + 64) * 4;
+    const int tab_bytes = (4 * MAXW + 3 * MAXCH + 16 * MAXW + 64) * 4;
     const int xs_bytes = pad_to(g.C * g.HW * 4, 16);
     const int budget = 225 * 1024 - tab_bytes - xs_bytes - off;
     int nslot = budget / g.slot_bytes;
@@ -104,7 +124,7 @@ static bool bt_geometry(const ibinn_aio_stage_args& a, BG& g) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
     uint32_t r;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
@@ -128,7 +148,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
     return v[0];
 }
 
-// grid-wide barrier of the 128 epilogue threads of every CTA (train mode; all CTAs are co-resident: cooperative launch)
+// grid-wide barrier of the epilogue threads of every CTA (train mode; all CTAs are co-resident: cooperative launch)
 // `episode` = 1, 2, ... counts this launch's barriers: the counter starts at zero (the last CTA to leave the kernel resets it)
 __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned nblk, unsigned episode, int tid) {
     epi_sync();
@@ -165,8 +185,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
     float* s_sc = s_B2 + MAXW;          // [MAXCH] exp(act_norm)
     float* s_of = s_sc + MAXCH;         // [MAXCH] act_offset
     float* s_b3 = s_of + MAXCH;         // [MAXCH] conv3 bias
-    float* s_red = s_b3 + MAXCH;        // [8][MAXW] reduction scratch
-    float* s_misc = s_red + 8 * MAXW;   // [64]
+    float* s_red = s_b3 + MAXCH;        // [16][MAXW] reduction scratch
+    float* s_misc = s_red + 16 * MAXW;  // [64]
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -174,13 +194,13 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
 
     if (tid < 9) s_tapoff[tid] = (uint32_t)(g.halo + (tid / 3 - 1) * g.P + (tid % 3 - 1));
     if (tid == 0) {
-        tc::mbar_init(&x1_full, 128);
-        for (int i = 0; i < MAXT; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&h1_done[i], 128); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&hu_full[i], 128); tc::mbar_init(&u_full[i], 128); }
+        tc::mbar_init(&x1_full, NEPI);
+        for (int i = 0; i < MAXT; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&h1_done[i], NEPI); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&hu_full[i], NEPI); tc::mbar_init(&u_full[i], NEPI); }
         for (int i = 0; i < MAXSLOT; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
         tc::mbar_fence_init();
     }
-    if (warp == 4) tc::tmem_alloc(&tmem_base_s, g.tmem_cols);
+    if (warp == 8) tc::tmem_alloc(&tmem_base_s, g.tmem_cols);
     // zero the top halo rows of both images once (positions < 0 = the zero padding above the first image row); everything
     // else is rewritten per image
     {
@@ -205,7 +225,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
 
     const int nimg = TRAIN ? 1 : (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-    if (warp == 5) {
+    if (warp == 9) {
         // ================= filter producer: chunks in consumption order through the ring =================
         if (lane == 0) {
             uint32_t ci = 0;
@@ -220,10 +240,14 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                 for (int k = 0; k < p.nblk; ++k) {
                     const ibinn_aio_block_desc* d = p.blocks + k;
                     const float* w1 = d->wprep1; const float* w2 = d->wprep2; const float* w3 = d->wprep3; const float* wp = d->wprep_perm;
-                    for (int t = 0; t < nt; ++t)
-                        for (int tap = 0; tap < 9; ++tap) push(w1 + (size_t)tap * (g.tap1_bytes / 4), g.tap1_bytes);
-                    for (int t = 0; t < nt; ++t)
-                        for (int tap = 0; tap < 9; ++tap) push(w2 + (size_t)tap * (g.tap2_bytes / 4), g.tap2_bytes);
+                    for (int c = 0; c < g.nch1; ++c) {
+                        const int t0 = c * g.tpc1, n = (9 - t0 < g.tpc1) ? 9 - t0 : g.tpc1;
+                        push(w1 + (size_t)t0 * (g.tap1_bytes / 4), n * g.tap1_bytes);
+                    }
+                    for (int c = 0; c < g.nch2; ++c) {
+                        const int t0 = c * g.tpc2, n = (9 - t0 < g.tpc2) ? 9 - t0 : g.tpc2;
+                        push(w2 + (size_t)t0 * (g.tap2_bytes / 4), n * g.tap2_bytes);
+                    }
                     for (int s = 0; s <= nt; ++s) {
                         if (s < nt) push(w3, g.w3_bytes);
                         if (s >= 1) push(wp, g.wp_bytes);
@@ -231,7 +255,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                 }
         }
         __syncwarp();
-    } else if (warp == 4) {
+    } else if (warp == 8) {
         // ================= MMA issuer =================
         if (tc::elect_one()) {
             uint32_t ci = 0, nblk_seen = 0, hu_cnt[2] = {0, 0}, u_cnt[2] = {0, 0};
@@ -265,32 +289,43 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
             for (int im = 0; im < nimg; ++im)
                 for (int k = 0; k < p.nblk; ++k, ++nblk_seen) {
                     // ---- conv1
+                    const bool dbg = (im == 0 && k < 2);
+                    const int db = 128 + 32 * k;
+                    (void)dbg; (void)db;
+                    BDBG(dbg, db + 0);
                     tc::mbar_wait(&x1_full, nblk_seen & 1);
                     tc::fence_after_sync();
-                    for (int t = 0; t < nt; ++t) {
-                        const uint32_t acc_addr = tmem_d + t * g.tile_cols;
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const uint32_t s = ring_wait();
-                            const uint32_t ro = (uint32_t)(t * TM) + s_tapoff[tap];
-                            gemm(acc_addr, xh + ro * 16, xl + ro * 16, g.lbo_img, ring_a + s * g.slot_bytes, 2 * g.width * 16, g.cin_p / 8, idW2, idW1, tap == 0);
-                            ring_release(s);
-                        }
-                        tc::mma_commit(&acc_full[t]);
+                    BDBG(dbg, db + 1);
+                    for (int c = 0; c < g.nch1; ++c) {
+                        const uint32_t s = ring_wait();
+                        const int t0 = c * g.tpc1, n = (9 - t0 < g.tpc1) ? 9 - t0 : g.tpc1;
+                        for (int i = 0; i < n; ++i)
+                            for (int t = 0; t < nt; ++t) {
+                                const uint32_t ro = (uint32_t)(t * TM) + s_tapoff[t0 + i];
+                                gemm(tmem_d + t * g.tile_cols, xh + ro * 16, xl + ro * 16, g.lbo_img, ring_a + s * g.slot_bytes + i * g.tap1_bytes,
+                                     2 * g.width * 16, g.cin_p / 8, idW2, idW1, t0 + i == 0);
+                            }
+                        ring_release(s);
                     }
-                    // ---- conv2 (tile t needs the H1 rows of tiles t-1 .. t+1)
-                    for (int t = 0; t < nt; ++t) {
-                        const int need = t + 1 < nt ? t + 1 : nt - 1;
-                        tc::mbar_wait(&h1_done[need], nblk_seen & 1);
-                        tc::fence_after_sync();
-                        const uint32_t acc_addr = tmem_d + t * g.tile_cols;
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const uint32_t s = ring_wait();
-                            const uint32_t ro = (uint32_t)(t * TM) + s_tapoff[tap];
-                            gemm(acc_addr, hh + ro * 16, hl + ro * 16, g.lbo_img, ring_a + s * g.slot_bytes, 2 * g.width * 16, g.width / 8, idW2, idW1, tap == 0);
-                            ring_release(s);
-                        }
-                        tc::mma_commit(&acc_full[t]);
+                    for (int t = 0; t < nt; ++t) tc::mma_commit(&acc_full[t]);
+                    BDBG(dbg, db + 2);
+                    // ---- conv2: tap-outer, so every tile needs the whole H1 image
+                    for (int t = 0; t < nt; ++t) tc::mbar_wait(&h1_done[t], nblk_seen & 1);
+                    tc::fence_after_sync();
+                    BDBG(dbg, db + 3);
+                    for (int c = 0; c < g.nch2; ++c) {
+                        const uint32_t s = ring_wait();
+                        const int t0 = c * g.tpc2, n = (9 - t0 < g.tpc2) ? 9 - t0 : g.tpc2;
+                        for (int i = 0; i < n; ++i)
+                            for (int t = 0; t < nt; ++t) {
+                                const uint32_t ro = (uint32_t)(t * TM) + s_tapoff[t0 + i];
+                                gemm(tmem_d + t * g.tile_cols, hh + ro * 16, hl + ro * 16, g.lbo_img, ring_a + s * g.slot_bytes + i * g.tap2_bytes,
+                                     2 * g.width * 16, g.width / 8, idW2, idW1, t0 + i == 0);
+                            }
+                        ring_release(s);
                     }
+                    for (int t = 0; t < nt; ++t) tc::mma_commit(&acc_full[t]);
+                    BDBG(dbg, db + 4);
                     // ---- conv3 (tile s) and soft permutation (tile s-1), software-pipelined against the epilogue
                     for (int s = 0; s <= nt; ++s) {
                         if (s < nt) {
@@ -314,13 +349,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                             tc::mma_commit(&acc_full[t]);
                         }
                     }
+                    BDBG(dbg, db + 5);
                 }
         }
         __syncwarp();
     } else {
         // ================= warps 0-3: staging + every epilogue; thread <-> position (TMEM lane) =================
-        const int row = tid;                                  // 0..127
-        const uint32_t lane_base = tmem_d + ((uint32_t)(warp * 32) << 16);
+        const int row = tid & 127;                            // 0..127: TMEM lane; the two warps of a lane quadrant split the channels
+        const int half = tid >> 7;
+        const uint32_t lane_base = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
         const float inv_n = 1.0f / (float)g.HW;
         // position decode of this thread's row in every tile
         int pixs[MAXT];                                       // pixel index inside the image or -1
@@ -333,7 +370,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
 
         // BatchNorm coefficients of block k from given statistics (eval) -> s_A*, s_B*
         auto load_bn_eval = [&](const ibinn_bn_ref& r, float* sA, float* sB) {
-            for (int c = tid; c < g.width; c += 128) {
+            for (int c = tid; c < g.width; c += NEPI) {
                 const float sc = r.scale[c];
                 const float is = r.scale_is_variance ? rsqrtf(sc + r.eps) : sc;
                 const float A = r.gamma[c] * is;
@@ -343,17 +380,22 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
         };
 
         unsigned n_episodes = 0;
+        bool sdbg = false;      // (debug build) stamp the statistics phases of this block
+        (void)sdbg;
         // ---- train: per-image statistics of the accumulators of all tiles (+ save the raw conv output), grid-wide combine
         auto batch_stats = [&](int kphase, const ibinn_bn_ref& r, float* sA, float* sB, float* raw_out, float* save, float* rmean, float* rvar,
                                int64_t* nbt, int b, int rec_slot) {
-            const int W2 = g.width;
+            const int W2 = g.width, ng = W2 / 32;
+            // work items (tile, group of 32 channels) alternate between the two warps of a lane quadrant
             // pass 1a: per-channel sums over the image (invalid rows masked by selection); the raw values are stored on the way
             float csum[2] = {0.f, 0.f};                        // lane <-> channel (group of 32)
             for (int t = 0; t < nt; ++t) {
                 tc::mbar_wait(&acc_full[t], kphase & 1);
                 tc::fence_after_sync();
                 const bool valid = pixs[t] >= 0;
-                for (int c0 = 0; c0 < W2; c0 += 32) {
+                for (int gi = 0; gi < ng; ++gi) {
+                    if (((t * ng + gi) & 1) != half) continue;
+                    const int c0 = gi * 32;
                     float v[32];
 #pragma unroll
                     for (int c8 = 0; c8 < 32; c8 += 8) {
@@ -369,18 +411,28 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
 #pragma unroll
                         for (int i = 0; i < 32; ++i) dst[(size_t)i * g.HW] = v[i];
                     }
-                    csum[c0 >> 5] += warp_colsum32(v, lane);
+                    const float cs = warp_colsum32(v, lane);
+                    if (gi == 0) csum[0] += cs; else csum[1] += cs;
                 }
             }
-            for (int c0 = 0; c0 < W2; c0 += 32) s_red[warp * MAXW + c0 + lane] = csum[c0 >> 5];
+            BDBG(sdbg, 16 + 8 * kphase + 0);
+            s_red[warp * MAXW + lane] = csum[0];
+            if (ng > 1) s_red[warp * MAXW + 32 + lane] = csum[1];
             epi_sync();
-            if (tid < W2) s_red[4 * MAXW + tid] = ((s_red[tid] + s_red[MAXW + tid]) + (s_red[2 * MAXW + tid] + s_red[3 * MAXW + tid])) * inv_n;
+            if (tid < W2) {
+                float a = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) a += s_red[w8 * MAXW + tid];
+                s_red[8 * MAXW + tid] = a * inv_n;
+            }
             epi_sync();
             // pass 1b: M2 about the image mean
             float csq[2] = {0.f, 0.f};
             for (int t = 0; t < nt; ++t) {
                 const bool valid = pixs[t] >= 0;
-                for (int c0 = 0; c0 < W2; c0 += 32) {
+                for (int gi = 0; gi < ng; ++gi) {
+                    if (((t * ng + gi) & 1) != half) continue;
+                    const int c0 = gi * 32;
                     float v[32];
 #pragma unroll
                     for (int c8 = 0; c8 < 32; c8 += 8) {
@@ -390,46 +442,57 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                         tc::tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float dlt = (a8[i] + b8[i]) - s_red[4 * MAXW + c0 + c8 + i];
+                            const float dlt = (a8[i] + b8[i]) - s_red[8 * MAXW + c0 + c8 + i];
                             v[c8 + i] = valid ? dlt * dlt : 0.f;
                         }
                     }
-                    csq[c0 >> 5] += warp_colsum32(v, lane);
+                    const float cs = warp_colsum32(v, lane);
+                    if (gi == 0) csq[0] += cs; else csq[1] += cs;
                 }
             }
-            for (int c0 = 0; c0 < W2; c0 += 32) s_red[warp * MAXW + c0 + lane] = csq[c0 >> 5];
+            BDBG(sdbg, 16 + 8 * kphase + 1);
+            s_red[warp * MAXW + lane] = csq[0];
+            if (ng > 1) s_red[warp * MAXW + 32 + lane] = csq[1];
             epi_sync();
             float* rec = p.stat_records + ((size_t)rec_slot * p.B + b) * 2 * W2;
             if (tid < W2) {
-                rec[tid] = s_red[4 * MAXW + tid];
-                rec[W2 + tid] = (s_red[tid] + s_red[MAXW + tid]) + (s_red[2 * MAXW + tid] + s_red[3 * MAXW + tid]);
+                float a = 0.f;
+#pragma unroll
+                for (int w8 = 0; w8 < 8; ++w8) a += s_red[w8 * MAXW + tid];
+                rec[tid] = s_red[8 * MAXW + tid];
+                rec[W2 + tid] = a;
             }
+            BDBG(sdbg, 16 + 8 * kphase + 2);
             grid_barrier(p.barrier, gridDim.x, ++n_episodes, tid);
+            BDBG(sdbg, 16 + 8 * kphase + 3);
             // combine the B records in fixed order: with K = mean of record 0, d_b = mean_b - K:
             //   mean = K + sum d_b / B,   M2 = sum M2_b + n (sum d_b^2 - (sum d_b)^2 / B)
             {
-                const int c = tid % W2, part = tid / W2, nparts = 128 / W2;
+                const int c = tid % W2, part = tid / W2, nparts = NEPI / W2;
                 const float* base = p.stat_records + (size_t)rec_slot * p.B * 2 * W2;
                 const float K = ldcg(base + c);
+                const float gam = tid < W2 ? r.gamma[c] : 0.f, bet = tid < W2 ? r.beta[c] : 0.f;
                 float s1 = 0.f, s2 = 0.f, m2 = 0.f;
-                for (int b0 = part; b0 < p.B; b0 += nparts * 8) {
-                    float mb[8], qb[8];
+                constexpr int UB = 16;          // loads in flight per thread: one L2 round trip per batch of 16 records
+                for (int b0 = part; b0 < p.B; b0 += nparts * UB) {
+                    float mb[UB], qb[UB];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < UB; ++u) {
                         const int bb = b0 + u * nparts;
-                        mb[u] = bb < p.B ? ldcg(base + (size_t)bb * 2 * W2 + c) : K;
+                        mb[u] = bb < p.B ? ldcg(base + (size_t)bb * 2 * W2 + c) : 0.f;
                         qb[u] = bb < p.B ? ldcg(base + (size_t)bb * 2 * W2 + W2 + c) : 0.f;
                     }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const float dlt = mb[u] - K;
+                    for (int u = 0; u < UB; ++u) {
+                        const int bb = b0 + u * nparts;
+                        const float dlt = bb < p.B ? mb[u] - K : 0.f;
                         s1 += dlt;
                         s2 = fmaf(dlt, dlt, s2);
                         m2 += qb[u];
                     }
                 }
                 epi_sync();                                   // s_red is free again
-                s_red[(part * 3 + 0) * W2 + c] = s1;        // [nparts][3][W2]: 128 / W2 * 3 * W2 = 384 floats
+                s_red[(part * 3 + 0) * W2 + c] = s1;        // [nparts][3][W2]: NEPI / W2 * 3 * W2 = 768 floats
                 s_red[(part * 3 + 1) * W2 + c] = s2;
                 s_red[(part * 3 + 2) * W2 + c] = m2;
                 epi_sync();
@@ -442,9 +505,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                     if (tot < 0.f) tot = 0.f;
                     const float var_b = tot / N;
                     const float is = 1.0f / sqrtf(var_b + r.eps);
-                    const float A = r.gamma[c] * is;
+                    const float A = gam * is;
                     sA[c] = A;
-                    sB[c] = r.beta[c] - mean * A;
+                    sB[c] = bet - mean * A;
                     if (blockIdx.x == 0) {
                         save[c] = mean;
                         save[W2 + c] = is;
@@ -458,6 +521,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                     }
                 }
                 epi_sync();
+                BDBG(sdbg, 16 + 8 * kphase + 4);
                 if (blockIdx.x == 0 && tid == 0 && nbt) *nbt = *nbt + 1;
             }
         };
@@ -469,7 +533,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                                       bool store) {
             const bool valid = pixs[t] >= 0;
             const int W2 = g.width;
-            for (int c8 = 0; c8 < W2; c8 += 8) {
+            for (int c8 = half * 8; c8 < W2; c8 += 16) {       // the two warps of a lane quadrant take alternate groups of 8 channels
                 float a8[8], b8[8], hi[8], lo[8];
                 tc::tmem_ld8(lane_base + t * g.tile_cols + c8, a8);
                 tc::tmem_ld8(lane_base + t * g.tile_cols + W2 + c8, b8);
@@ -497,18 +561,23 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
             // ---- stage the first block's input: fp32 copy for the coupling + X1 operand image
             {
                 const float* xb = p.x + (size_t)b * g.C * g.HW;
-                for (int i = tid; i < g.C * g.HW; i += 128) xs[i] = __ldg(xb + i);
+                for (int i = tid; i < g.C * g.HW; i += NEPI) xs[i] = __ldg(xb + i);
                 epi_sync();
             }
             for (int k = 0; k < p.nblk; ++k, ++blk_seen) {
                 const ibinn_aio_block_desc* d = p.blocks + k;
                 const bool last = (k == p.nblk - 1);
                 epi_sync();                                   // every thread is done with the previous block's tables
+                const bool dbg = (im == 0 && k < 2 && tid == 0);
+                const int db = 32 * k;
+                (void)dbg; (void)db;
+                sdbg = (im == 0 && k == 1 && tid == 0);
+                BDBG(dbg, db + 0);
                 // X1 image of this block from xs (the previous block's epilogue has already written it for k > 0)
                 if (k == 0) {
                     const int nk4 = g.cin_p / 4;
                     const bool rf = d->relu_first != 0;
-                    for (int i = tid; i < nk4 * g.S; i += 128) {
+                    for (int i = tid; i < nk4 * g.S; i += NEPI) {
                         const int k4 = i / g.S, q = i - k4 * g.S;
                         const int yy = q / g.P, xx = q - yy * g.P;
                         float hi[4], lo[4];
@@ -527,8 +596,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                     }
                 }
                 // per-block tables
-                for (int c = tid; c < g.C; c += 128) { s_sc[c] = expf(d->act_norm[c]); s_of[c] = d->act_offset[c]; }
-                for (int c = tid; c < 2 * g.c2; c += 128) s_b3[c] = d->bias3[c];
+                for (int c = tid; c < g.C; c += NEPI) { s_sc[c] = expf(d->act_norm[c]); s_of[c] = d->act_offset[c]; }
+                for (int c = tid; c < 2 * g.c2; c += NEPI) s_b3[c] = d->bias3[c];
                 if (!TRAIN) { load_bn_eval(d->bn1, s_A1, s_B1); load_bn_eval(d->bn2, s_A2, s_B2); }
                 if (warp == 3) {
                     float v = 0.f;
@@ -539,20 +608,25 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                 tc::fence_async_smem();
                 mbar_arrive(&x1_full);
                 epi_sync();                                   // tables visible to all epilogue threads
+                BDBG(dbg, db + 1);
 
                 const float* dmask = (TRAIN && d->drop_mask) ? d->drop_mask + (size_t)b * g.width : nullptr;
+                const bool rf_next = !last && (d + 1)->relu_first != 0;      // leading ReLU of the NEXT block's subnet
                 // ---- B: conv1 accumulators -> H1 image
                 if (TRAIN) batch_stats(0, d->bn1, s_A1, s_B1, d->h1, d->save, d->running_mean1, d->running_var1, d->nbt1, b, 0);
                 for (int t = 0; t < nt; ++t) {
                     if (!TRAIN) { tc::mbar_wait(&acc_full[t], 0); tc::fence_after_sync(); }
+                    if (t == 0) BDBG(dbg, db + 2);
                     const int q = t * TM + row;
                     bn_relu_to_operand(t, s_A1, s_B1, nullptr, h_hi + (g.halo + q) * 16, h_lo + (g.halo + q) * 16, g.lbo_img, q < g.S);
                     tc::fence_before_sync();
                     tc::fence_async_smem();
                     mbar_arrive(&h1_done[t]);
                 }
+                BDBG(dbg, db + 3);
                 // ---- train: statistics of conv2 need all of its tiles before any of them can be normalised
                 if (TRAIN) batch_stats(1, d->bn2, s_A2, s_B2, d->h2, d->save + 2 * g.width, d->running_mean2, d->running_var2, d->nbt2, b, 1);
+                BDBG(dbg, db + 4);
                 // ---- pipelined tail: H(s-2), D(s), F(s-1)
                 for (int s = 0; s < nt + 2; ++s) {
                     if (s >= 2) {
@@ -560,11 +634,12 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                         const int t = s - 2;
                         tc::mbar_wait(&acc_full[t], 1);
                         tc::fence_after_sync();
+                        if (s == 2) BDBG(dbg, db + 10);
                         const int pix = pixs[t];
                         const int q = t * TM + row;
                         float* og = (d->out && pix >= 0) ? d->out + (size_t)b * g.C * g.HW + pix : nullptr;
                         const int nk4 = g.cin_p / 4;
-                        for (int c8 = 0; c8 < g.npC; c8 += 8) {
+                        for (int c8 = half * 8; c8 < g.npC; c8 += 16) {
                             float a8[8], b8[8], o8[8];
                             tc::tmem_ld8(lane_base + t * g.tile_cols + c8, a8);
                             tc::tmem_ld8(lane_base + t * g.tile_cols + g.npC + c8, b8);
@@ -582,9 +657,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                                 }
                             }
                             if (!last && q < g.S) {
-                                // next block's X1 image: relu(out[:c1]) (every block after the first of the network has the leading ReLU;
-                                // the flag of the NEXT block decides)
-                                const bool rf = (d + 1)->relu_first != 0;
+                                // next block's X1 image: [relu](out[:c1]), zeros at the padding positions
+                                const bool rf = rf_next;
 #pragma unroll
                                 for (int h4 = 0; h4 < 2; ++h4) {
                                     const int k4 = c8 / 4 + h4;
@@ -610,22 +684,25 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                         const int t = s, sl = t % g.nhu;
                         tc::mbar_wait(&acc_full[t], 1);
                         tc::fence_after_sync();
+                        if (s == 0) BDBG(dbg, db + 5);
                         unsigned char* dh = hu + (size_t)sl * 2 * g.hu_bytes + row * 16;
                         bn_relu_to_operand(t, s_A2, s_B2, dmask, dh, dh + g.hu_bytes, TM * 16, true);
                         tc::fence_before_sync();
                         tc::fence_async_smem();
                         mbar_arrive(&hu_full[sl]);
+                        if (s == 0) BDBG(dbg, db + 6);
                     }
                     if (s >= 1 && s - 1 < nt) {
                         // F: subnet output -> affine coupling -> U tile (same slot), log-det
                         const int t = s - 1, sl = t % g.nhu;
                         tc::mbar_wait(&acc_full[t], 0);
                         tc::fence_after_sync();
+                        if (s == 1) BDBG(dbg, db + 7);
                         const int pix = pixs[t];
                         const uint32_t tb = lane_base + t * g.tile_cols;
                         unsigned char* uh = hu + (size_t)sl * 2 * g.hu_bytes + row * 16;
                         float* ag = (TRAIN && d->a && pix >= 0) ? d->a + (size_t)b * 2 * g.c2 * g.HW + pix : nullptr;
-                        for (int k4 = 0; k4 < g.kC / 4; ++k4) {
+                        for (int k4 = half; k4 < g.kC / 4; k4 += 2) {
                             float sv[4], tv[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -660,8 +737,10 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                         tc::fence_before_sync();
                         tc::fence_async_smem();
                         mbar_arrive(&u_full[sl]);
+                        if (s == 1) BDBG(dbg, db + 8);
                     }
                 }
+                BDBG(dbg, db + 9);
                 // xs / X1 of the next block are complete in shared memory; the arrive on x1_full at the top of the next
                 // iteration (after its epi_sync) publishes them to the MMA issuer
             }
@@ -672,7 +751,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                 if (lane == 0) s_misc[warp] = w;
                 if (warp == 3 && lane == 0) s_misc[8] = san_tot;
                 epi_sync();
-                if (tid == 0) p.jac[b] = ((s_misc[0] + s_misc[1]) + (s_misc[2] + s_misc[3])) + (float)g.HW * s_misc[8];
+                if (tid == 0) p.jac[b] = (((s_misc[0] + s_misc[1]) + (s_misc[2] + s_misc[3])) + ((s_misc[4] + s_misc[5]) + (s_misc[6] + s_misc[7]))) + (float)g.HW * s_misc[8];
                 epi_sync();
             }
         }
@@ -689,7 +768,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 4) tc::tmem_dealloc(tmem_d, g.tmem_cols);
+    if (warp == 8) tc::tmem_dealloc(tmem_d, g.tmem_cols);
 }
 
 }  // namespace

@@ -1,0 +1,52 @@
+"""Phase time line of the fused AIO-run kernel (csrc/block_tc.cu built with -DIBINN_BLK_DBG; globaltimer stamps of CTA 0,
+first image, first two blocks).  Usage on the GPU box:
+    IBINN_B200_LIB=ibinn_b200/csrc/libibinn_b200_dbg.so python scripts/blk_timeline.py"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'tests'), os.path.join(ROOT, 'oracle')]
+from test_fused_stage import make_run       # noqa: E402
+from ibinn_b200 import _lib, ops            # noqa: E402
+
+E = ['top', 'x1+tables', 'conv1 done(t0)', 'B done', 'stats2 done', 'conv2 done(t0)', 'D0 done', 'conv3 done(t0)', 'F0 done', 'tail end', 'perm done(t0)']
+M = ['start', 'x1_full seen', 'conv1 issued', 'h1 seen', 'conv2 issued', 'tail issued']
+
+
+def main():
+    dev = torch.device('cuda:0')
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for (C, H, width) in ((12, 16, 32), (48, 8, 64)):
+        for train, B in ((False, 296), (True, 128)):
+            blocks = make_run(C, H, width, 4)
+            for b in blocks:
+                b.to(dev).train(train)
+            plan = ops.AioStagePlan(blocks)
+            x = torch.randn(B, C, H, H, device=dev)
+            for it in range(3):
+                L.ibinn_blk_debug_clear()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ops.aio_stage_forward(plan, x, train, [None] * 4)
+                e1.record()
+                torch.cuda.synchronize()
+            buf = (ctypes.c_ulonglong * 256)()
+            L.ibinn_blk_debug_read(buf)
+            v = np.array(list(buf), dtype=np.float64)
+            t0 = v[0]
+            print('\n== C=%d H=%d width=%d %s B=%d: kernel %.1f us (4 blocks)' % (C, H, width, 'train' if train else 'eval', B, e0.elapsed_time(e1) * 1e3))
+            for k in range(2):
+                print(' block %d epilogue: ' % k + ', '.join('%s %.2f' % (n, (v[32 * k + i] - t0) / 1e3) for i, n in enumerate(E) if v[32 * k + i] > 0))
+                print(' block %d mma     : ' % k + ', '.join('%s %.2f' % (n, (v[128 + 32 * k + i] - t0) / 1e3) for i, n in enumerate(M) if v[128 + 32 * k + i] > 0))
+            if train:
+                S = ['pass1a', 'pass1b', 'records', 'barrier', 'combine']
+                for ph in range(2):
+                    print(' block 1 stats %d  : ' % ph + ', '.join('%s %.2f' % (n, (v[16 + 8 * ph + i] - t0) / 1e3) for i, n in enumerate(S)))
+
+
+if __name__ == '__main__':
+    main()
