@@ -244,6 +244,24 @@ class TrainStep:
         self.reduce_group = int(os.environ.get('IBINN_WGRAD_REDUCE_GROUP', '0'))
         self.reduce_stream = torch.cuda.Stream() if self.side_streams and self.reduce_group > 0 else None
         self._pinned_groups = []
+        # Gradient exchange: the flat gradient is laid out in parameter order, so everything from the first
+        # fully connected coupling block to the end (84 % of the payload: the FC subnets, then mu and phi) is complete as soon as
+        # that block's backward has run.  Its all-reduce starts there, on a side stream, and runs under the backward pass of the 56
+        # convolutional blocks; only the remaining 16 % is reduced after the backward pass.
+        self.early_start, self._first_glow, self.comm_stream, self._early_issued = None, None, None, False
+        if self.world > 1 and os.environ.get('IBINN_OVERLAP_ALLREDUCE', '1') != '0':
+            from .modules import GLOWCouplingBlock
+            glows = [m for m in model.inn.modules() if isinstance(m, GLOWCouplingBlock)]
+            if glows:
+                first = glows[0]
+                p0 = next(p for p in first.parameters() if p.requires_grad)
+                off = (p0.data.data_ptr() - self.flat.flat.data_ptr()) // 4
+                tail = {id(p) for gl in glows for p in gl.parameters()} | {id(model.mu), id(model.phi)}
+                after = [p for g in model.optimizer.param_groups for p in g['params']
+                         if p.requires_grad and (p.data.data_ptr() - self.flat.flat.data_ptr()) // 4 >= off]
+                if all(id(p) in tail for p in after) and 0 < off < self.flat.grad.numel():
+                    self.early_start, self._first_glow = int(off), first
+                    self.comm_stream = torch.cuda.Stream() if dev.type == 'cuda' else None
         self._g1 = self._g2 = None
         self.out = None
         self.launches = None
@@ -297,6 +315,9 @@ class TrainStep:
         ops.DEFERRED_WGRAD = pending = []
         ops.DEFERRED_AIO = pending_aio = [] if self.x.is_cuda else None
         ops.WGRAD_STREAMS = self.side_streams
+        from . import functions as Fn
+        self._early_issued = False
+        Fn.AFTER_GLOW_BACKWARD = self._early_allreduce if self.early_start is not None else None
         grouped = self.side_streams is not None and self.reduce_stream is not None
         if grouped:
             ops.WGRAD_REDUCE = dict(stream=self.reduce_stream, group=self.reduce_group, pinned=self._pinned_groups, upto=0, keep=[])
@@ -307,6 +328,7 @@ class TrainStep:
                 self._reduce_keep = ops.WGRAD_REDUCE['keep']
             ops.join_wgrad_streams()
         finally:
+            Fn.AFTER_GLOW_BACKWARD = None
             ops.DEFERRED_WGRAD = None
             ops.DEFERRED_AIO = None
             ops.WGRAD_STREAMS = None
@@ -319,9 +341,28 @@ class TrainStep:
         self._pending = pending            # keeps the record workspaces alive until the reduction has run
         self.out = {k: losses[k].detach() for k in ('L_x_tr', 'L_y_tr', 'acc_tr', 'L_cNLL_tr')}
 
+    def _early_allreduce(self, blk):
+        """called at the end of a GLOW block's backward: when it is the first one (forward order), the tail of the flat
+        gradient is final; reduce it on the communication stream while the convolutional blocks run their backward"""
+        if blk is not self._first_glow or self._early_issued:
+            return
+        tail = self.flat.grad[self.early_start:]
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                dist.all_reduce(tail, op=dist.ReduceOp.SUM, group=self.pg)
+        else:
+            dist.all_reduce(tail, op=dist.ReduceOp.SUM, group=self.pg)
+        self._early_issued = True
+
     def _reduce(self):
         if self.world > 1:
-            dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
+            if self._early_issued:
+                dist.all_reduce(self.flat.grad[:self.early_start], op=dist.ReduceOp.SUM, group=self.pg)
+                if self.comm_stream is not None:
+                    torch.cuda.current_stream().wait_stream(self.comm_stream)
+            else:
+                dist.all_reduce(self.flat.grad, op=dist.ReduceOp.SUM, group=self.pg)
 
     def _update(self):
         # the all-reduce sums; the mean gradient is grad / world (folded into the clip and the update)
@@ -358,12 +399,32 @@ class TrainStep:
         self._restore(snap)
         torch.cuda.synchronize()
         n0 = L.ibinn_launch_count()
-        self._g1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._g1, stream=s):
-            self._fwd_bwd()
-        self._g2 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self._g2, pool=self._g1.pool(), stream=s):
-            self._update()
+        self._one_graph = False
+        if self.world > 1 and os.environ.get('IBINN_NCCL_IN_GRAPH', '1') != '0':
+            # the whole step, collectives included, as ONE graph: no host round trip between backward, all-reduce and update
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=s):
+                    self._fwd_bwd()
+                    self._reduce()
+                    self._update()
+                self._g1, self._g2, self._one_graph = g, None, True
+            except Exception as e:      # noqa: BLE001  (an NCCL build without capture support): two graphs around the collective
+                import warnings
+                warnings.warn('ibinn_b200: capturing the gradient all-reduce failed (%s); falling back to two graphs' % e)
+                torch.cuda.synchronize()
+                self._restore(snap)
+                self.flat.zero_grad()
+        if not self._one_graph:
+            early = self.early_start
+            self.early_start = None          # a collective between two graphs cannot start inside the first one
+            self._g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._g1, stream=s):
+                self._fwd_bwd()
+            self._g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._g2, pool=self._g1.pool(), stream=s):
+                self._update()
+            self._early_for_eager = early
         n1 = L.ibinn_launch_count()
         self.launches = int(n1 - n0)
         torch.cuda.synchronize()
@@ -380,8 +441,9 @@ class TrainStep:
             if self._g1 is None:
                 self.capture()
             self._g1.replay()
-            self._reduce()
-            self._g2.replay()
+            if not getattr(self, '_one_graph', False):
+                self._reduce()
+                self._g2.replay()
         else:
             self._eager()
         return self.out
