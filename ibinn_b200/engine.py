@@ -248,8 +248,9 @@ class TrainStep:
         # fully connected coupling block to the end (84 % of the payload: the FC subnets, then mu and phi) is complete as soon as
         # that block's backward has run.  Its all-reduce starts there, on a side stream, and runs under the backward pass of the 56
         # convolutional blocks; only the remaining 16 % is reduced after the backward pass.
-        self.early_start, self._first_glow, self.comm_stream, self._early_issued = None, None, None, False
-        if self.world > 1 and os.environ.get('IBINN_OVERLAP_ALLREDUCE', '1') != '0':
+        self.early_start, self._first_glow, self.comm_stream, self._early_issued, self._glow_idx = None, None, None, False, None
+        force_split = os.environ.get('IBINN_FORCE_SPLIT_BACKWARD', '0') == '1'      # one-GPU validation of the two-piece backward
+        if (self.world > 1 or force_split) and os.environ.get('IBINN_OVERLAP_ALLREDUCE', '1') != '0':
             from .modules import GLOWCouplingBlock
             glows = [m for m in model.inn.modules() if isinstance(m, GLOWCouplingBlock)]
             if glows:
@@ -261,8 +262,10 @@ class TrainStep:
                          if p.requires_grad and (p.data.data_ptr() - self.flat.flat.data_ptr()) // 4 >= off]
                 if all(id(p) in tail for p in after) and 0 < off < self.flat.grad.numel():
                     self.early_start, self._first_glow = int(off), first
+                    self._glow_idx = [i for i, mm in enumerate(model.inn.module_list) if mm is first][0]
                     self.comm_stream = torch.cuda.Stream() if dev.type == 'cuda' else None
-        self._g1 = self._g2 = None
+        self._g1 = self._g1b = self._g2 = None
+        self._one_graph = False
         self.out = None
         self.launches = None
 
@@ -301,50 +304,75 @@ class TrainStep:
             self.wprep.invalidate()
 
     # -- pieces ---------------------------------------------------------------------------------
-    def _fwd_bwd(self):
+    def _fwd_bwd_a(self):
+        """forward, loss, and the backward pass down to the input of the first fully connected coupling block: after this the
+        tail of the flat gradient (FC subnets, mu, phi) is final"""
         self.flat.zero_grad()
         if self.wprep is not None:
             self.wprep.refresh()
         if self.model.inn.training:
             self.masks.redraw()
-        losses = self.model(self.x, self.y)
+        self.model.inn.cut_before = self._glow_idx if self.early_start is not None else None
+        try:
+            losses = self.model(self.x, self.y)
+        finally:
+            self.model.inn.cut_before = None
         if self.class_nll:
             loss = 2. * losses['L_cNLL_tr']
         else:
             loss = self.bx * losses['L_x_tr'] - self.by * losses['L_y_tr']
-        ops.DEFERRED_WGRAD = pending = []
-        ops.DEFERRED_AIO = pending_aio = [] if self.x.is_cuda else None
+        ops.DEFERRED_WGRAD = self._pending = []
+        ops.DEFERRED_AIO = self._pending_aio = [] if self.x.is_cuda else None
         ops.WGRAD_STREAMS = self.side_streams
-        from . import functions as Fn
-        self._early_issued = False
-        Fn.AFTER_GLOW_BACKWARD = self._early_allreduce if self.early_start is not None else None
-        grouped = self.side_streams is not None and self.reduce_stream is not None
-        if grouped:
+        self._grouped = self.side_streams is not None and self.reduce_stream is not None
+        if self._grouped:
             ops.WGRAD_REDUCE = dict(stream=self.reduce_stream, group=self.reduce_group, pinned=self._pinned_groups, upto=0, keep=[])
+        self.out = {k: losses[k].detach() for k in ('L_x_tr', 'L_y_tr', 'acc_tr', 'L_cNLL_tr')}
+        self._split = None
         try:
-            loss.backward()
-            if grouped:
+            cut = self.model.inn._cut
+            if cut:
+                # the graph above the cut (head, FC block) is complete in itself: its backward leaves the gradients of the detached
+                # leaves, and every parameter gradient of the tail in flat.grad
+                loss.backward()
+                self._split = ([t for t, _ in cut], [d.grad for _, d in cut])
+                self.model.inn._cut = []
+            else:
+                self._split = ([loss], None)
+        except BaseException:
+            self._clear_backward_state()
+            raise
+
+    def _fwd_bwd_b(self):
+        """the rest of the backward pass (DCT, the convolutional blocks) and the deferred record reductions"""
+        t, g = self._split
+        self._split = None
+        try:
+            torch.autograd.backward(t, grad_tensors=g)
+            if self._grouped:
                 ops.flush_wgrad_group(final=True)
                 self._reduce_keep = ops.WGRAD_REDUCE['keep']
             ops.join_wgrad_streams()
         finally:
-            Fn.AFTER_GLOW_BACKWARD = None
-            ops.DEFERRED_WGRAD = None
-            ops.DEFERRED_AIO = None
-            ops.WGRAD_STREAMS = None
-            ops.WGRAD_REDUCE = None
-        if pending_aio:
-            self._pinned_aio = ops.flush_deferred_aio(pending_aio, self.x, getattr(self, '_pinned_aio', None))
-            self._pending_aio = pending_aio    # keeps the records alive until the reduction has run
-        if not grouped:
-            self._pinned = ops.flush_deferred_wgrad(pending, self.x, getattr(self, '_pinned', None))
-        self._pending = pending            # keeps the record workspaces alive until the reduction has run
-        self.out = {k: losses[k].detach() for k in ('L_x_tr', 'L_y_tr', 'acc_tr', 'L_cNLL_tr')}
+            self._clear_backward_state()
+        if self._pending_aio:
+            self._pinned_aio = ops.flush_deferred_aio(self._pending_aio, self.x, getattr(self, '_pinned_aio', None))
+        if not self._grouped:
+            self._pinned = ops.flush_deferred_wgrad(self._pending, self.x, getattr(self, '_pinned', None))
+        # self._pending / self._pending_aio keep the record workspaces alive until the reductions have run
 
-    def _early_allreduce(self, blk):
-        """called at the end of a GLOW block's backward: when it is the first one (forward order), the tail of the flat
-        gradient is final; reduce it on the communication stream while the convolutional blocks run their backward"""
-        if blk is not self._first_glow or self._early_issued:
+    @staticmethod
+    def _clear_backward_state():
+        ops.DEFERRED_WGRAD = None
+        ops.DEFERRED_AIO = None
+        ops.WGRAD_STREAMS = None
+        ops.WGRAD_REDUCE = None
+
+    def _early_allreduce(self):
+        """between the two pieces of the backward pass: reduce the (final) tail of the flat gradient on the communication
+        stream, under the backward pass of the convolutional blocks"""
+        self._early_issued = False
+        if self.world <= 1 or self.early_start is None:
             return
         tail = self.flat.grad[self.early_start:]
         if self.comm_stream is not None:
@@ -354,6 +382,11 @@ class TrainStep:
         else:
             dist.all_reduce(tail, op=dist.ReduceOp.SUM, group=self.pg)
         self._early_issued = True
+
+    def _fwd_bwd(self):
+        self._fwd_bwd_a()
+        self._early_allreduce()
+        self._fwd_bwd_b()
 
     def _reduce(self):
         if self.world > 1:
@@ -400,31 +433,32 @@ class TrainStep:
         torch.cuda.synchronize()
         n0 = L.ibinn_launch_count()
         self._one_graph = False
-        if self.world > 1 and os.environ.get('IBINN_NCCL_IN_GRAPH', '1') != '0':
-            # the whole step, collectives included, as ONE graph: no host round trip between backward, all-reduce and update
-            try:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=s):
-                    self._fwd_bwd()
-                    self._reduce()
-                    self._update()
-                self._g1, self._g2, self._one_graph = g, None, True
-            except Exception as e:      # noqa: BLE001  (an NCCL build without capture support): two graphs around the collective
-                import warnings
-                warnings.warn('ibinn_b200: capturing the gradient all-reduce failed (%s); falling back to two graphs' % e)
-                torch.cuda.synchronize()
-                self._restore(snap)
-                self.flat.zero_grad()
-        if not self._one_graph:
-            early = self.early_start
-            self.early_start = None          # a collective between two graphs cannot start inside the first one
-            self._g1 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._g1, stream=s):
+        if self.world > 1 and os.environ.get('IBINN_NCCL_IN_GRAPH', '0') == '1':
+            # opt-in: the whole step, collectives included, as ONE graph (needs an NCCL build that supports stream capture)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=s):
                 self._fwd_bwd()
+                self._reduce()
+                self._update()
+            self._g1, self._g1b, self._g2, self._one_graph = g, None, None, True
+        else:
+            # the collectives stay outside the graphs: [forward + head / FC backward] -> early all-reduce of the gradient tail on the
+            # communication stream -> [rest of the backward pass] -> all-reduce of the rest -> [clip + SGD]
+            self._g1 = torch.cuda.CUDAGraph()
+            if self.early_start is None:
+                with torch.cuda.graph(self._g1, stream=s):          # nothing to exchange in between: one graph for forward + backward
+                    self._fwd_bwd_a()
+                    self._fwd_bwd_b()
+                self._g1b = None
+            else:
+                with torch.cuda.graph(self._g1, stream=s):
+                    self._fwd_bwd_a()
+                self._g1b = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._g1b, pool=self._g1.pool(), stream=s):
+                    self._fwd_bwd_b()
             self._g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._g2, pool=self._g1.pool(), stream=s):
                 self._update()
-            self._early_for_eager = early
         n1 = L.ibinn_launch_count()
         self.launches = int(n1 - n0)
         torch.cuda.synchronize()
@@ -441,7 +475,10 @@ class TrainStep:
             if self._g1 is None:
                 self.capture()
             self._g1.replay()
-            if not getattr(self, '_one_graph', False):
+            if not self._one_graph:
+                if self._g1b is not None:
+                    self._early_allreduce()
+                    self._g1b.replay()
                 self._reduce()
                 self._g2.replay()
         else:

@@ -73,6 +73,11 @@ class ReversibleGraphNet(nn.Module):
         # geometry (functions.AIOStageFn); `fused_stages = False` (or IBINN_FUSED=0) keeps one node = one autograd function
         self.fused_stages = os.environ.get('IBINN_FUSED', '1') != '0'
         self._runs = None
+        # engine.TrainStep: cut the autograd graph in front of node `cut_before` (the first fully connected block), so that the
+        # backward pass can run in two pieces with the gradient all-reduce of the tail started in between.  `_cut` then holds
+        # [(tensor below the cut, detached leaf above it), ...] for the activation and for the summed log-dets of the nodes below.
+        self.cut_before = None
+        self._cut = []
         if verbose:
             for n in node_list:
                 print(n.name, n.output_dims)
@@ -113,12 +118,17 @@ class ReversibleGraphNet(nn.Module):
             return h
         if self.fused_stages and self._runs is None:
             self._runs = self._find_runs()
+        self._cut = []
         k = 0
         while k < n:
             m = self.module_list[k]
             if m is None:
                 k += 1
                 continue
+            if k == self.cut_before and torch.is_grad_enabled() and h.requires_grad:
+                hd = h.detach().requires_grad_(True)
+                self._cut.append((h, hd))
+                h = hd
             plan = self._runs.get(k) if self.fused_stages else None
             if plan is not None and (m.training or not torch.is_grad_enabled()) and plan.supported(h, m.training):
                 # the whole run in one launch; its log-det is reported by the first block of the run
@@ -140,7 +150,7 @@ class ReversibleGraphNet(nn.Module):
         """Drop every reference to autograd graphs of earlier passes (cached per-node log-dets, node
         inputs).  engine.TrainStep calls this before CUDA-graph capture: a live old graph keeps the
         parameters' gradient accumulators -- and the stream they were created on -- alive."""
-        self._node_inputs, self._jacs = {}, []
+        self._node_inputs, self._jacs, self._cut = {}, [], []
         for m in self.module_list:
             if m is not None and hasattr(m, 'last_jac') and torch.is_tensor(m.last_jac):
                 m.last_jac = None
@@ -148,13 +158,21 @@ class ReversibleGraphNet(nn.Module):
     def log_jacobian(self, x=None, c=None, rev=False, run_forward=True, intermediate_outputs=False):
         if run_forward:
             self.forward(x, rev=rev)
-        const, tens = 0., []
+        const, tens, below = 0., [], []
+        cutting = bool(self._cut) and not rev
         for k, h in self._node_inputs.items():
             j = self.module_list[k].jacobian([h], rev=rev)
             if torch.is_tensor(j):
-                tens.append(j)
+                (below if cutting and k < self.cut_before else tens).append(j)
             else:
                 const = const + j
+        if below:
+            jb = below[0] if len(below) == 1 else torch.stack(below).sum(0)
+            if jb.requires_grad:
+                jd = jb.detach().requires_grad_(True)
+                self._cut.append((jb, jd))
+                jb = jd
+            tens.append(jb)
         if not tens:
             return const
         if len(tens) == 1:

@@ -10,9 +10,6 @@ from . import ops
 from .ops import BN, EPI_BNSTATS, EPI_MASKSTATS, EPI_RELUMASK, EPI_STORE, PRE_BN_RELU, PRE_BNBWD, PRE_NONE, PRE_RELU
 
 
-AFTER_GLOW_BACKWARD = None      # callable(blk) while engine.TrainStep overlaps the gradient all-reduce with the backward pass
-
-
 # ------------------------------------------------------------------------------------ helpers
 
 class GradSink:
@@ -370,8 +367,6 @@ class GlowBlockFn(torch.autograd.Function):
         fc_subnet_backward(blk.s1, ctx.sv1, out[:, :l1], g_r1, sink, 0, g_y1, True)
         g_r2 = ops.glow_affine_backward(g_y1, g_jac, x[:, :l1], r2, g_x[:, :l1], blk.clamp)
         fc_subnet_backward(blk.s2, ctx.sv2, x[:, l1:], g_r2, sink, 4, g_x[:, l1:], True)
-        if AFTER_GLOW_BACKWARD is not None:
-            AFTER_GLOW_BACKWARD(blk)           # engine.TrainStep: the tail of the flat gradient is complete -> start its all-reduce
         return (g_x, None, None) + tuple(sink.returns())
 
 

@@ -281,3 +281,37 @@ def test_checkpoint_carries_momentum_and_load_is_strict(dev, tmp_path):
     other = _model(dev, overrides={'model': dict(SMALL['model'], n_coupling_blocks_conv='[1, 2, 1]')})
     with pytest.raises(RuntimeError):
         other.load(f)
+
+
+@pytest.mark.gpu
+def test_two_piece_backward_equals_single_pass(cuda_dev):
+    """engine.TrainStep splits the backward pass after the fully connected block (that is where the gradient all-reduce of the
+    FC / mu / phi tail starts on multi-GPU runs); forced on one GPU, eager and as [graph | graph | graph], it must give the
+    parameters of the single-pass step."""
+    dev = cuda_dev
+    base = _model(dev, overrides={'model': {'n_coupling_blocks_conv': '[1, 2, 2]', 'fc_width': '16'}})
+    gen = torch.Generator().manual_seed(5)
+    batches = [_batch(8, 10, gen) for _ in range(2)]
+    results = []
+    for force, graph in (('0', False), ('1', False), ('1', True)):
+        old = os.environ.get('IBINN_FORCE_SPLIT_BACKWARD')
+        os.environ['IBINN_FORCE_SPLIT_BACKWARD'] = force
+        try:
+            m = copy.deepcopy(base)
+            m.eval()
+            step = TrainStep(m, batch_size=8, beta=1.0, clip=8., use_graph=graph)
+            assert (step.early_start is not None) == (force == '1')
+            for x, y in batches:
+                step.step(x.to(dev), y.to(dev))
+            torch.cuda.synchronize()
+            if graph:
+                assert step._g1b is not None
+            results.append({k: v.clone() for k, v in m.state_dict().items() if v.is_floating_point()})
+        finally:
+            if old is None:
+                os.environ.pop('IBINN_FORCE_SPLIT_BACKWARD', None)
+            else:
+                os.environ['IBINN_FORCE_SPLIT_BACKWARD'] = old
+    flat = lambda r: torch.cat([r[k].flatten().double() for k in results[0]])
+    for other in results[1:]:
+        assert float((flat(other) - flat(results[0])).norm() / flat(results[0]).norm()) < 1e-4
