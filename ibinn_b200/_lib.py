@@ -119,6 +119,9 @@ _SIGNATURES = {
     'ibinn_linear_wgrad': ([P, P, P, I, P, L, P, I, P, P, I, I, I, P], c_int),
     'ibinn_gmm_head_partials_floats': ([I], c_int64),
     'ibinn_gmm_head_forward': ([P] * 14 + [I, I, I, P], c_int),
+    'ibinn_gmm_head_gemm_supported': ([I, I, I], c_int),
+    'ibinn_gmm_head_gemm_workspace_floats': ([I, I, I], c_int64),
+    'ibinn_gmm_head_forward_gemm': ([P] * 15 + [I, I, I, I, P], c_int),
     'ibinn_gmm_head_backward': ([P] * 6 + [P, I, P, I, P, I, P, I, F, F, P, P, P, P, P, I, P, I, I, I, I, P], c_int),
     'ibinn_grad_norm_partials_doubles': ([], c_int64),
     'ibinn_grad_norm_clip': ([P, L, P, I, F, P, P, P, P], c_int),

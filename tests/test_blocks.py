@@ -355,7 +355,11 @@ def test_head_large_batch_is_batch_size_independent(dev, B, C):
     lab = torch.randint(0, C, (B,), generator=g)
     y = torch.zeros(B, C).scatter_(1, lab.view(-1, 1), 1.) * 0.98 + 0.02 / C
     t = lambda v: v.to(dev).contiguous()
-    big = ops.gmm_head_forward(t(z), t(jac), t(mu), t(phi), t(y))
+    ops.HEAD_GEMM = False                  # the CUDA-core kernels: bit-identical per-sample results for every batch size
+    try:
+        big = ops.gmm_head_forward(t(z), t(jac), t(mu), t(phi), t(y))
+    finally:
+        ops.HEAD_GEMM = True
     n = 100
     small = ops.gmm_head_forward(t(z[:n]), t(jac[:n]), t(mu), t(phi), t(y[:n]))
     for k in ('L_x', 'logits', 'lse', 'L_cNLL', 'L_y', 'correct'):
@@ -371,6 +375,48 @@ def test_head_large_batch_is_batch_size_independent(dev, B, C):
     assert torch.equal(big['logits'].cpu().argmax(1), (-0.5 * zz).argmax(1))
     ref_means = torch.stack([L_x.mean(), (-0.5 * zz).mean()])
     assert rel(big['means'][:2], ref_means) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('B,C,offset', [(2048, 10, 0.), (8192, 10, 0.), (1300, 100, 0.), (8192, 100, 0.), (4096, 37, 25.)])
+def test_head_gemm_scoring_batch(cuda_dev, B, C, offset):
+    """The tensor-core head (ibinn_gmm_head_forward_gemm: z . mu^T as a tcgen05 3xTF32 GEMM, split-K, centred on the mean of the class
+    means) against the fp64 restatement of model.py:113-126,144-159 and against the CUDA-core kernels: losses / logits 1e-3 (here
+    1e-5), bit-exact arg-max; `offset` moves all class means and samples far from the origin (the cancellation case of the expanded form)."""
+    from ibinn_b200 import ops
+    dev, D = cuda_dev, 3072
+    g = torch.Generator().manual_seed(23)
+    mu = torch.randn(C, D, generator=g) * 0.3 + offset
+    lab = torch.randint(0, C, (B,), generator=g)
+    z = mu[lab] + torch.randn(B, D, generator=g)
+    jac, phi = torch.randn(B, generator=g), 0.3 * torch.randn(C, generator=g)
+    y = torch.zeros(B, C).scatter_(1, lab.view(-1, 1), 1.) * 0.98 + 0.02 / C
+    t = lambda v: v.to(dev).contiguous()
+    assert ops._lib.lib().ibinn_gmm_head_gemm_supported(B, C, D)
+    ops.HEAD_GEMM = 'force'                # also for C = 10, where the dispatcher prefers the shared-memory stream kernel
+    try:
+        got = ops.gmm_head_forward(t(z), t(jac), t(mu), t(phi), t(y))
+    finally:
+        ops.HEAD_GEMM = True
+    ops.HEAD_GEMM = False
+    try:
+        old = ops.gmm_head_forward(t(z), t(jac), t(mu), t(phi), t(y))
+    finally:
+        ops.HEAD_GEMM = True
+    zd, mud = z.double(), mu.double()
+    zz = torch.stack([((zd - mud[k]) ** 2).sum(-1) for k in range(C)], 1)
+    lw = torch.log_softmax(phi.double(), 0)
+    lse = torch.logsumexp(-0.5 * zz + lw, 1)
+    L_x = (-lse - jac.double()) / D
+    L_y = (y.double() * (torch.log_softmax(-0.5 * zz + lw, 1) - lw)).sum(1)
+    L_c = (0.5 * (zz * y.double().round()).sum(1) - jac.double()) / D
+    assert rel(got['logits'], -0.5 * zz) < 1e-5 and rel(got['L_x'], L_x) < 1e-5 and rel(got['L_cNLL'], L_c) < 1e-5
+    assert (got['L_y'].cpu().double() - L_y).abs().max() < 1e-3 * max(1., float(L_y.abs().max()))
+    assert torch.equal(got['logits'].cpu().argmax(1), (-0.5 * zz).argmax(1))
+    assert torch.equal(got['correct'].cpu(), old['correct'].cpu())
+    assert rel(got['logits'], old['logits']) < 1e-5 and rel(got['L_x'], old['L_x']) < 1e-5
+    ref_means = torch.stack([L_x.mean(), (-0.5 * zz).mean(), L_c.mean(), L_y.mean(), (zz.argmin(1) == lab).double().mean()])
+    assert rel(got['means'], ref_means) < 1e-5
 
 
 @pytest.mark.gpu
