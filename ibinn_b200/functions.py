@@ -4,6 +4,8 @@ backward = the hand-derived CUDA backward), so autograd sees ~60 nodes per step 
 engine.FlatParams has attached a flat gradient view to each parameter (`p._ibinn_grad`) --
 accumulated straight into that buffer by the kernels (no per-tensor add kernels).
 """
+import os
+
 import torch
 
 from . import ops
@@ -53,23 +55,31 @@ def pooled_mask(net, shape, p, ref):
 
 # ------------------------------------------------------------------------------------ conv subnet
 
-def conv_subnet_forward(net, x, training, mask=None):
+def conv_subnet_forward(net, x, training, mask=None, stats=None):
     """basic_residual_block / strided_residual_block (reference inn_architecture.py:68-110).
-    x: (B,cin,H,W) possibly a channel slice.  Returns a and the tensors the backward needs."""
+    x: (B,cin,H,W) possibly a channel slice.  Returns a and the tensors the backward needs.
+    stats: (4,width) = batch mean1, inv-std1, mean2, inv-std2 of an earlier training-mode forward: normalise with exactly those
+    (the recomputation of the invertibility-based backward), nothing is updated."""
     bn1, bn2 = net.bn1, net.bn2
     dev = x.device
     width = net.conv1.weight.shape[0]
     stride2 = 2 if net.strided else 1
     pre0 = PRE_RELU if net.relu_first else PRE_NONE
-    if training:
+    if stats is not None:
+        h1 = ops.conv_forward(x, net.conv1.weight, 3, 1, pre=pre0)
+        r1 = BN(stats[0], stats[1], bn1.weight, bn1.bias, bn1.eps, False)
+        h2 = ops.conv_forward(h1, net.conv2.weight, 3, stride2, pre=PRE_BN_RELU, pre_bn=r1)
+        r2 = BN(stats[2], stats[3], bn2.weight, bn2.bias, bn2.eps, False)
+        training = True
+    elif training:
         sv = torch.empty(4, width, dtype=torch.float32, device=dev)
 
-        def stats(bn, k):
+        def bn_stats(bn, k):
             return dict(save_mean=sv[2 * k], save_invstd=sv[2 * k + 1], running_mean=bn.running_mean,
                         running_var=bn.running_var, nbt=bn.num_batches_tracked, momentum=bn.momentum, eps=bn.eps)
-        h1 = ops.conv_forward(x, net.conv1.weight, 3, 1, pre=pre0, epi=EPI_BNSTATS, stats=stats(bn1, 0))
+        h1 = ops.conv_forward(x, net.conv1.weight, 3, 1, pre=pre0, epi=EPI_BNSTATS, stats=bn_stats(bn1, 0))
         r1 = BN(sv[0], sv[1], bn1.weight, bn1.bias, bn1.eps, False)
-        h2 = ops.conv_forward(h1, net.conv2.weight, 3, stride2, pre=PRE_BN_RELU, pre_bn=r1, epi=EPI_BNSTATS, stats=stats(bn2, 1))
+        h2 = ops.conv_forward(h1, net.conv2.weight, 3, stride2, pre=PRE_BN_RELU, pre_bn=r1, epi=EPI_BNSTATS, stats=bn_stats(bn2, 1))
         r2 = BN(sv[2], sv[3], bn2.weight, bn2.bias, bn2.eps, False)
         if mask is None and net.p_drop > 0.:
             mask = pooled_mask(net, (x.shape[0], width), net.p_drop, x)
@@ -172,9 +182,25 @@ class AIOBlockFn(torch.autograd.Function):
         return (g_x, None, None) + tuple(sink.returns())
 
 
+INVERTIBLE_BACKWARD = os.environ.get('IBINN_INVERTIBLE_BACKWARD', '0') == '1'
+INVERTIBLE_ANCHOR_EVERY = int(os.environ.get('IBINN_INVERTIBLE_ANCHOR', '2'))      # blocks between stored outputs (0: only the run's last output)
+
+
+def aio_block_recompute(blk, y, stats, mask):
+    """Invert an AIO block whose OUTPUT y is known (reference all_in_one_block.py:69,93-103) with the batch statistics of the
+    forward pass: returns the block input x and everything the backward kernels need (a, h1, h2, BN references), so that the
+    forward pass has to keep nothing but y and the statistics."""
+    u = ops.aio_unpermute(y, blk.w_inv, blk.act_norm, blk.act_offset)
+    a, saved = conv_subnet_forward(blk.s, u[:, :blk.split_len1], True, mask, stats=stats)
+    ops.aio_affine_inverse_(u, a, blk.act_norm, blk.clamp, 0.1)          # in place: u becomes x
+    return u, a, saved
+
+
 class AIOStageFn(torch.autograd.Function):
     """A run of consecutive AIO_Blocks as ONE launch (ops.aio_stage_forward).  The backward walks the run's blocks in
-    reverse with the per-block backward kernels, on the tensors the fused forward saved."""
+    reverse with the per-block backward kernels, on the tensors the fused forward saved -- or, with INVERTIBLE_BACKWARD
+    (IBINN_INVERTIBLE_BACKWARD=1), on tensors recomputed block by block from the run's OUTPUT by inverting each block: the forward
+    then keeps only the last output and 4 x width batch statistics per block instead of x, a, h1, h2 of every block."""
 
     @staticmethod
     def forward(ctx, x, plan, *params):
@@ -185,9 +211,13 @@ class AIOStageFn(torch.autograd.Function):
         masks = None
         if train:
             masks = [pooled_mask(blk.s, (B, plan.width), blk.s.p_drop, x) if blk.s.p_drop > 0. else None for blk in blocks]
-        res = ops.aio_stage_forward(plan, x, train, masks)
+        ctx.invertible = bool(INVERTIBLE_BACKWARD and train)          # (grad mode is off inside Function.forward: cannot be consulted here)
+        res = ops.aio_stage_forward(plan, x, train, masks, save_intermediates=not ctx.invertible, anchor_every=INVERTIBLE_ANCHOR_EVERY)
         ctx.plan, ctx.masks, ctx.train = plan, masks, train
-        if train:
+        if ctx.invertible:
+            ctx.anchor_keys = sorted(res['anchors'])
+            ctx.save_for_backward(res['out'], res['save'], *[res['anchors'][k] for k in ctx.anchor_keys])
+        elif train:
             ctx.save_for_backward(x, res['outs'], res['h1'], res['h2'], res['a'], res['save'])
         ctx.res = res if train else None
         out = res['out']
@@ -197,10 +227,15 @@ class AIOStageFn(torch.autograd.Function):
     def backward(ctx, g_out, g_jac):
         if not ctx.train:
             raise RuntimeError('ibinn_b200: the fused eval-mode run keeps no activations; it is only used under torch.no_grad()')
-        x, outs, h1, h2, a, save = ctx.saved_tensors
         blocks = ctx.plan.blocks
+        if ctx.invertible:
+            y, save = ctx.saved_tensors[:2]
+            anchors = dict(zip(ctx.anchor_keys, ctx.saved_tensors[2:]))
+        else:
+            x, outs, h1, h2, a, save = ctx.saved_tensors
+            y = outs[-1]
         if g_out is None:
-            g_out = torch.zeros_like(outs[-1])
+            g_out = torch.zeros_like(y)
         g = g_out.contiguous()
         g_jac = None if g_jac is None else g_jac.contiguous()
         grads = [None] * len(blocks)
@@ -208,15 +243,21 @@ class AIOStageFn(torch.autograd.Function):
             blk = blocks[k]
             net = blk.s
             c1 = blk.split_len1
-            xk = x if k == 0 else outs[k - 1]
             sink = GradSink(conv_subnet_params(net) + [blk.act_norm, blk.act_offset])
-            g_x, g_a = ops.aio_coupling_backward(g, g_jac, xk, a[k], outs[k], blk.w, blk.act_norm, blk.act_offset, blk.clamp, 0.1,
+            if ctx.invertible:
+                y = anchors.get(k, y)                                                    # a stored output re-anchors the reconstruction
+                xk, ak, saved = aio_block_recompute(blk, y, save[k], ctx.masks[k])        # x_k = f_k^-1(y); y is the block output
+                yk = y
+            else:
+                xk, ak, yk = (x if k == 0 else outs[k - 1]), a[k], outs[k]
+                r1 = BN(save[k][0], save[k][1], net.bn1.weight, net.bn1.bias, net.bn1.eps, False)
+                r2 = BN(save[k][2], save[k][3], net.bn2.weight, net.bn2.bias, net.bn2.eps, False)
+                saved = (h1[k], h2[k], r1, r2, ctx.masks[k], True)
+            g_x, g_a = ops.aio_coupling_backward(g, g_jac, xk, ak, yk, blk.w, blk.act_norm, blk.act_offset, blk.clamp, 0.1,
                                                  sink[8], sink[9])
-            r1 = BN(save[k][0], save[k][1], net.bn1.weight, net.bn1.bias, net.bn1.eps, False)
-            r2 = BN(save[k][2], save[k][3], net.bn2.weight, net.bn2.bias, net.bn2.eps, False)
-            conv_subnet_backward(net, (h1[k], h2[k], r1, r2, ctx.masks[k], True), xk[:, :c1], g_a, sink, 0, g_x[:, :c1], g_x[:, :c1])
+            conv_subnet_backward(net, saved, xk[:, :c1], g_a, sink, 0, g_x[:, :c1], g_x[:, :c1])
             grads[k] = sink.returns()
-            g = g_x
+            g, y = g_x, xk
         ctx.res = None
         return (g, None) + tuple(t for gk in grads for t in gk)
 

@@ -338,20 +338,27 @@ class AioStagePlan:
         return self._own['bufs']
 
 
-def aio_stage_forward(plan, x, train, masks=None):
+def aio_stage_forward(plan, x, train, masks=None, save_intermediates=True, anchor_every=0):
     """One launch for the whole run.  Returns dict(out, jac[, outs, h1, h2, a, save]) -- in train mode the per-block tensors
-    the backward entry points need (outs[k] = output of block k)."""
+    the backward entry points need (outs[k] = output of block k); with save_intermediates=False only the batch statistics
+    (`save`), the last output and -- every `anchor_every` blocks counted from the end -- an anchor output (`anchors[k]`) are
+    written: the invertibility-based backward recomputes the rest, re-starting from an anchor so that the reconstruction error of
+    this (random-init: chaotic) network cannot grow over more than `anchor_every` blocks."""
     B, C, H, W = x.shape
     nblk, width, c2 = len(plan.blocks), plan.width, C // 2
     dev = x.device
     f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
     res = dict(jac=f(B))
-    if train:
+    keep_all = train and save_intermediates
+    if keep_all:
         res.update(outs=f(nblk, B, C, H, W), h1=f(nblk, B, width, H, W), h2=f(nblk, B, width, H, W), a=f(nblk, B, 2 * c2, H, W),
                    save=f(nblk, 4, width))
         res['out'] = res['outs'][nblk - 1]
     else:
         res['out'] = f(B, C, H, W)
+        if train:
+            res['save'] = f(nblk, 4, width)
+            res['anchors'] = {k: f(B, C, H, W) for k in range(nblk - 1) if anchor_every > 0 and (nblk - 1 - k) % anchor_every == 0}
     imgs = plan.weight_images(x)
     entries = []
     for k, blk in enumerate(plan.blocks):
@@ -369,7 +376,13 @@ def aio_stage_forward(plan, x, train, masks=None):
         if train:
             m = masks[k] if masks is not None else None
             d.drop_mask = ptr(m)
-            d.out, d.h1, d.h2, d.a, d.save = ptr(res['outs'][k]), ptr(res['h1'][k]), ptr(res['h2'][k]), ptr(res['a'][k]), ptr(res['save'][k])
+            d.save = ptr(res['save'][k])
+            if keep_all:
+                d.out, d.h1, d.h2, d.a = ptr(res['outs'][k]), ptr(res['h1'][k]), ptr(res['h2'][k]), ptr(res['a'][k])
+            elif k == nblk - 1:
+                d.out = ptr(res['out'])
+            elif k in res['anchors']:
+                d.out = ptr(res['anchors'][k])
             d.running_mean1, d.running_var1, d.nbt1 = ptr(net.bn1.running_mean), ptr(net.bn1.running_var), ptr(net.bn1.num_batches_tracked, torch.int64)
             d.running_mean2, d.running_var2, d.nbt2 = ptr(net.bn2.running_mean), ptr(net.bn2.running_var), ptr(net.bn2.num_batches_tracked, torch.int64)
         elif k == nblk - 1:

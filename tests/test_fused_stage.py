@@ -189,3 +189,43 @@ def test_fused_run_train_is_deterministic(cuda_dev, C, H, width, B):
     for r in runs[1:]:
         for k, v in r.items():
             assert torch.equal(v, runs[0][k]), k
+
+
+@pytest.mark.parametrize('C,H,width,dropout', [(12, 16, 32, 0.), (48, 8, 64, 0.25)])
+def test_fused_run_invertible_backward(cuda_dev, C, H, width, dropout):
+    """Backward that exploits invertibility (functions.INVERTIBLE_BACKWARD): the forward keeps only the run's output and the batch
+    statistics; every block's input, subnet output and raw conv outputs are recomputed from its OUTPUT (all_in_one_block.py:93-103).
+    Gradients must agree with the stored-activation backward up to the rounding of the reconstruction."""
+    dev, nblk, B = cuda_dev, 4, 64
+    blocks = make_run(C, H, width, nblk, dropout=dropout)
+    for b in blocks:
+        b.to(dev).train()
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(B, C, H, H, generator=g)
+    masks = [((torch.rand(B, width, generator=g) >= dropout).float() / (1. - dropout)).to(dev) if dropout > 0 else None for _ in blocks]
+    gout = torch.randn(B, C, H, H, generator=g).to(dev)
+    gjac = (0.01 * torch.randn(B, generator=g)).to(dev)
+    res = {}
+    for inv in (False, True):
+        bl = [copy.deepcopy(b) for b in blocks]
+        plan = ops.AioStagePlan(bl)
+        for b, m in zip(bl, masks):
+            if m is not None:
+                b.s._ibinn_mask, b.s._ibinn_mask_fresh = m, True
+        Fn.INVERTIBLE_BACKWARD = inv
+        try:
+            xf = x.to(dev).requires_grad_()
+            out, jac = Fn.AIOStageFn.apply(xf, plan, *Fn.aio_stage_params(plan))
+            kept = sum(t.numel() for t in out.grad_fn.saved_tensors) if hasattr(out.grad_fn, 'saved_tensors') else 0
+            ((out * gout).sum() + (jac * gjac).sum()).backward()
+        finally:
+            Fn.INVERTIBLE_BACKWARD = False
+        torch.cuda.synchronize()
+        res[inv] = (out.detach(), xf.grad, [p.grad for b in bl for p in b.parameters() if p.requires_grad], kept)
+    assert torch.equal(res[True][0], res[False][0])
+    assert res[True][3] * 6 < res[False][3]                  # the forward keeps less than a sixth of the floats (anchor every 2nd block)
+    # the reconstruction is good to ~1e-6 per inverted block; what shows in the gradients are the few ReLU decisions it flips
+    assert rel(res[True][1], res[False][1]) < 2e-2
+    for a, b in zip(res[True][2], res[False][2]):
+        assert rel(a, b) < 5e-2
+    print('saved floats: stored %d, invertible %d' % (res[False][3], res[True][3]))
