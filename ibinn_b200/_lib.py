@@ -123,6 +123,7 @@ _SIGNATURES = {
     'ibinn_gmm_head_gemm_workspace_floats': ([I, I, I], c_int64),
     'ibinn_gmm_head_forward_gemm': ([P] * 15 + [I, I, I, I, P], c_int),
     'ibinn_gmm_head_backward': ([P] * 6 + [P, I, P, I, P, I, P, I, F, F, P, P, P, P, P, I, P, I, I, I, I, P], c_int),
+    'ibinn_augment_batch': ([P, P, P, P, P, P, I, I, I, I, I, POINTER(c_float), POINTER(c_float), F, F, I, P], c_int),
     'ibinn_grad_norm_partials_doubles': ([], c_int64),
     'ibinn_grad_norm_clip': ([P, L, P, I, F, P, P, P, P], c_int),
     'ibinn_sgd_step': ([P, P, P, L, P, P, F, P], c_int),

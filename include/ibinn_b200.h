@@ -304,6 +304,16 @@ int ibinn_gmm_head_backward(const float* z, const float* mu, const float* phi, c
                             int accumulate_mu, float* g_phi, int accumulate_phi, int B, int C, int D,
                             ibinn_stream_t stream);
 
+/* ---------------------------------------------------------------- training-data pipeline
+ * Replaces the per-image CPU work of reference data.py:47-90 (`Augmentor`) and data.py:152-160 (the torchvision transform chain
+ * of the CIFAR training set) for a batch whose raw images live in HBM: images (N,H,W,C) uint8; index (B) int32 or NULL;
+ * params (B,8) = flip, brightness, contrast, saturation, rotation angle [rad], crop_x, crop_y in [0,4], unused -- NULL selects the
+ * deterministic test transform (ToTensor + normalisation); unif (B,C,H,W) U[0,1) or NULL; gauss (B,C+pad,H,W) N(0,1) or NULL;
+ * out (B,C+pad,H,W) fp32 NCHW.  beta / gamma are HOST arrays of C floats (data.py:107-110). */
+int ibinn_augment_batch(const unsigned char* images, const int32_t* index, const float* params, const float* unif, const float* gauss,
+                        float* out, int B, int H, int W, int C, int pad_channels, const float* beta, const float* gamma, float sigma,
+                        float pad_sigma, int tanh_augmentation, ibinn_stream_t stream);
+
 /* ---------------------------------------------------------------- clip_grad_norm_ + SGD (reference train.py:109-110)
  * out_norm_coef[0] = sqrt(sum grad^2 + sum extra_sumsq), [1] = min(1, max_norm/(norm+1e-6)). */
 int64_t ibinn_grad_norm_partials_doubles(void);
