@@ -335,6 +335,10 @@ class TrainStep:
                 # the graph above the cut (head, FC block) is complete in itself: its backward leaves the gradients of the detached
                 # leaves, and every parameter gradient of the tail in flat.grad
                 loss.backward()
+                if self.side_streams:                  # the FC weight gradients were forked onto the side stream(s): the tail of the
+                    cur = torch.cuda.current_stream()  # flat gradient is final (and this piece's graph closed) only after they join
+                    for s_ in self.side_streams:
+                        cur.wait_stream(s_)
                 self._split = ([t for t, _ in cut], [d.grad for _, d in cut])
                 self.model.inn._cut = []
             else:

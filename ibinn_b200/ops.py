@@ -593,8 +593,17 @@ def linear_wgrad(g, x, dw, db, *, g_pre=0, h=None, g_mask=None, x_pre=0, x_mask=
     B, N = g.shape
     K = x.shape[1]
     xp, xrs = _rows(x)
-    check(_lib.lib().ibinn_linear_wgrad(ptr(g), ptr(h), ptr(g_mask), g_pre, xp, xrs, ptr(x_mask), x_pre, ptr(dw), ptr(db), B, K, N,
-                                        stream(g)), 'linear_wgrad')
+    st = stream(g)
+    if DEFERRED_WGRAD is not None and WGRAD_STREAMS and g.is_cuda:
+        # like the convolution weight gradients: nothing downstream in the backward pass reads dw, so it leaves the critical path
+        global _wgrad_rr
+        side = WGRAD_STREAMS[_wgrad_rr % len(WGRAD_STREAMS)]
+        _wgrad_rr += 1
+        side.wait_stream(torch.cuda.current_stream())
+        st = side.cuda_stream
+        DEFERRED_WGRAD.append(((g, x, h, g_mask, x_mask, dw, db), None))      # operands stay referenced until the join
+    check(_lib.lib().ibinn_linear_wgrad(ptr(g), ptr(h), ptr(g_mask), g_pre, xp, xrs, ptr(x_mask), x_pre, ptr(dw), ptr(db), B, K, N, st),
+          'linear_wgrad')
 
 
 # ------------------------------------------------------------------------------------ head / optimiser
