@@ -405,7 +405,8 @@ def main():
     traffic = None
     try:
         ncu = json.load(open(os.path.join(ROOT, 'profiles', 'r02_ncu_full.json' if os.path.exists(os.path.join(ROOT, 'profiles', 'r02_ncu_full.json')) else 'r01_ncu_full.json')))
-        traffic = ncu[top.split(' ')[0]]['dram_bytes_per_launch']
+        key = top.split(' ')[0]
+        traffic = ncu[key + '_eval' if kind in ('fwd', 'infer') and key + '_eval' in ncu else key]['dram_bytes_per_launch']
     except Exception:
         pass
     # HBM-bound kernel families at this batch: algorithmic bytes / CUDA-event time of the same launches
