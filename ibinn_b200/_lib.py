@@ -60,6 +60,13 @@ class WgradArgs(Structure):
                 ('Wout', c_int32), ('ksize', c_int32), ('stride', c_int32), ('workspace', c_void_p), ('defer_reduce', c_int32)]
 
 
+class Conv1x1BwdArgs(Structure):
+    _fields_ = [('g', c_void_p), ('h', c_void_p), ('h_bs', c_int64), ('bn', BnRef), ('drop', c_void_p), ('w', c_void_p),
+                ('g_in', c_void_p), ('sums_out', c_void_p), ('dgamma', c_void_p), ('dbeta', c_void_p),
+                ('partials', c_void_p), ('counter', c_void_p), ('wrecords', c_void_p),
+                ('B', c_int32), ('Cin', c_int32), ('Cout', c_int32), ('H', c_int32), ('W', c_int32)]
+
+
 class AioBlockDesc(Structure):
     _fields_ = [('wprep1', c_void_p), ('wprep2', c_void_p), ('wprep3', c_void_p), ('wprep_perm', c_void_p), ('bias3', c_void_p),
                 ('bn1', BnRef), ('bn2', BnRef), ('act_norm', c_void_p), ('act_offset', c_void_p), ('drop_mask', c_void_p),
@@ -78,6 +85,9 @@ class AioStageArgs(Structure):
 
 P, I, F, L = c_void_p, c_int, c_float, c_int64
 _SIGNATURES = {
+    'ibinn_sizeof_conv1x1_bwd_args': ([], c_size_t),
+    'ibinn_conv1x1_bwd_geometry': ([POINTER(Conv1x1BwdArgs), POINTER(c_int32), POINTER(c_int32)], c_int),
+    'ibinn_conv1x1_backward': ([POINTER(Conv1x1BwdArgs), P], c_int),
     'ibinn_sizeof_aio_block_desc': ([], c_size_t),
     'ibinn_sizeof_aio_stage_args': ([], c_size_t),
     'ibinn_aio_stage_supported': ([POINTER(AioStageArgs)], c_int),
@@ -137,7 +147,7 @@ def _declare(lib):
         fn.argtypes = argtypes
         fn.restype = restype
     if lib.ibinn_sizeof_conv_args() != ctypes.sizeof(ConvArgs) or lib.ibinn_sizeof_wgrad_args() != ctypes.sizeof(WgradArgs) \
-            or lib.ibinn_sizeof_aio_block_desc() != ctypes.sizeof(AioBlockDesc) or lib.ibinn_sizeof_aio_stage_args() != ctypes.sizeof(AioStageArgs):
+            or lib.ibinn_sizeof_conv1x1_bwd_args() != ctypes.sizeof(Conv1x1BwdArgs) or lib.ibinn_sizeof_aio_block_desc() != ctypes.sizeof(AioBlockDesc) or lib.ibinn_sizeof_aio_stage_args() != ctypes.sizeof(AioStageArgs):
         raise RuntimeError('ibinn_b200: ctypes structure layout does not match include/ibinn_b200.h')
     return lib
 

@@ -5,7 +5,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ['runtime.cu', 'conv.cu', 'conv_tc.cu', 'block_tc.cu', 'wgrad.cu', 'wgrad_tc.cu', 'coupling.cu', 'layout.cu', 'augment.cu', 'linear.cu', 'head.cu', 'head_tc.cu', 'optim.cu']
+SOURCES = ['runtime.cu', 'conv.cu', 'conv_tc.cu', 'conv1x1_bwd.cu', 'block_tc.cu', 'wgrad.cu', 'wgrad_tc.cu', 'coupling.cu', 'layout.cu', 'augment.cu', 'linear.cu', 'head.cu', 'head_tc.cu', 'optim.cu']
 OUT = os.path.join(HERE, 'libibinn_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC']

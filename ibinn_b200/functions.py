@@ -113,10 +113,12 @@ def conv_subnet_backward(net, saved, x, g_a, sink, s0, g_in_out, addend):
     sums = torch.empty(2, 2, width, dtype=torch.float32, device=dev)
     zero_sums = None if training else torch.zeros(2, width, dtype=torch.float32, device=dev)
     g_a = g_a.contiguous()
-    # 1x1 head
-    ops.conv_wgrad(g_a, h2, dw3, 1, 1, x_pre=PRE_BN_RELU, x_bn=r2, x_mask=mask, dbias=dbias3)
-    g2 = ops.conv_forward(g_a, net.conv3.weight, 1, 1, cout=width, w_transposed=True, epi=EPI_MASKSTATS,
-                          mask=dict(h=h2, bn=r2, drop=mask, sums_out=sums[1], dgamma=dg2, dbeta=db2))
+    # 1x1 head: input gradient (+ BatchNorm-backward sums) and weight / bias gradient in one launch where the shape allows
+    g2 = ops.conv1x1_backward(g_a, h2, r2, mask, net.conv3.weight, sums[1], dg2, db2, dw3, dbias3)
+    if g2 is None:
+        ops.conv_wgrad(g_a, h2, dw3, 1, 1, x_pre=PRE_BN_RELU, x_bn=r2, x_mask=mask, dbias=dbias3)
+        g2 = ops.conv_forward(g_a, net.conv3.weight, 1, 1, cout=width, w_transposed=True, epi=EPI_MASKSTATS,
+                              mask=dict(h=h2, bn=r2, drop=mask, sums_out=sums[1], dgamma=dg2, dbeta=db2))
     s2 = sums[1] if training else zero_sums
     # middle 3x3 (stride 1 or 2)
     ops.conv_wgrad(g2, h1, dw2, 3, stride2, g_pre=PRE_BNBWD, gh=h2, g_bn=r2, g_sums=s2, x_pre=PRE_BN_RELU, x_bn=r1)

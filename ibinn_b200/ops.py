@@ -2,6 +2,7 @@
 `functions.py` builds the torch.autograd.Function layer on top.  Everything raises if the CUDA
 library is missing or a tensor is not on the B200 (see _lib.py)."""
 import ctypes
+import os
 
 import torch
 
@@ -262,6 +263,48 @@ def conv_wgrad(g, x, dw, ksize, stride=1, *, g_pre=PRE_NONE, gh=None, g_bn=None,
     _lib.set_tag('')
     if DEFERRED_WGRAD is not None and WGRAD_REDUCE is not None:
         flush_wgrad_group()
+
+
+# Off by default: measured on the whole step, the one CUDA-core launch (~30 us) loses to the two tcgen05 launches it replaces, which
+# run concurrently on the main and the weight-gradient stream (9.40 -> 10.21 ms per step with it); kept as a tested alternative.
+FUSED_1X1_BWD = os.environ.get('IBINN_FUSED_1X1_BWD', '0') == '1'
+
+
+def conv1x1_backward(g, h, bn, drop, w, sums_out, dgamma, dbeta, dw, dbias):
+    """Backward of the subnets' 1x1 output convolution in ONE launch (ibinn_conv1x1_backward): returns the masked gradient w.r.t.
+    the BatchNorm output (what conv_forward(..., w_transposed=True, epi=EPI_MASKSTATS) returns) and accumulates dw / dbias (what
+    conv_wgrad does), or returns None when the shape is not served (the caller then takes the two-launch route)."""
+    if not FUSED_1X1_BWD or not g.is_cuda:      # (the simulator build has no batched record reduction: it keeps the two-launch route)
+        return None
+    B, Cout, H, W = g.shape
+    Cin = h.shape[1]
+    a = _lib.Conv1x1BwdArgs()
+    a.B, a.Cin, a.Cout, a.H, a.W = B, Cin, Cout, H, W
+    L = _lib.lib()
+    ncta, rec = ctypes.c_int32(), ctypes.c_int32()
+    if L.ibinn_conv1x1_bwd_geometry(ctypes.byref(a), ctypes.byref(ncta), ctypes.byref(rec)) != 0:
+        return None
+    g = g.contiguous()
+    a.g = ptr(g)
+    a.h, a.h_bs = _nchw(h)
+    a.bn = bn.ref()
+    a.drop, a.w = ptr(drop), ptr(w)
+    g_in = torch.empty((B, Cin, H, W), dtype=torch.float32, device=g.device)
+    part = torch.empty(ncta.value * 2 * Cin, dtype=torch.float32, device=g.device)
+    wrec = torch.empty(ncta.value * rec.value, dtype=torch.float32, device=g.device)
+    a.g_in, a.sums_out, a.dgamma, a.dbeta = ptr(g_in), ptr(sums_out), ptr(dgamma), ptr(dbeta)
+    a.partials, a.counter, a.wrecords = ptr(part), counter_ptr(g), ptr(wrec)
+    if _lib._profiler is not None:
+        _lib.set_tag('k1 %d->%d @%dx%d' % (Cin, Cout, H, W))
+    check(L.ibinn_conv1x1_backward(ctypes.byref(a), stream(g)), 'conv1x1_backward')
+    _lib.set_tag('')
+    desc = _lib.WreduceDesc(ptr(wrec), ptr(dw), ptr(dbias), ncta.value, rec.value, Cout, Cin, 1)
+    if DEFERRED_WGRAD is not None:
+        DEFERRED_WGRAD.append((wrec, desc))                          # engine.TrainStep: summed with every other layer's records in one launch
+        DEFERRED_WGRAD.append(((part, g, h, drop), None))            # operands stay referenced until the reduction has run
+    else:
+        flush_deferred_wgrad([(wrec, desc)], g, None)
+    return g_in
 
 
 # ------------------------------------------------------------------------------------ fused run of AIO blocks

@@ -176,6 +176,25 @@ typedef struct {
 /* g_act_offset[c] += sum_r partials[r][c],  g_act_norm[c] += sum_r partials[r][C + c]  for every entry of the table
  * (device memory, n entries), records summed in index order. */
 int ibinn_aio_param_reduce_many(const ibinn_aio_reduce_desc* table, int n, ibinn_stream_t stream);
+/* Backward of the subnets' 1x1 output convolution (inn_architecture.py:88,106) in one launch: the masked input gradient with its
+ * BatchNorm-backward sums (what ibinn_conv_forward with w_transposed + EPI_MASKSTATS computes) AND the weight / bias gradient
+ * records (what ibinn_conv_wgrad computes), exact fp32.  g (B,Cout,H,W) contiguous; h (B,Cin,H,W) raw input of the preceding
+ * BatchNorm, batch stride h_bs; w (Cout,Cin); g_in (B,Cin,H,W) contiguous out; sums_out (2,Cin); dgamma / dbeta (Cin) accumulated or
+ * NULL; partials: ncta * 2 * Cin floats; wrecords: ncta * rec_floats floats, to be summed into dw / dbias by ibinn_wgrad_reduce_many
+ * (ibinn_wreduce_desc with kk = 1); ncta / rec_floats from ibinn_conv1x1_bwd_geometry.  Needs H*W % 4 == 0, Cin % 4 == 0, <= 64 channels. */
+typedef struct ibinn_conv1x1_bwd_args {
+    const float* g; const float* h; int64_t h_bs;
+    ibinn_bn_ref bn;
+    const float* drop;          /* (B,Cin) Dropout2d mask or NULL */
+    const float* w;
+    float* g_in; float* sums_out; float* dgamma; float* dbeta;
+    float* partials; uint32_t* counter; float* wrecords;
+    int32_t B, Cin, Cout, H, W;
+} ibinn_conv1x1_bwd_args;
+size_t ibinn_sizeof_conv1x1_bwd_args(void);
+int ibinn_conv1x1_bwd_geometry(const ibinn_conv1x1_bwd_args* a, int32_t* ncta, int32_t* rec_floats);
+int ibinn_conv1x1_backward(const ibinn_conv1x1_bwd_args* a, ibinn_stream_t stream);
+
 /* ---------------------------------------------------------------- fused AIO_Block forward (one launch for a RUN of blocks)
  * Replaces, for a run of `nblk` consecutive AIO_Blocks of one resolution stage, everything the entry points above do in
  * 4 launches per block (reference all_in_one_block.py:83-114 + inn_architecture.py:68-92): conv3x3 -> BN -> ReLU -> conv3x3 ->

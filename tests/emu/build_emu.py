@@ -6,7 +6,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, '..', '..', 'ibinn_b200', 'csrc')
-SOURCES = ['runtime.cu', 'conv.cu', 'conv_tc.cu', 'block_tc.cu', 'wgrad.cu', 'wgrad_tc.cu', 'coupling.cu', 'layout.cu', 'augment.cu', 'linear.cu', 'head.cu', 'head_tc.cu', 'optim.cu']
+SOURCES = ['runtime.cu', 'conv.cu', 'conv_tc.cu', 'conv1x1_bwd.cu', 'block_tc.cu', 'wgrad.cu', 'wgrad_tc.cu', 'coupling.cu', 'layout.cu', 'augment.cu', 'linear.cu', 'head.cu', 'head_tc.cu', 'optim.cu']
 OUT = os.path.join(HERE, 'libibinn_emu.so')
 
 

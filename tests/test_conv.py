@@ -152,3 +152,65 @@ def test_bn_statistics_with_large_mean(dev):
     xd = x.double()
     assert rel(sm, xd.mean(dim=(0, 2, 3))) < 1e-6
     assert rel(si, torch.rsqrt(xd.var(dim=(0, 2, 3), unbiased=False) + 1e-4)) < 2e-4
+
+
+@pytest.mark.parametrize('B,Cin,Cout,H,drop', [(3, 32, 12, 16, False), (2, 64, 48, 8, True), (2, 16, 2, 32, False), (130, 64, 48, 8, True), (5, 32, 4, 14, False)])
+def test_conv1x1_backward_fused(dev, B, Cin, Cout, H, drop):
+    """ibinn_conv1x1_backward (input gradient with mask + BatchNorm-backward sums AND weight / bias gradient records in one launch)
+    against autograd of conv1x1(relu(bn_train(h)) * dropmask) in fp64."""
+    import ctypes
+    from ibinn_b200 import _lib
+    if dev.type == 'cpu' and B > 100:
+        pytest.skip('large case: B200 only')
+    g = torch.Generator().manual_seed(17 * Cin + Cout)
+    d = lambda t: t.to(dev)
+    hh = torch.randn(B, Cin + 2, H, H, generator=g)
+    h = hh[:, 1:1 + Cin].double().requires_grad_()
+    gam, bet = (torch.randn(Cin, generator=g).double() + 1.5).requires_grad_(), torch.randn(Cin, generator=g).double().requires_grad_()
+    w = (torch.randn(Cout, Cin, 1, 1, generator=g) * 0.3).double().requires_grad_()
+    bias = torch.zeros(Cout).double().requires_grad_()
+    mask = ((torch.rand(B, Cin, generator=g) > 0.25).float() / 0.75) if drop else None
+    mu, var = h.mean(dim=(0, 2, 3)), h.var(dim=(0, 2, 3), unbiased=False)
+    xhat = (h - mu.view(1, -1, 1, 1)) * torch.rsqrt(var + 1e-4).view(1, -1, 1, 1)
+    z = xhat * gam.view(1, -1, 1, 1) + bet.view(1, -1, 1, 1)
+    z.retain_grad()
+    act = F.relu(z)
+    if drop:
+        act = act * mask.double().view(B, Cin, 1, 1)
+    out = F.conv2d(act, w, bias)
+    gy = torch.randn(out.shape, generator=g)
+    (out * gy.double()).sum().backward()
+    # ---- ours, straight through the C ABI (the record reduction is done here with torch so that the simulator can run it too)
+    bn = BN(d(mu.detach().float()), d(torch.rsqrt(var + 1e-4).detach().float()), d(gam.detach().float()), d(bet.detach().float()), 1e-4, False)
+    a = _lib.Conv1x1BwdArgs()
+    a.B, a.Cin, a.Cout, a.H, a.W = B, Cin, Cout, H, H
+    L = _lib.lib()
+    ncta, rec = ctypes.c_int32(), ctypes.c_int32()
+    assert L.ibinn_conv1x1_bwd_geometry(ctypes.byref(a), ctypes.byref(ncta), ctypes.byref(rec)) == 0
+    gd, hd = d(gy.float()), d(hh.float())[:, 1:1 + Cin]
+    wd, md = d(w.detach().float().reshape(Cout, Cin).contiguous()), (d(mask) if drop else None)
+    g_in = torch.empty(B, Cin, H, H, device=dev)
+    sums, dgam, dbet = torch.empty(2, Cin, device=dev), torch.zeros(Cin, device=dev), torch.zeros(Cin, device=dev)
+    part = torch.empty(ncta.value * 2 * Cin, device=dev)
+    wrec = torch.zeros(ncta.value, rec.value, device=dev)
+    a.g = _lib.ptr(gd)
+    a.h, a.h_bs = ops._nchw(hd)
+    a.bn = bn.ref()
+    a.drop, a.w = _lib.ptr(md), _lib.ptr(wd)
+    a.g_in, a.sums_out, a.dgamma, a.dbeta = _lib.ptr(g_in), _lib.ptr(sums), _lib.ptr(dgam), _lib.ptr(dbet)
+    a.partials, a.counter, a.wrecords = _lib.ptr(part), ops.counter_ptr(gd), _lib.ptr(wrec)
+    _lib.check(L.ibinn_conv1x1_backward(ctypes.byref(a), _lib.stream(gd)), 'conv1x1_backward')
+    assert rel(g_in, z.grad) < 2e-5
+    assert rel(sums[0], bet.grad) < 2e-5 and rel(sums[1], gam.grad) < 2e-5
+    assert rel(dbet, bet.grad) < 2e-5 and rel(dgam, gam.grad) < 2e-5
+    tot = wrec.double().sum(0)
+    assert rel(tot[:Cout * Cin].view(Cout, Cin), w.grad.view(Cout, Cin)) < 2e-5
+    assert rel(tot[Cout * Cin:Cout * Cin + Cout], bias.grad) < 2e-5
+    if dev.type == 'cuda':
+        # and through ops.conv1x1_backward (records summed by ibinn_wgrad_reduce_many, accumulated into dw / dbias)
+        dw0, db0 = torch.randn(Cout, Cin, 1, 1, generator=g), torch.randn(Cout, generator=g)
+        dw, db = d(dw0.clone()), d(db0.clone())
+        s2 = torch.empty(2, Cin, device=dev)
+        g2 = ops.conv1x1_backward(gd, hd, bn, md, d(w.detach().float()), s2, None, None, dw, db)
+        assert g2 is not None and torch.equal(g2, g_in)
+        assert rel(dw, dw0.double() + w.grad) < 2e-5 and rel(db, db0.double() + bias.grad) < 2e-5
