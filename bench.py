@@ -306,14 +306,16 @@ def main():
         main_e.side_streams = None                        # serialised on one stream: every launch gets its own event pair
     eager(main_e)
     torch.cuda.synchronize()
-    _lib.profile(True)
-    n0 = _lib.lib().ibinn_launch_count()
-    eager(main_e)
-    prof = _lib.profile(False)
+    table = None
+    for _ in range(2):                                    # two profiled passes, the faster time per entry point (one-off stalls out)
+        _lib.profile(True)
+        n0 = _lib.lib().ibinn_launch_count()
+        eager(main_e)
+        t = _lib.profile(False).summary()
+        table = t if table is None else {k: (min(v[0], table[k][0]) if k in table else v[0], v[1]) for k, v in t.items()}
+        eager_launches = int(_lib.lib().ibinn_launch_count() - n0)
     if side is not None:
         main_e.side_streams = side
-    table = prof.summary()
-    eager_launches = int(_lib.lib().ibinn_launch_count() - n0)
     total_ms = sum(t for t, _ in table.values())
     if kind in ('fwd', 'infer'):
         main_e.refresh()
