@@ -103,7 +103,7 @@ static bool bt_geometry(const ibinn_aio_stage_args& a, BG& g) {
     g.off_h = off;  off += 2 * g.h_bytes;
     g.off_hu = off; off += g.nhu * 2 * g.hu_bytes;
     g.off_ring = off;
-    const int tab_bytes = (4 * MAXW + 3 * MAXCH + 16 * MAXW + 64) * 4;
+    const int tab_bytes = (4 * MAXW + 3 * MAXCH + 16 * MAXW + 64 + MAXCH) * 4;
     const int xs_bytes = pad_to(g.C * g.HW * 4, 16);
     const int budget = 225 * 1024 - tab_bytes - xs_bytes - off;
     int nslot = budget / g.slot_bytes;
@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
     __shared__ __align__(8) uint64_t x1_full, acc_full[MAXT], h1_done[MAXT], hu_full[2], u_full[2], w_full[MAXSLOT], w_empty[MAXSLOT];
     __shared__ uint32_t tmem_base_s;
     __shared__ uint32_t s_tapoff[9];
+    __shared__ __align__(16) ibinn_aio_block_desc s_desc[2];      // this block's and the next block's descriptor (prefetched one block ahead)
 
     unsigned char* x_hi = sm + g.off_x;
     unsigned char* x_lo = x_hi + g.x_bytes;
@@ -187,6 +188,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
     float* s_b3 = s_of + MAXCH;         // [MAXCH] conv3 bias
     float* s_red = s_b3 + MAXCH;        // [16][MAXW] reduction scratch
     float* s_misc = s_red + 16 * MAXW;  // [64]
+    float* s_an = s_misc + 64;          // [MAXCH] act_norm (log-scales) of the current block
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -554,6 +556,28 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
             }
         };
 
+        // ---- per-block descriptor and tables, prefetched ONE BLOCK AHEAD: the descriptor into shared memory, the raw table values
+        // (BatchNorm parameters / running statistics, ActNorm, conv3 bias: one item per thread) into registers; at the top of a block
+        // only arithmetic and shared-memory stores remain (they were 2 us of dependent global-load latency per block)
+        float pre[4] = {0.f, 0.f, 0.f, 0.f};
+        auto prefetch_block = [&](int kn, int buf) {
+            const ibinn_aio_block_desc* dn = p.blocks + kn;
+            if (tid < (int)(sizeof(ibinn_aio_block_desc) / 4))
+                reinterpret_cast<uint32_t*>(&s_desc[buf])[tid] = reinterpret_cast<const uint32_t*>(dn)[tid];
+            if (tid < 2 * g.width) {
+                const ibinn_bn_ref& r = (tid < g.width) ? dn->bn1 : dn->bn2;
+                const int c = tid < g.width ? tid : tid - g.width;
+                pre[0] = r.gamma[c]; pre[1] = r.beta[c];
+                if (!TRAIN) { pre[2] = r.mean[c]; pre[3] = r.scale[c]; }
+            } else if (tid >= 128 && tid < 128 + g.C) {
+                pre[0] = dn->act_norm[tid - 128]; pre[1] = dn->act_offset[tid - 128];
+            } else if (tid >= 192 && tid < 192 + 2 * g.c2) {
+                pre[0] = dn->bias3[tid - 192];
+            }
+        };
+        prefetch_block(0, 0);
+        epi_sync();
+
         uint32_t blk_seen = 0;
         for (int im = 0; im < nimg; ++im) {
             const int b = (int)blockIdx.x + im * (int)gridDim.x;
@@ -565,7 +589,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                 epi_sync();
             }
             for (int k = 0; k < p.nblk; ++k, ++blk_seen) {
-                const ibinn_aio_block_desc* d = p.blocks + k;
+                const ibinn_aio_block_desc* d = &s_desc[blk_seen & 1];
                 const bool last = (k == p.nblk - 1);
                 epi_sync();                                   // every thread is done with the previous block's tables
                 const bool dbg = (im == 0 && k < 2 && tid == 0);
@@ -595,23 +619,38 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                         *reinterpret_cast<float4*>(x_lo + (size_t)k4 * g.lbo_img + (g.halo + q) * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
-                // per-block tables
-                for (int c = tid; c < g.C; c += NEPI) { s_sc[c] = expf(d->act_norm[c]); s_of[c] = d->act_offset[c]; }
-                for (int c = tid; c < 2 * g.c2; c += NEPI) s_b3[c] = d->bias3[c];
-                if (!TRAIN) { load_bn_eval(d->bn1, s_A1, s_B1); load_bn_eval(d->bn2, s_A2, s_B2); }
-                if (warp == 3) {
-                    float v = 0.f;
-                    for (int c = lane; c < g.C; c += 32) v += d->act_norm[c];
-                    v = warp_sum(v);
-                    san_tot += v;                            // the same value in every lane of warp 3
+                // per-block tables from the values prefetched during the previous block
+                if (tid < 2 * g.width) {
+                    if (!TRAIN) {
+                        const ibinn_bn_ref& r = (tid < g.width) ? d->bn1 : d->bn2;
+                        const int c = tid < g.width ? tid : tid - g.width;
+                        const float is = r.scale_is_variance ? rsqrtf(pre[3] + r.eps) : pre[3];
+                        const float A = pre[0] * is;
+                        (tid < g.width ? s_A1 : s_A2)[c] = A;
+                        (tid < g.width ? s_B1 : s_B2)[c] = pre[1] - pre[2] * A;
+                    }
+                } else if (tid >= 128 && tid < 128 + g.C) {
+                    s_sc[tid - 128] = expf(pre[0]); s_of[tid - 128] = pre[1]; s_an[tid - 128] = pre[0];
+                } else if (tid >= 192 && tid < 192 + 2 * g.c2) {
+                    s_b3[tid - 192] = pre[0];
                 }
                 tc::fence_async_smem();
                 mbar_arrive(&x1_full);
+                // the NEXT block's descriptor / table values (the first block of the next image after the last block)
+                {
+                    const int kn = last ? 0 : k + 1;
+                    if (!last || im + 1 < nimg) prefetch_block(kn, (blk_seen + 1) & 1);
+                }
                 epi_sync();                                   // tables visible to all epilogue threads
+                if (warp == 3) {
+                    float v = 0.f;
+                    for (int c = lane; c < g.C; c += 32) v += s_an[c];
+                    san_tot += warp_sum(v);                  // the same value in every lane of warp 3
+                }
                 BDBG(dbg, db + 1);
 
                 const float* dmask = (TRAIN && d->drop_mask) ? d->drop_mask + (size_t)b * g.width : nullptr;
-                const bool rf_next = !last && (d + 1)->relu_first != 0;      // leading ReLU of the NEXT block's subnet
+                const bool rf_next = !last && s_desc[(blk_seen + 1) & 1].relu_first != 0;      // leading ReLU of the NEXT block's subnet (prefetched descriptor)
                 // ---- B: conv1 accumulators -> H1 image
                 if (TRAIN) batch_stats(0, d->bn1, s_A1, s_B1, d->h1, d->save, d->running_mean1, d->running_var1, d->nbt1, b, 0);
                 for (int t = 0; t < nt; ++t) {
