@@ -17,6 +17,9 @@
 //            (deterministic) -> BN coefficients; two barriers per block; raw conv outputs / subnet output / block output saved.
 #include "common.cuh"
 #include "tc.cuh"
+#ifndef IBINN_EMU
+#include <type_traits>
+#endif
 
 #ifndef IBINN_EMU
 #ifdef IBINN_BLK_DBG
@@ -279,6 +282,31 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                     ah += a_step; al += a_step; b += b_step;
                 }
             };
+            // The 3x3 convolutions: 27 (tap, tile) pairs x nks k-steps.  The issuing lane is a latency-bound scalar chain (measured with
+            // scripts/issue_probe.cu: the tensor pipe needs 47 cycles per MMA, the generic routine above spent ~70), so here the
+            // descriptor low words advance by 32-bit adds only (rows are 16 bytes apart: a row shift is +1), the k-loop is unrolled at
+            // compile time and the tap offset comes from arithmetic instead of a shared-memory load.
+            const uint32_t hI = (uint32_t)(tc::smem_desc(0, g.lbo_img) >> 32), lI = (uint32_t)tc::smem_desc(0, g.lbo_img);      // image operands
+            const uint32_t hW = (uint32_t)(tc::smem_desc(0, 2 * g.width * 16) >> 32), lW = (uint32_t)tc::smem_desc(0, 2 * g.width * 16);
+            const uint32_t stepI = (uint32_t)(2 * g.lbo_img) >> 4, stepW = (uint32_t)(2 * 2 * g.width * 16) >> 4;
+            auto conv_taps = [&](auto nks_tag, uint32_t img_hi16, uint32_t img_lo16, uint32_t slot16, uint32_t tap_step16, int t0, int n) {
+                constexpr int NKS = decltype(nks_tag)::value;
+                for (int i = 0; i < n; ++i) {
+                    const int tap = t0 + i, dy = (tap * 11) >> 5, dx = tap - 3 * dy;
+                    const uint32_t toff = (uint32_t)(g.halo + (dy - 1) * g.P + (dx - 1));
+                    const uint32_t b0 = lW + slot16 + (uint32_t)i * tap_step16;
+                    const uint32_t first = tap == 0 ? 0u : 1u;
+                    uint32_t acc_addr = tmem_d, ah0 = lI + img_hi16 + toff, al0 = lI + img_lo16 + toff;
+                    for (int t = 0; t < nt; ++t) {
+#pragma unroll
+                        for (int ks = 0; ks < NKS; ++ks) {
+                            tc::mma_tf32(acc_addr, ((uint64_t)hI << 32) | (ah0 + ks * stepI), ((uint64_t)hW << 32) | (b0 + ks * stepW), idW2, ks ? 1u : first);
+                            tc::mma_tf32(acc_addr, ((uint64_t)hI << 32) | (al0 + ks * stepI), ((uint64_t)hW << 32) | (b0 + ks * stepW), idW1, 1u);
+                        }
+                        acc_addr += g.tile_cols; ah0 += TM; al0 += TM;
+                    }
+                }
+            };
             auto ring_wait = [&]() -> uint32_t {
                 const uint32_t s = ci % g.nslot;
                 tc::mbar_wait(&w_full[s], (ci / g.nslot) & 1);
@@ -299,14 +327,21 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                     tc::fence_after_sync();
                     BDBG(dbg, db + 1);
                     for (int c = 0; c < g.nch1; ++c) {
+#ifdef IBINN_BLK_DBG
+                        const long long w0 = clock64();
+#endif
                         const uint32_t s = ring_wait();
+#ifdef IBINN_BLK_DBG
+                        BDBG_ADD(dbg, 200 + k, (unsigned long long)(clock64() - w0));
+#endif
                         const int t0 = c * g.tpc1, n = (9 - t0 < g.tpc1) ? 9 - t0 : g.tpc1;
-                        for (int i = 0; i < n; ++i)
-                            for (int t = 0; t < nt; ++t) {
-                                const uint32_t ro = (uint32_t)(t * TM) + s_tapoff[t0 + i];
-                                gemm(tmem_d + t * g.tile_cols, xh + ro * 16, xl + ro * 16, g.lbo_img, ring_a + s * g.slot_bytes + i * g.tap1_bytes,
-                                     2 * g.width * 16, g.cin_p / 8, idW2, idW1, t0 + i == 0);
-                            }
+                        const uint32_t slot16 = (ring_a + s * g.slot_bytes) >> 4, ts16 = (uint32_t)g.tap1_bytes >> 4;
+                        switch (g.cin_p >> 3) {
+                            case 1: conv_taps(std::integral_constant<int, 1>{}, xh >> 4, xl >> 4, slot16, ts16, t0, n); break;
+                            case 2: conv_taps(std::integral_constant<int, 2>{}, xh >> 4, xl >> 4, slot16, ts16, t0, n); break;
+                            case 3: conv_taps(std::integral_constant<int, 3>{}, xh >> 4, xl >> 4, slot16, ts16, t0, n); break;
+                            default: conv_taps(std::integral_constant<int, 4>{}, xh >> 4, xl >> 4, slot16, ts16, t0, n); break;
+                        }
                         ring_release(s);
                     }
                     for (int t = 0; t < nt; ++t) tc::mma_commit(&acc_full[t]);
@@ -316,14 +351,18 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                     tc::fence_after_sync();
                     BDBG(dbg, db + 3);
                     for (int c = 0; c < g.nch2; ++c) {
+#ifdef IBINN_BLK_DBG
+                        const long long w0 = clock64();
+#endif
                         const uint32_t s = ring_wait();
+#ifdef IBINN_BLK_DBG
+                        BDBG_ADD(dbg, 204 + k, (unsigned long long)(clock64() - w0));
+                        if (c == 0) BDBG(dbg, 208 + k);
+#endif
                         const int t0 = c * g.tpc2, n = (9 - t0 < g.tpc2) ? 9 - t0 : g.tpc2;
-                        for (int i = 0; i < n; ++i)
-                            for (int t = 0; t < nt; ++t) {
-                                const uint32_t ro = (uint32_t)(t * TM) + s_tapoff[t0 + i];
-                                gemm(tmem_d + t * g.tile_cols, hh + ro * 16, hl + ro * 16, g.lbo_img, ring_a + s * g.slot_bytes + i * g.tap2_bytes,
-                                     2 * g.width * 16, g.width / 8, idW2, idW1, t0 + i == 0);
-                            }
+                        const uint32_t slot16 = (ring_a + s * g.slot_bytes) >> 4, ts16 = (uint32_t)g.tap2_bytes >> 4;
+                        if (g.width == 32) conv_taps(std::integral_constant<int, 4>{}, hh >> 4, hl >> 4, slot16, ts16, t0, n);
+                        else conv_taps(std::integral_constant<int, 8>{}, hh >> 4, hl >> 4, slot16, ts16, t0, n);
                         ring_release(s);
                     }
                     for (int t = 0; t < nt; ++t) tc::mma_commit(&acc_full[t]);

@@ -42,6 +42,7 @@ def main():
             for k in range(2):
                 print(' block %d epilogue: ' % k + ', '.join('%s %.2f' % (n, (v[32 * k + i] - t0) / 1e3) for i, n in enumerate(E) if v[32 * k + i] > 0))
                 print(' block %d mma     : ' % k + ', '.join('%s %.2f' % (n, (v[128 + 32 * k + i] - t0) / 1e3) for i, n in enumerate(M) if v[128 + 32 * k + i] > 0))
+            print(' ring-wait cycles (MMA issuer): conv1 %s, conv2 %s; first conv2 chunk seen at %s us' % ([int(v[200 + k]) for k in range(2)], [int(v[204 + k]) for k in range(2)], ['%.2f' % ((v[208 + k] - t0) / 1e3) for k in range(2)]))
             if train:
                 S = ['pass1a', 'pass1b', 'records', 'barrier', 'combine']
                 for ph in range(2):
