@@ -186,8 +186,7 @@ class _Profiler:
         torch.cuda.synchronize()
         out = {}
         for name, a, b in self.records:
-            t, n = out.get(name, (0., 0))
-            out[name] = (t + a.elapsed_time(b), n + 1)
+            out.setdefault(name, []).append(a.elapsed_time(b))        # one duration per launch, in launch order
         return out
 
 

@@ -37,8 +37,15 @@ extern "C" int ibinn_blk_debug_clear() { unsigned long long z[256] = {0}; return
 namespace {
 
 constexpr int TM = 128;
-constexpr int NEPI = 256;            // epilogue threads: warps 0-7, two warps per TMEM lane quadrant (they split the channels)
-constexpr int BT_THREADS = 320;      // warps 0-7 epilogue, warp 8 MMA issuer, warp 9 filter producer
+#ifndef IBINN_BLK_NPART
+#define IBINN_BLK_NPART 4
+#endif
+constexpr int NPART = IBINN_BLK_NPART;    // epilogue warps per TMEM lane quadrant: they split the channels of a position (the epilogues are
+                                          // dependent-latency chains - TMEM load, tanh / exp, shared-memory store - so warps are what hides them)
+constexpr int NEPI = 128 * NPART;         // epilogue threads: warps 0 .. NW_EPI-1
+constexpr int NW_EPI = NEPI / 32;
+constexpr int WARP_MMA = NW_EPI, WARP_PROD = NW_EPI + 1;
+constexpr int BT_THREADS = NEPI + 64;     // + the MMA issuer warp and the filter producer warp
 constexpr int MAXT = 4;              // tiles of 128 positions per image
 constexpr int MAXSLOT = 8;           // filter ring
 constexpr int MAXW = 64;             // subnet width
@@ -106,7 +113,7 @@ static bool bt_geometry(const ibinn_aio_stage_args& a, BG& g) {
     g.off_h = off;  off += 2 * g.h_bytes;
     g.off_hu = off; off += g.nhu * 2 * g.hu_bytes;
     g.off_ring = off;
-    const int tab_bytes = (4 * MAXW + 3 * MAXCH + 16 * MAXW + 64 + MAXCH) * 4;
+    const int tab_bytes = (4 * MAXW + 3 * MAXCH + 24 * MAXW + 64 + MAXCH) * 4;
     const int xs_bytes = pad_to(g.C * g.HW * 4, 16);
     const int budget = 225 * 1024 - tab_bytes - xs_bytes - off;
     int nslot = budget / g.slot_bytes;
@@ -127,7 +134,7 @@ static bool bt_geometry(const ibinn_aio_stage_args& a, BG& g) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory"); }
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
     uint32_t r;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
@@ -189,8 +196,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
     float* s_sc = s_B2 + MAXW;          // [MAXCH] exp(act_norm)
     float* s_of = s_sc + MAXCH;         // [MAXCH] act_offset
     float* s_b3 = s_of + MAXCH;         // [MAXCH] conv3 bias
-    float* s_red = s_b3 + MAXCH;        // [16][MAXW] reduction scratch
-    float* s_misc = s_red + 16 * MAXW;  // [64]
+    float* s_red = s_b3 + MAXCH;        // [24][MAXW] reduction scratch
+    float* s_misc = s_red + 24 * MAXW;  // [64]
     float* s_an = s_misc + 64;          // [MAXCH] act_norm (log-scales) of the current block
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
         for (int i = 0; i < MAXSLOT; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
         tc::mbar_fence_init();
     }
-    if (warp == 8) tc::tmem_alloc(&tmem_base_s, g.tmem_cols);
+    if (warp == WARP_MMA) tc::tmem_alloc(&tmem_base_s, g.tmem_cols);
     // zero the top halo rows of both images once (positions < 0 = the zero padding above the first image row); everything
     // else is rewritten per image
     {
@@ -230,16 +237,15 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
 
     const int nimg = TRAIN ? 1 : (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
-    if (warp == 9) {
+    if (warp == WARP_PROD) {
         // ================= filter producer: chunks in consumption order through the ring =================
         if (lane == 0) {
-            uint32_t ci = 0;
+            uint32_t ps = 0, turn = 0;                       // ring slot and how often the ring has wrapped (no division per chunk)
             auto push = [&](const float* src, int bytes) {
-                const uint32_t s = ci % g.nslot;
-                if (ci >= (uint32_t)g.nslot) tc::mbar_wait(&w_empty[s], ((ci / g.nslot) - 1) & 1);
-                tc::mbar_arrive_expect_tx(&w_full[s], (uint32_t)bytes);
-                tc::bulk_g2s(ring + (size_t)s * g.slot_bytes, src, (uint32_t)bytes, &w_full[s]);
-                ++ci;
+                if (turn) tc::mbar_wait(&w_empty[ps], (turn - 1) & 1);
+                tc::mbar_arrive_expect_tx(&w_full[ps], (uint32_t)bytes);
+                tc::bulk_g2s(ring + (size_t)ps * g.slot_bytes, src, (uint32_t)bytes, &w_full[ps]);
+                if (++ps == (uint32_t)g.nslot) { ps = 0; ++turn; }
             };
             for (int im = 0; im < nimg; ++im)
                 for (int k = 0; k < p.nblk; ++k) {
@@ -260,10 +266,10 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                 }
         }
         __syncwarp();
-    } else if (warp == 8) {
+    } else if (warp == WARP_MMA) {
         // ================= MMA issuer =================
         if (tc::elect_one()) {
-            uint32_t ci = 0, nblk_seen = 0, hu_cnt[2] = {0, 0}, u_cnt[2] = {0, 0};
+            uint32_t rslot = 0, rphase = 0, nblk_seen = 0, hu_cnt[2] = {0, 0}, u_cnt[2] = {0, 0};
             const uint32_t idW2 = tc::idesc_tf32(TM, 2 * g.width), idW1 = tc::idesc_tf32(TM, g.width);
             const uint32_t id32 = tc::idesc_tf32(TM, 2 * g.np3), id31 = tc::idesc_tf32(TM, g.np3);
             const uint32_t idC2 = tc::idesc_tf32(TM, 2 * g.npC), idC1 = tc::idesc_tf32(TM, g.npC);
@@ -307,13 +313,34 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                     }
                 }
             };
+#ifdef IBINN_BLK_DBG
+            unsigned long long c_wait = 0, c_fence = 0, c_commit = 0;
+#endif
             auto ring_wait = [&]() -> uint32_t {
-                const uint32_t s = ci % g.nslot;
-                tc::mbar_wait(&w_full[s], (ci / g.nslot) & 1);
+                const uint32_t s = rslot;
+#ifdef IBINN_BLK_DBG
+                const long long q0 = clock64();
+#endif
+                tc::mbar_wait(&w_full[s], rphase);
+#ifdef IBINN_BLK_DBG
+                const long long q1 = clock64();
+#endif
                 tc::fence_after_sync();
+#ifdef IBINN_BLK_DBG
+                c_wait += q1 - q0; c_fence += clock64() - q1;
+#endif
                 return s;
             };
-            auto ring_release = [&](uint32_t s) { tc::mma_commit(&w_empty[s]); ++ci; };
+            auto ring_release = [&](uint32_t s) {
+#ifdef IBINN_BLK_DBG
+                const long long q0 = clock64();
+#endif
+                tc::mma_commit(&w_empty[s]);
+                if (++rslot == (uint32_t)g.nslot) { rslot = 0; rphase ^= 1u; }
+#ifdef IBINN_BLK_DBG
+                c_commit += clock64() - q0;
+#endif
+            };
             const uint32_t xh = tc::smem_u32(x_hi), xl = tc::smem_u32(x_lo), hh = tc::smem_u32(h_hi), hl = tc::smem_u32(h_lo);
             const uint32_t ring_a = tc::smem_u32(ring), hu_a = tc::smem_u32(hu);
             for (int im = 0; im < nimg; ++im)
@@ -326,13 +353,16 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                     tc::mbar_wait(&x1_full, nblk_seen & 1);
                     tc::fence_after_sync();
                     BDBG(dbg, db + 1);
+#ifdef IBINN_BLK_DBG
+                    unsigned long long rw_acc = 0;      // (kept in a register: a global read-modify-write per chunk would distort the phase)
+#endif
                     for (int c = 0; c < g.nch1; ++c) {
 #ifdef IBINN_BLK_DBG
                         const long long w0 = clock64();
 #endif
                         const uint32_t s = ring_wait();
 #ifdef IBINN_BLK_DBG
-                        BDBG_ADD(dbg, 200 + k, (unsigned long long)(clock64() - w0));
+                        rw_acc += (unsigned long long)(clock64() - w0);
 #endif
                         const int t0 = c * g.tpc1, n = (9 - t0 < g.tpc1) ? 9 - t0 : g.tpc1;
                         const uint32_t slot16 = (ring_a + s * g.slot_bytes) >> 4, ts16 = (uint32_t)g.tap1_bytes >> 4;
@@ -346,27 +376,43 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                     }
                     for (int t = 0; t < nt; ++t) tc::mma_commit(&acc_full[t]);
                     BDBG(dbg, db + 2);
+#ifdef IBINN_BLK_DBG
+                    if (dbg && blockIdx.x == 0) ibinn_blk_dbg[200 + k] = rw_acc;
+                    rw_acc = 0;
+#endif
                     // ---- conv2: tap-outer, so every tile needs the whole H1 image
                     for (int t = 0; t < nt; ++t) tc::mbar_wait(&h1_done[t], nblk_seen & 1);
                     tc::fence_after_sync();
                     BDBG(dbg, db + 3);
+#ifdef IBINN_BLK_DBG
+                    c_wait = c_fence = c_commit = 0;
+                    if (dbg && blockIdx.x == 0) ibinn_blk_dbg[212 + k] = (unsigned long long)clock64();
+#endif
                     for (int c = 0; c < g.nch2; ++c) {
 #ifdef IBINN_BLK_DBG
                         const long long w0 = clock64();
 #endif
                         const uint32_t s = ring_wait();
 #ifdef IBINN_BLK_DBG
-                        BDBG_ADD(dbg, 204 + k, (unsigned long long)(clock64() - w0));
+                        rw_acc += (unsigned long long)(clock64() - w0);
                         if (c == 0) BDBG(dbg, 208 + k);
+                        if (dbg && k == 1 && blockIdx.x == 0 && c < 9) ibinn_blk_dbg[220 + 2 * c] = (unsigned long long)clock64();
 #endif
                         const int t0 = c * g.tpc2, n = (9 - t0 < g.tpc2) ? 9 - t0 : g.tpc2;
                         const uint32_t slot16 = (ring_a + s * g.slot_bytes) >> 4, ts16 = (uint32_t)g.tap2_bytes >> 4;
                         if (g.width == 32) conv_taps(std::integral_constant<int, 4>{}, hh >> 4, hl >> 4, slot16, ts16, t0, n);
                         else conv_taps(std::integral_constant<int, 8>{}, hh >> 4, hl >> 4, slot16, ts16, t0, n);
+#ifdef IBINN_BLK_DBG
+                        if (dbg && k == 1 && blockIdx.x == 0 && c < 9) ibinn_blk_dbg[221 + 2 * c] = (unsigned long long)clock64();
+#endif
                         ring_release(s);
                     }
                     for (int t = 0; t < nt; ++t) tc::mma_commit(&acc_full[t]);
                     BDBG(dbg, db + 4);
+#ifdef IBINN_BLK_DBG
+                    if (dbg && blockIdx.x == 0) { ibinn_blk_dbg[216 + k] = (unsigned long long)clock64(); ibinn_blk_dbg[204 + k] = rw_acc;
+                        if (k == 1) { ibinn_blk_dbg[240] = c_wait; ibinn_blk_dbg[241] = c_fence; ibinn_blk_dbg[242] = c_commit; } }
+#endif
                     // ---- conv3 (tile s) and soft permutation (tile s-1), software-pipelined against the epilogue
                     for (int s = 0; s <= nt; ++s) {
                         if (s < nt) {
@@ -396,8 +442,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
         __syncwarp();
     } else {
         // ================= warps 0-3: staging + every epilogue; thread <-> position (TMEM lane) =================
-        const int row = tid & 127;                            // 0..127: TMEM lane; the two warps of a lane quadrant split the channels
-        const int half = tid >> 7;
+        const int row = tid & 127;                            // 0..127: TMEM lane; the NPART warps of a lane quadrant split the channels
+        const int half = tid >> 7;                            // 0..NPART-1
         const uint32_t lane_base = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
         const float inv_n = 1.0f / (float)g.HW;
         // position decode of this thread's row in every tile
@@ -435,7 +481,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                 tc::fence_after_sync();
                 const bool valid = pixs[t] >= 0;
                 for (int gi = 0; gi < ng; ++gi) {
-                    if (((t * ng + gi) & 1) != half) continue;
+                    if ((t * ng + gi) % NPART != half) continue;
                     const int c0 = gi * 32;
                     float v[32];
 #pragma unroll
@@ -463,8 +509,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
             if (tid < W2) {
                 float a = 0.f;
 #pragma unroll
-                for (int w8 = 0; w8 < 8; ++w8) a += s_red[w8 * MAXW + tid];
-                s_red[8 * MAXW + tid] = a * inv_n;
+                for (int w8 = 0; w8 < NW_EPI; ++w8) a += s_red[w8 * MAXW + tid];
+                s_red[NW_EPI * MAXW + tid] = a * inv_n;
             }
             epi_sync();
             // pass 1b: M2 about the image mean
@@ -472,7 +518,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
             for (int t = 0; t < nt; ++t) {
                 const bool valid = pixs[t] >= 0;
                 for (int gi = 0; gi < ng; ++gi) {
-                    if (((t * ng + gi) & 1) != half) continue;
+                    if ((t * ng + gi) % NPART != half) continue;
                     const int c0 = gi * 32;
                     float v[32];
 #pragma unroll
@@ -483,7 +529,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                         tc::tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            const float dlt = (a8[i] + b8[i]) - s_red[8 * MAXW + c0 + c8 + i];
+                            const float dlt = (a8[i] + b8[i]) - s_red[NW_EPI * MAXW + c0 + c8 + i];
                             v[c8 + i] = valid ? dlt * dlt : 0.f;
                         }
                     }
@@ -499,8 +545,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
             if (tid < W2) {
                 float a = 0.f;
 #pragma unroll
-                for (int w8 = 0; w8 < 8; ++w8) a += s_red[w8 * MAXW + tid];
-                rec[tid] = s_red[8 * MAXW + tid];
+                for (int w8 = 0; w8 < NW_EPI; ++w8) a += s_red[w8 * MAXW + tid];
+                rec[tid] = s_red[NW_EPI * MAXW + tid];
                 rec[W2 + tid] = a;
             }
             BDBG(sdbg, 16 + 8 * kphase + 2);
@@ -533,7 +579,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                     }
                 }
                 epi_sync();                                   // s_red is free again
-                s_red[(part * 3 + 0) * W2 + c] = s1;        // [nparts][3][W2]: NEPI / W2 * 3 * W2 = 768 floats
+                s_red[(part * 3 + 0) * W2 + c] = s1;        // [nparts][3][W2]: NEPI / W2 * 3 * W2 = 3 NEPI floats (<= 24 MAXW)
                 s_red[(part * 3 + 1) * W2 + c] = s2;
                 s_red[(part * 3 + 2) * W2 + c] = m2;
                 epi_sync();
@@ -574,7 +620,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                                       bool store) {
             const bool valid = pixs[t] >= 0;
             const int W2 = g.width;
-            for (int c8 = half * 8; c8 < W2; c8 += 16) {       // the two warps of a lane quadrant take alternate groups of 8 channels
+            for (int c8 = half * 8; c8 < W2; c8 += 8 * NPART) {       // the warps of a lane quadrant take alternate groups of 8 channels
                 float a8[8], b8[8], hi[8], lo[8];
                 tc::tmem_ld8(lane_base + t * g.tile_cols + c8, a8);
                 tc::tmem_ld8(lane_base + t * g.tile_cols + W2 + c8, b8);
@@ -717,7 +763,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                         const int q = t * TM + row;
                         float* og = (d->out && pix >= 0) ? d->out + (size_t)b * g.C * g.HW + pix : nullptr;
                         const int nk4 = g.cin_p / 4;
-                        for (int c8 = half * 8; c8 < g.npC; c8 += 16) {
+                        for (int c8 = half * 8; c8 < g.npC; c8 += 8 * NPART) {
                             float a8[8], b8[8], o8[8];
                             tc::tmem_ld8(lane_base + t * g.tile_cols + c8, a8);
                             tc::tmem_ld8(lane_base + t * g.tile_cols + g.npC + c8, b8);
@@ -780,7 +826,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                         const uint32_t tb = lane_base + t * g.tile_cols;
                         unsigned char* uh = hu + (size_t)sl * 2 * g.hu_bytes + row * 16;
                         float* ag = (TRAIN && d->a && pix >= 0) ? d->a + (size_t)b * 2 * g.c2 * g.HW + pix : nullptr;
-                        for (int k4 = half; k4 < g.kC / 4; k4 += 2) {
+                        for (int k4 = half; k4 < g.kC / 4; k4 += NPART) {
                             float sv[4], tv[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
@@ -827,9 +873,14 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                 const float w = warp_sum(jsum);
                 epi_sync();
                 if (lane == 0) s_misc[warp] = w;
-                if (warp == 3 && lane == 0) s_misc[8] = san_tot;
+                if (warp == 3 && lane == 0) s_misc[NW_EPI] = san_tot;
                 epi_sync();
-                if (tid == 0) p.jac[b] = (((s_misc[0] + s_misc[1]) + (s_misc[2] + s_misc[3])) + ((s_misc[4] + s_misc[5]) + (s_misc[6] + s_misc[7]))) + (float)g.HW * s_misc[8];
+                if (tid == 0) {
+                    float js = 0.f;
+#pragma unroll
+                    for (int w8 = 0; w8 < NW_EPI; w8 += 4) js += (s_misc[w8] + s_misc[w8 + 1]) + (s_misc[w8 + 2] + s_misc[w8 + 3]);
+                    p.jac[b] = js + (float)g.HW * s_misc[NW_EPI];
+                }
                 epi_sync();
             }
         }
@@ -846,7 +897,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 8) tc::tmem_dealloc(tmem_d, g.tmem_cols);
+    if (warp == WARP_MMA) tc::tmem_dealloc(tmem_d, g.tmem_cols);
 }
 
 }  // namespace

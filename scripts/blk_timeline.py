@@ -43,6 +43,13 @@ def main():
                 print(' block %d epilogue: ' % k + ', '.join('%s %.2f' % (n, (v[32 * k + i] - t0) / 1e3) for i, n in enumerate(E) if v[32 * k + i] > 0))
                 print(' block %d mma     : ' % k + ', '.join('%s %.2f' % (n, (v[128 + 32 * k + i] - t0) / 1e3) for i, n in enumerate(M) if v[128 + 32 * k + i] > 0))
             print(' ring-wait cycles (MMA issuer): conv1 %s, conv2 %s; first conv2 chunk seen at %s us' % ([int(v[200 + k]) for k in range(2)], [int(v[204 + k]) for k in range(2)], ['%.2f' % ((v[208 + k] - t0) / 1e3) for k in range(2)]))
+            for k in range(2):
+                dt = v[128 + 32 * k + 4] - v[128 + 32 * k + 3]
+                if dt > 0:
+                    print(' block %d conv2 issue: %.0f SM cycles in %.0f ns -> %.2f GHz' % (k, v[216 + k] - v[212 + k], dt, (v[216 + k] - v[212 + k]) / dt))
+            base = v[213]
+            print(' conv2 chunks of block 1 (cycles from start: after ring wait / after issue):', ' '.join('%d/%d' % (v[220 + 2 * c] - base, v[221 + 2 * c] - base) for c in range(9) if v[220 + 2 * c] > 0))
+            print(' conv2 of block 1, issuer cycles in: mbarrier wait %d, tcgen05 fence %d, tcgen05.commit %d' % (v[240], v[241], v[242]))
             if train:
                 S = ['pass1a', 'pass1b', 'records', 'barrier', 'combine']
                 for ph in range(2):

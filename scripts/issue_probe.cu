@@ -3,12 +3,13 @@
 // tensor pipe (216 MMAs x ~45 cycles) or by the issuing thread?  Variants: A as in the kernel, B with the k-loop unrolled by 4,
 // C only the N = 64 MMAs (how much the second MMA of the pair costs), D only N = 32.
 #include <cstdio>
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include "../ibinn_b200/csrc/tc.cuh"
 
-constexpr int ROWS = 420, WIDTH = 32;
+constexpr int MAXROWS = 420, WIDTH = 32;
 
-__global__ void __launch_bounds__(320) probe(long long* cyc, int variant) {
+__global__ void __launch_bounds__(320) probe(long long* cyc, int variant, int ROWS, int rnd) {
     extern __shared__ __align__(1024) unsigned char sm[];
     __shared__ __align__(8) uint64_t bar, tapbar[9];
     __shared__ uint32_t tmem_s;
@@ -17,7 +18,7 @@ __global__ void __launch_bounds__(320) probe(long long* cyc, int variant) {
     unsigned char* A_hi = sm;                                   // 8 chunks x ROWS x 16
     unsigned char* A_lo = sm + 8 * ROWS * 16;
     unsigned char* Bm = sm + 2 * 8 * ROWS * 16;                 // 9 taps x (8 chunks x 64 rows x 16 B)
-    for (int i = tid; i < (2 * 8 * ROWS * 16 + 9 * 8 * 64 * 16) / 4; i += blockDim.x) reinterpret_cast<float*>(sm)[i] = 1.f;
+    for (int i = tid; i < (2 * 8 * ROWS * 16 + 9 * 8 * 64 * 16) / 4; i += blockDim.x) reinterpret_cast<float*>(sm)[i] = rnd ? __uint_as_float(0x3f000000u + ((i * 2654435761u) >> 9)) : 1.f;
     if (tid < 9) s_tapoff[tid] = 18 + (tid / 3 - 1) * 17 + (tid % 3 - 1);
     if (tid == 0) { tc::mbar_init(&bar, 1); for (int i = 0; i < 9; ++i) tc::mbar_init(&tapbar[i], 1); tc::mbar_fence_init(); }
     if (warp == 0) tc::tmem_alloc(&tmem_s, 256);
@@ -59,8 +60,7 @@ __global__ void __launch_bounds__(320) probe(long long* cyc, int variant) {
         long long t1 = clock64();
         tc::mma_commit(&bar);
         tc::mbar_wait(&bar, 0);
-        cyc[0] = t1 - t0;
-        cyc[1] = clock64() - t0;
+        if (blockIdx.x == gridDim.x - 1) { cyc[0] = t1 - t0; cyc[1] = clock64() - t0; }
     }
     // variants 5 / 6: the other warps POLL the completion barrier while the MMAs run (256 threads, or one lane per warp), as the
     // epilogue warps of block_tc.cu do on acc_full
@@ -71,13 +71,15 @@ __global__ void __launch_bounds__(320) probe(long long* cyc, int variant) {
     if (warp == 0) tc::tmem_dealloc(tm, 256);
 }
 
-int main() {
+int main(int argc, char** argv) {
+    const int grid = argc > 1 ? atoi(argv[1]) : 1, rows = argc > 2 ? atoi(argv[2]) : 420, rnd = argc > 3 ? atoi(argv[3]) : 0;
+    printf("grid %d rows %d (lbo %d B) random data %d\n", grid, rows, rows * 16, rnd);
     long long* c; cudaMalloc(&c, 16);
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     const char* names[] = {"as in block_tc.cu (N=64 + N=32 per k-step)", "k-loop unrolled, descriptors by constant offsets", "only the N=64 MMAs", "only the N=32 MMAs", "as in block_tc.cu + a commit per tap", "as in block_tc.cu + 9 warps polling the mbarrier", "as in block_tc.cu + one lane per warp polling"};
-    for (int v = 0; v < 7; ++v)
+    for (int v = 0; v < 2; ++v)
         for (int rep = 0; rep < 2; ++rep) {
-            probe<<<1, 320, 200 * 1024>>>(c, v);
+            probe<<<grid, 320, 200 * 1024>>>(c, v, rows, rnd);
             cudaError_t e = cudaDeviceSynchronize();
             long long h[2]; cudaMemcpy(h, c, 16, cudaMemcpyDeviceToHost);
             const int n = (v == 2 || v == 3) ? 108 : 216;
