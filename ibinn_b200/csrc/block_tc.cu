@@ -134,6 +134,13 @@ static bool bt_geometry(const ibinn_aio_stage_args& a, BG& g) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
+// One arrival per epilogue WARP (the barriers count NW_EPI): 512 arrivals on one shared-memory word serialise, and they sit on
+// the hand-off from every epilogue to the MMA issuer.  Each lane has fenced its own writes; __syncwarp orders them before lane 0's
+// (releasing) arrive.
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory"); }
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
     uint32_t r;
@@ -206,9 +213,9 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
 
     if (tid < 9) s_tapoff[tid] = (uint32_t)(g.halo + (tid / 3 - 1) * g.P + (tid % 3 - 1));
     if (tid == 0) {
-        tc::mbar_init(&x1_full, NEPI);
-        for (int i = 0; i < MAXT; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&h1_done[i], NEPI); }
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&hu_full[i], NEPI); tc::mbar_init(&u_full[i], NEPI); }
+        tc::mbar_init(&x1_full, NW_EPI);
+        for (int i = 0; i < MAXT; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&h1_done[i], NW_EPI); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&hu_full[i], NW_EPI); tc::mbar_init(&u_full[i], NW_EPI); }
         for (int i = 0; i < MAXSLOT; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
         tc::mbar_fence_init();
     }
@@ -306,8 +313,12 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                     for (int t = 0; t < nt; ++t) {
 #pragma unroll
                         for (int ks = 0; ks < NKS; ++ks) {
+#if !defined(IBINN_EXP_NOMMA)
                             tc::mma_tf32(acc_addr, ((uint64_t)hI << 32) | (ah0 + ks * stepI), ((uint64_t)hW << 32) | (b0 + ks * stepW), idW2, ks ? 1u : first);
+#if !defined(IBINN_EXP_SKIPLO)
                             tc::mma_tf32(acc_addr, ((uint64_t)hI << 32) | (al0 + ks * stepI), ((uint64_t)hW << 32) | (b0 + ks * stepW), idW1, 1u);
+#endif
+#endif
                         }
                         acc_addr += g.tile_cols; ah0 += TM; al0 += TM;
                     }
@@ -325,7 +336,8 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
 #ifdef IBINN_BLK_DBG
                 const long long q1 = clock64();
 #endif
-                tc::fence_after_sync();
+                // (no tcgen05.fence here: the chunk was written by the TMA engine and its arrival on the mbarrier is all the MMAs need;
+                // the fences of this lane order TMEM accesses against the epilogue warps and sit at x1_full / h1_done / hu_full / u_full)
 #ifdef IBINN_BLK_DBG
                 c_wait += q1 - q0; c_fence += clock64() - q1;
 #endif
@@ -720,7 +732,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                     s_b3[tid - 192] = pre[0];
                 }
                 tc::fence_async_smem();
-                mbar_arrive(&x1_full);
+                warp_arrive(&x1_full, lane);
                 // the NEXT block's descriptor / table values (the first block of the next image after the last block)
                 {
                     const int kn = last ? 0 : k + 1;
@@ -745,7 +757,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                     bn_relu_to_operand(t, s_A1, s_B1, nullptr, h_hi + (g.halo + q) * 16, h_lo + (g.halo + q) * 16, g.lbo_img, q < g.S);
                     tc::fence_before_sync();
                     tc::fence_async_smem();
-                    mbar_arrive(&h1_done[t]);
+                    warp_arrive(&h1_done[t], lane);
                 }
                 BDBG(dbg, db + 3);
                 // ---- train: statistics of conv2 need all of its tiles before any of them can be normalised
@@ -813,7 +825,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                         bn_relu_to_operand(t, s_A2, s_B2, dmask, dh, dh + g.hu_bytes, TM * 16, true);
                         tc::fence_before_sync();
                         tc::fence_async_smem();
-                        mbar_arrive(&hu_full[sl]);
+                        warp_arrive(&hu_full[sl], lane);
                         if (s == 0) BDBG(dbg, db + 6);
                     }
                     if (s >= 1 && s - 1 < nt) {
@@ -860,7 +872,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                         }
                         tc::fence_before_sync();
                         tc::fence_async_smem();
-                        mbar_arrive(&u_full[sl]);
+                        warp_arrive(&u_full[sl], lane);
                         if (s == 1) BDBG(dbg, db + 8);
                     }
                 }
