@@ -7,6 +7,30 @@
 extern unsigned long long ibinn_launch_counter;
 #define IBINN_LAUNCH(kernel, grid, block, smem, stream, ...) \
     (++ibinn_launch_counter, kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__))
+// Programmatic dependent launch (PDL) for the latency-bound chains of small launches: a kernel launched with IBINN_LAUNCH_PDL may be
+// scheduled while its predecessor in the stream is still draining (once every CTA of the predecessor has executed
+// ibinn_pdl_trigger() or exited); it sets up shared memory / barriers / TMEM and then blocks in ibinn_pdl_wait() until the
+// predecessor has completed and its writes are visible.  ONLY kernels that execute ibinn_pdl_wait() in every thread before their
+// first global-memory access may be launched this way.  IBINN_PDL=0 turns the launch attribute off (the device calls are no-ops then).
+extern int ibinn_pdl_enabled;
+__device__ __forceinline__ void ibinn_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void ibinn_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <class... KArgs, class... Args>
+static inline void ibinn_launch_pdl_(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = ibinn_pdl_enabled ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define IBINN_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) \
+    (++ibinn_launch_counter, ibinn_launch_pdl_(kernel, (grid), (block), (smem), (stream), __VA_ARGS__))
 #define IBINN_DYN_SMEM(type, name)                                  \
     extern __shared__ __align__(16) unsigned char ibinn_dyn_raw[]; \
     type* name = reinterpret_cast<type*>(ibinn_dyn_raw)

@@ -285,6 +285,9 @@ __global__ void __launch_bounds__(NTHREADS_TC, 2) conv_tc_kernel(const ibinn_con
         tc::mbar_fence_init();
     }
     if (warp == 8) tc::tmem_alloc(&tmem_base_s, g.tmem_cols);
+    // everything above is private to this CTA; from here on the kernel reads what its predecessor in the stream wrote
+    ibinn_pdl_wait();
+    ibinn_pdl_trigger();
     if (PRE == IBINN_PRE_BN_RELU) {
         for (int c = tid; c < p.Cin; c += NTHREADS_TC) {
             const float is = tc_invstd(p.pre_bn, c), A = p.pre_bn.gamma[c] * is;
@@ -673,7 +676,7 @@ static int tc_launch_inst(const ibinn_conv_args& a, const TcGeom& g, cudaStream_
     auto kfn = conv_tc_kernel<PRE, EPI>;
     int e = ibinn_set_smem(kfn, g.smem_bytes);
     if (e) return e;
-    IBINN_LAUNCH(kfn, dim3(g.grid), dim3(NTHREADS_TC), g.smem_bytes, st, a, g);
+    IBINN_LAUNCH_PDL(kfn, dim3(g.grid), dim3(NTHREADS_TC), g.smem_bytes, st, a, g);
     return ibinn_launch_status();
 }
 

@@ -223,6 +223,8 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_affine_inverse_kernel(const
 __global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
     IBINN_DYN_SMEM(float, smem);
     __shared__ int s_flag;
+    ibinn_pdl_wait();           // (common.cuh: launched with IBINN_LAUNCH_PDL)
+    ibinn_pdl_trigger();
     // A sample may be split over `nsplit` CTAs along the pixel axis (HWl pixels each, starting at qo): nothing in the backward
     // couples pixels except the ActNorm sums, which are per-CTA partial records anyway.
     const int C = p.C, HW = p.HW, HWl = HW / p.nsplit, HWp = round4(HWl), Cp = round4(C);
@@ -688,7 +690,7 @@ extern "C" int ibinn_aio_coupling_backward(const float* g_out, const float* g_ja
     size_t sm = aio_smem(C, H * W / p.nsplit);
     int e = ibinn_set_smem(aio_bwd_kernel, sm);
     if (e) return e;
-    IBINN_LAUNCH(aio_bwd_kernel, dim3(B * p.nsplit), dim3(IBINN_THREADS), sm, (cudaStream_t)stream, p);
+    IBINN_LAUNCH_PDL(aio_bwd_kernel, dim3(B * p.nsplit), dim3(IBINN_THREADS), sm, (cudaStream_t)stream, p);
     return ibinn_launch_status();
 }
 

@@ -2,7 +2,10 @@
 #include "common.cuh"
 
 #ifndef IBINN_EMU
+#include <stdlib.h>
 unsigned long long ibinn_launch_counter = 0;
+static int pdl_from_env() { const char* e = getenv("IBINN_PDL"); return !(e && e[0] == '0'); }
+int ibinn_pdl_enabled = pdl_from_env();
 #endif
 
 char ibinn_errbuf[256] = "";

@@ -164,6 +164,8 @@ __global__ void __launch_bounds__(WT_THREADS, 1) wgrad_tc_kernel(const ibinn_wgr
         tc::mbar_fence_init();
     }
     if (warp == WT_MMA_WARP) tc::tmem_alloc(&tmem_base_s, g.tmem_cols);
+    ibinn_pdl_wait();           // (common.cuh: the set-up above overlaps the tail of the previous launch in the stream)
+    ibinn_pdl_trigger();
     if (GPRE == IBINN_PRE_BNBWD) {
         for (int c = tid; c < p.Cout; c += WT_THREADS) {
             const float is = wt_invstd(p.g_bn, c), k = p.g_bn.gamma[c] * is;
@@ -582,7 +584,7 @@ int wgrad_tc_launch(const ibinn_wgrad_args& a, float* workspace, cudaStream_t st
         auto kfn = wgrad_tc_kernel<GP, XP, K3_, V_>; \
         e = ibinn_set_smem(kfn, g.smem_bytes); \
         if (e) return e; \
-        IBINN_LAUNCH(kfn, dim3(g.ncta), dim3(WT_THREADS), g.smem_bytes, st, a, g, workspace); \
+        IBINN_LAUNCH_PDL(kfn, dim3(g.ncta), dim3(WT_THREADS), g.smem_bytes, st, a, g, workspace); \
         e = ibinn_launch_status(); \
     }
 #define WT_CASES(GP, XP) WT_CASE(GP, XP, true, true) WT_CASE(GP, XP, true, false) WT_CASE(GP, XP, false, true) WT_CASE(GP, XP, false, false)

@@ -118,6 +118,9 @@ static inline float __uint_as_float(unsigned i) { float f; memcpy(&f, &i, 4); re
 using std::max;
 using std::min;
 
+#define IBINN_LAUNCH_PDL IBINN_LAUNCH
+static inline void ibinn_pdl_wait() {}
+static inline void ibinn_pdl_trigger() {}
 #define IBINN_LAUNCH(kernel, grid, block, smem, stream, ...) \
     emu::launch((grid), (block), (smem), [=]() { kernel(__VA_ARGS__); })
 #define IBINN_DYN_SMEM(type, name) type* name = reinterpret_cast<type*>(emu::dyn_smem())

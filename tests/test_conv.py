@@ -155,7 +155,7 @@ def test_bn_statistics_with_large_mean(dev):
 
 
 @pytest.mark.parametrize('B,Cin,Cout,H,drop', [(3, 32, 12, 16, False), (2, 64, 48, 8, True), (2, 16, 2, 32, False), (130, 64, 48, 8, True), (5, 32, 4, 14, False)])
-def test_conv1x1_backward_fused(dev, B, Cin, Cout, H, drop):
+def test_conv1x1_backward_fused(dev, monkeypatch, B, Cin, Cout, H, drop):
     """ibinn_conv1x1_backward (input gradient with mask + BatchNorm-backward sums AND weight / bias gradient records in one launch)
     against autograd of conv1x1(relu(bn_train(h)) * dropmask) in fp64."""
     import ctypes
@@ -211,6 +211,7 @@ def test_conv1x1_backward_fused(dev, B, Cin, Cout, H, drop):
         dw0, db0 = torch.randn(Cout, Cin, 1, 1, generator=g), torch.randn(Cout, generator=g)
         dw, db = d(dw0.clone()), d(db0.clone())
         s2 = torch.empty(2, Cin, device=dev)
+        monkeypatch.setattr(ops, 'FUSED_1X1_BWD', True)        # (opt-in: IBINN_FUSED_1X1_BWD=1)
         g2 = ops.conv1x1_backward(gd, hd, bn, md, d(w.detach().float()), s2, None, None, dw, db)
         assert g2 is not None and torch.equal(g2, g_in)
         assert rel(dw, dw0.double() + w.grad) < 2e-5 and rel(db, db0.double() + bias.grad) < 2e-5
