@@ -9,7 +9,7 @@
 //   perm   1x1  C     -> C         A = U tile    ([x1 | x2 exp(clamp tanh(alpha s)) + t], the coupling output) in the same slot
 // The 3x3 taps are nine shifted descriptors onto the same image (one padded 1-D pixel sequence per image: pitch W+1, one zero
 // row below), exactly as in conv_tc.cu; filters arrive as the operand images of ibinn_wprep_many through a ring of TMA bulk copies.
-// Epilogues (warps 0-3, thread <-> TMEM lane <-> position): BatchNorm + ReLU + split -> next operand image; coupling + log-det;
+// Epilogues (warps 0 .. 4 NPART - 1; thread <-> TMEM lane <-> position, the NPART warps of a lane quadrant split the channels): BatchNorm + ReLU + split -> next operand image; coupling + log-det;
 // ActNorm + store + the next block's X1 image.  The block input itself stays in shared memory as fp32 ([C][HW]) for the coupling.
 //
 // train = 0: running statistics; nothing couples CTAs; persistent over images.
@@ -295,10 +295,11 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                     ah += a_step; al += a_step; b += b_step;
                 }
             };
-            // The 3x3 convolutions: 27 (tap, tile) pairs x nks k-steps.  The issuing lane is a latency-bound scalar chain (measured with
-            // scripts/issue_probe.cu: the tensor pipe needs 47 cycles per MMA, the generic routine above spent ~70), so here the
-            // descriptor low words advance by 32-bit adds only (rows are 16 bytes apart: a row shift is +1), the k-loop is unrolled at
-            // compile time and the tap offset comes from arithmetic instead of a shared-memory load.
+            // The 3x3 convolutions: 27 (tap, tile) pairs x nks k-steps.  The tensor pipe needs ~47 cycles per MMA of these shapes
+            // (scripts/issue_probe.cu) and the issuing lane must not be slower: the descriptor low words advance by 32-bit adds only
+            // (rows are 16 bytes apart: a row shift is +1), the k-loop is unrolled at compile time and the tap offset comes from
+            // arithmetic instead of a shared-memory load (the generic routine above spent ~70 cycles per MMA).  Measured with the
+            // IBINN_EXP_NOMMA / IBINN_EXP_SKIPLO builds below: conv1 + conv2 now cost 50 cycles per MMA inside the kernel.
             const uint32_t hI = (uint32_t)(tc::smem_desc(0, g.lbo_img) >> 32), lI = (uint32_t)tc::smem_desc(0, g.lbo_img);      // image operands
             const uint32_t hW = (uint32_t)(tc::smem_desc(0, 2 * g.width * 16) >> 32), lW = (uint32_t)tc::smem_desc(0, 2 * g.width * 16);
             const uint32_t stepI = (uint32_t)(2 * g.lbo_img) >> 4, stepW = (uint32_t)(2 * 2 * g.width * 16) >> 4;
@@ -453,7 +454,7 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
         }
         __syncwarp();
     } else {
-        // ================= warps 0-3: staging + every epilogue; thread <-> position (TMEM lane) =================
+        // ================= epilogue warps: staging + every epilogue; thread <-> position (TMEM lane) =================
         const int row = tid & 127;                            // 0..127: TMEM lane; the NPART warps of a lane quadrant split the channels
         const int half = tid >> 7;                            // 0..NPART-1
         const uint32_t lane_base = tmem_d + ((uint32_t)((warp & 3) * 32) << 16);
