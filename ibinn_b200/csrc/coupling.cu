@@ -220,7 +220,14 @@ __global__ void __launch_bounds__(IBINN_THREADS) aio_affine_inverse_kernel(const
 }
 
 // backward of MODE 0.  Needs x, a, out (the block output = next block's input) and g_out.
-__global__ void __launch_bounds__(IBINN_THREADS) aio_bwd_kernel(const AioP p) {
+#ifndef IBINN_AIO_BWD_MINB
+// Occupancy is what this kernel lives on (its phases are load -> sync -> compute -> store per sample): unbounded it takes 136 registers =
+// ONE CTA per SM; 3 -> 79 registers, no spills; 4 -> 64 registers, 124 bytes of spill.  B = 8192, C = 3 / 12 / 48: 559 / 706 / 873 us (1),
+// 208 / 288 / 399 us (3), 186 / 241 / 335 us (4); training step at B = 128: 9.51 ms (1), 8.97 ms (3 and 4) - the smaller footprint also
+// lets the weight-gradient stream's CTAs share the SMs.
+#define IBINN_AIO_BWD_MINB 4
+#endif
+__global__ void __launch_bounds__(IBINN_THREADS, IBINN_AIO_BWD_MINB) aio_bwd_kernel(const AioP p) {
     IBINN_DYN_SMEM(float, smem);
     __shared__ int s_flag;
     ibinn_pdl_wait();           // (common.cuh: launched with IBINN_LAUNCH_PDL)
