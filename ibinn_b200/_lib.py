@@ -124,9 +124,11 @@ _SIGNATURES = {
     'ibinn_haar_forward': ([P, P, I, I, I, I, F, P], c_int),
     'ibinn_haar_inverse': ([P, P, I, I, I, I, F, P], c_int),
     'ibinn_permute_features': ([P, P, P, I, I, P], c_int),
-    'ibinn_linear_forward': ([P, L, P, I, P, P, P, I, I, I, P], c_int),
-    'ibinn_linear_dgrad': ([P, P, P, I, P, P, L, I, I, I, I, P], c_int),
-    'ibinn_linear_wgrad': ([P, P, P, I, P, L, P, I, P, P, I, I, I, P], c_int),
+    'ibinn_linear_workspace_floats': ([I, I, I], c_int64),
+    'ibinn_linear_tickets': ([I, I, I], c_int),
+    'ibinn_linear_forward': ([P, L, P, I, P, P, P, I, I, I, P, P, P], c_int),
+    'ibinn_linear_dgrad': ([P, P, P, I, P, P, L, I, I, I, I, P, P, P], c_int),
+    'ibinn_linear_wgrad': ([P, P, P, I, P, L, P, I, P, P, I, I, I, P, P, P], c_int),
     'ibinn_gmm_head_partials_floats': ([I], c_int64),
     'ibinn_gmm_head_forward': ([P] * 14 + [I, I, I, P], c_int),
     'ibinn_gmm_head_gemm_supported': ([I, I, I], c_int),

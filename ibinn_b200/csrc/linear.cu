@@ -8,6 +8,7 @@
 // never launches it.)
 #include "common.cuh"
 #include "tc.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -22,6 +23,7 @@ struct GemmP {
     const float* bias;                       // (N) or NULL
     float* C; long long ldc;
     int M, N, K, kchunk, splits, accumulate;
+    float* ws; unsigned* counter;            // split-K: partial results [splits][M][N] + one ticket per output tile (NULL: fp32 atomics)
 };
 
 __device__ __forceinline__ float gemm_load_a(const GemmP& p, int i, int k) {
@@ -216,6 +218,7 @@ __global__ void __launch_bounds__(IBINN_THREADS) gemm_tc_kernel(const GemmP p) {
     __shared__ __align__(8) uint64_t bar_stage[2];
     __shared__ __align__(8) uint64_t bar_done;
     __shared__ uint32_t tmem_base_s;
+    __shared__ int s_last;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * TC_M, n0 = blockIdx.x * TC_N;
     const int kbeg = blockIdx.z * p.kchunk, kend = min(p.K, kbeg + p.kchunk);
@@ -302,10 +305,73 @@ __global__ void __launch_bounds__(IBINN_THREADS) gemm_tc_kernel(const GemmP p) {
                 if (j >= p.N) continue;
                 const float o = s_o[r * (TC_N + 1) + h * 32 + lane] + bj[h];
                 float* dst = p.C + (size_t)row * p.ldc + j;
-                if (p.splits > 1) atomicAdd(dst, o);
-                else if (p.accumulate) *dst += o;
+                if (p.splits > 1) {
+                    if (p.ws) p.ws[((size_t)blockIdx.z * p.M + row) * p.N + j] = o;
+                    else atomicAdd(dst, o);
+                } else if (p.accumulate) *dst += o;
                 else *dst = o;
             }
+        }
+    }
+    if (p.splits > 1 && p.ws) {
+        // Deterministic split-K: the last CTA of an output tile to arrive adds the partial tiles in split order (fixed order:
+        // the step is bit-reproducible; no fp32 atomics, no memset of C).
+        const unsigned tile = blockIdx.y * gridDim.x + blockIdx.x;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) s_last = (atomicAdd(p.counter + tile, 1u) == (unsigned)p.splits - 1u) ? 1 : 0;
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            // all 256 threads, four consecutive columns each, up to 16 partial values in flight per thread (the sum itself runs in
+            // split order): the tail costs two or three L2 round trips instead of one per split and row
+            const int rows = min(TC_M, p.M - m0);
+            const bool v4 = ((p.N & 3) == 0) && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (n0 + TC_N <= p.N);
+            if (v4) {
+                constexpr int UB = 8;
+                for (int e = tid; e < rows * (TC_N / 4); e += 2 * IBINN_THREADS) {
+                    const int e2 = e + IBINN_THREADS;
+                    const bool has2 = e2 < rows * (TC_N / 4);
+                    const int r1 = e / (TC_N / 4), c1 = (e % (TC_N / 4)) * 4, r2 = e2 / (TC_N / 4), c2 = (e2 % (TC_N / 4)) * 4;
+                    const float* s1 = p.ws + (size_t)(m0 + r1) * p.N + n0 + c1;
+                    const float* s2 = p.ws + (size_t)(m0 + r2) * p.N + n0 + c2;
+                    const size_t zs = (size_t)p.M * p.N;
+                    float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+                    for (int z0 = 0; z0 < p.splits; z0 += UB) {
+                        float4 v1[UB], v2[UB];
+#pragma unroll
+                        for (int u = 0; u < UB; ++u) {
+                            const bool in = z0 + u < p.splits;
+                            v1[u] = in ? __ldcg(reinterpret_cast<const float4*>(s1 + (size_t)(z0 + u) * zs)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            v2[u] = (in && has2) ? __ldcg(reinterpret_cast<const float4*>(s2 + (size_t)(z0 + u) * zs)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int u = 0; u < UB; ++u) {
+                            a1.x += v1[u].x; a1.y += v1[u].y; a1.z += v1[u].z; a1.w += v1[u].w;
+                            a2.x += v2[u].x; a2.y += v2[u].y; a2.z += v2[u].z; a2.w += v2[u].w;
+                        }
+                    }
+                    float4* d1 = reinterpret_cast<float4*>(p.C + (size_t)(m0 + r1) * p.ldc + n0 + c1);
+                    if (p.accumulate) { const float4 o = *d1; a1.x += o.x; a1.y += o.y; a1.z += o.z; a1.w += o.w; }
+                    *d1 = a1;
+                    if (has2) {
+                        float4* d2 = reinterpret_cast<float4*>(p.C + (size_t)(m0 + r2) * p.ldc + n0 + c2);
+                        if (p.accumulate) { const float4 o = *d2; a2.x += o.x; a2.y += o.y; a2.z += o.z; a2.w += o.w; }
+                        *d2 = a2;
+                    }
+                }
+            } else {
+                for (int e = tid; e < rows * TC_N; e += IBINN_THREADS) {
+                    const int r = e / TC_N, j = n0 + e % TC_N;
+                    if (j >= p.N) continue;
+                    float acc = 0.f;
+                    for (int z = 0; z < p.splits; ++z) acc += __ldcg(p.ws + ((size_t)z * p.M + m0 + r) * p.N + j);
+                    float* dst = p.C + (size_t)(m0 + r) * p.ldc + j;
+                    if (p.accumulate) *dst += acc;
+                    else *dst = acc;
+                }
+            }
+            if (tid == 0) p.counter[tile] = 0u;
         }
     }
     tc::fence_before_sync();
@@ -350,24 +416,38 @@ __global__ void __launch_bounds__(IBINN_THREADS) colsum_kernel(const float* __re
     }
 }
 
-static int gemm_run(GemmP p, cudaStream_t st) {
+// grid and K split of a GEMM with an (M, N) result and contraction length K
+static void gemm_plan(int M, int N, int K, int& gx, int& gy, int& splits, int& kchunk) {
 #ifndef IBINN_EMU
     const int tile_m = TC_M, tile_n = TC_N, tile_k = TC_BK;
 #else
     const int tile_m = BM, tile_n = BN, tile_k = BK;
 #endif
-    const int gx = (p.N + tile_n - 1) / tile_n, gy = (p.M + tile_m - 1) / tile_m;
-    int splits = 1;
+    gx = (N + tile_n - 1) / tile_n;
+    gy = (M + tile_m - 1) / tile_m;
+    splits = 1;
     {
         const int ctas = gx * gy;
-        while (ctas * splits < 148 && splits < 16 && p.K / (splits * 2) >= 4 * tile_k) splits *= 2;
+        // CTAs to aim for.  96 (4 splits for the 128 x 1536 x 1536 GEMMs of the default model) beats 148 (8 splits) once the partial
+        // tiles are summed in order by the last CTA of a tile: 9.00 vs 9.04 ms per step (2 splits: 9.16, no split: 9.35).
+        static const int cap = [] { const char* e = getenv("IBINN_GEMM_SPLIT_TARGET"); return e ? atoi(e) : 96; }();
+        while (ctas * splits < cap && splits < 16 && K / (splits * 2) >= 4 * tile_k) splits *= 2;
     }
-    int kchunk = (p.K + splits - 1) / splits;
+    kchunk = (K + splits - 1) / splits;
     kchunk = (kchunk + tile_k - 1) / tile_k * tile_k;
-    splits = (p.K + kchunk - 1) / kchunk;
+    splits = (K + kchunk - 1) / kchunk;
+}
+
+static int gemm_run(GemmP p, cudaStream_t st) {
+    int gx, gy, splits, kchunk;
+    gemm_plan(p.M, p.N, p.K, gx, gy, splits, kchunk);
     p.kchunk = kchunk;
     p.splits = splits;
-    if (splits > 1 && !p.accumulate) {
+#ifdef IBINN_EMU
+    p.ws = nullptr;           // (the simulator's CUDA-core kernel keeps the atomics: its threads run one after the other anyway)
+#endif
+    if (p.ws && !p.counter) return IBINN_ENULL;
+    if (splits > 1 && !p.accumulate && !p.ws) {
         // contiguous rows only (ldc == N) for a single memset; otherwise row by row is not needed here
         if (p.ldc != p.N) return IBINN_EINVAL;
         cudaError_t e = cudaMemsetAsync(p.C, 0, (size_t)p.M * p.N * sizeof(float), st);
@@ -387,8 +467,24 @@ static int gemm_run(GemmP p, cudaStream_t st) {
 
 // y(B,N) = pre(x)(B,K; row stride x_rs) . w(N,K)^T + bias         pre: 0 none, 1 relu(x)*mask
 // (a mask is only meaningful for a contiguous x: it is indexed with the same offsets)
+// workspace / tickets of the three GEMMs below (result (M, N), contraction length Kc): forward (B, N, K), dgrad (B, K, N),
+// wgrad (N, K, B).  0 floats = no split along K for this shape.
+extern "C" int64_t ibinn_linear_workspace_floats(int M, int N, int Kc) {
+    if (M <= 0 || N <= 0 || Kc <= 0) return IBINN_EINVAL;
+    int gx, gy, splits, kchunk;
+    gemm_plan(M, N, Kc, gx, gy, splits, kchunk);
+    return splits > 1 ? (int64_t)splits * M * N : 0;
+}
+extern "C" int ibinn_linear_tickets(int M, int N, int Kc) {
+    if (M <= 0 || N <= 0 || Kc <= 0) return IBINN_EINVAL;
+    int gx, gy, splits, kchunk;
+    gemm_plan(M, N, Kc, gx, gy, splits, kchunk);
+    return gx * gy;
+}
+
 extern "C" int ibinn_linear_forward(const float* x, int64_t x_rs, const float* x_mask, int x_pre, const float* w,
-                                    const float* bias, float* y, int B, int K, int N, ibinn_stream_t stream) {
+                                    const float* bias, float* y, int B, int K, int N, float* workspace, uint32_t* tickets,
+                                    ibinn_stream_t stream) {
     int e = ibinn_check_device();
     if (e) return e;
     if (!x || !w || !y) return IBINN_ENULL;
@@ -396,12 +492,14 @@ extern "C" int ibinn_linear_forward(const float* x, int64_t x_rs, const float* x
     GemmP p{};
     p.A = x; p.sAi = x_rs; p.sAk = 1; p.Amask = x_mask; p.a_pre = x_pre;
     p.Bm = w; p.sBk = 1; p.sBj = K; p.bias = bias; p.C = y; p.ldc = N; p.M = B; p.N = N; p.K = K;
+    p.ws = workspace; p.counter = tickets;
     return gemm_run(p, (cudaStream_t)stream);
 }
 
 // dx(B,K; row stride dx_rs) (+)= pre(g)(B,N) . w(N,K)            pre: 0 none, 2 g*[h>0]*mask
 extern "C" int ibinn_linear_dgrad(const float* g, const float* h, const float* g_mask, int g_pre, const float* w, float* dx,
-                                  int64_t dx_rs, int accumulate, int B, int K, int N, ibinn_stream_t stream) {
+                                  int64_t dx_rs, int accumulate, int B, int K, int N, float* workspace, uint32_t* tickets,
+                                  ibinn_stream_t stream) {
     int e = ibinn_check_device();
     if (e) return e;
     if (!g || !w || !dx || (g_pre == 2 && !h)) return IBINN_ENULL;
@@ -409,6 +507,7 @@ extern "C" int ibinn_linear_dgrad(const float* g, const float* h, const float* g
     GemmP p{};
     p.A = g; p.sAi = N; p.sAk = 1; p.A2 = h; p.Amask = g_mask; p.a_pre = g_pre;
     p.Bm = w; p.sBk = K; p.sBj = 1; p.C = dx; p.ldc = dx_rs; p.M = B; p.N = K; p.K = N; p.accumulate = accumulate;
+    p.ws = workspace; p.counter = tickets;
     return gemm_run(p, (cudaStream_t)stream);
 }
 
@@ -416,7 +515,7 @@ extern "C" int ibinn_linear_dgrad(const float* g, const float* h, const float* g
 //   g_pre: 0 none, 2 g*[h>0]*g_mask ;  x_pre: 0 none, 1 relu(x)*x_mask
 extern "C" int ibinn_linear_wgrad(const float* g, const float* h, const float* g_mask, int g_pre, const float* x,
                                   int64_t x_rs, const float* x_mask, int x_pre, float* dw, float* db, int B, int K, int N,
-                                  ibinn_stream_t stream) {
+                                  float* workspace, uint32_t* tickets, ibinn_stream_t stream) {
     int e = ibinn_check_device();
     if (e) return e;
     if (!g || !x || !dw || (g_pre == 2 && !h)) return IBINN_ENULL;
@@ -427,6 +526,7 @@ extern "C" int ibinn_linear_wgrad(const float* g, const float* h, const float* g
     p.A = g; p.sAi = 1; p.sAk = N; p.A2 = h; p.Amask = g_mask; p.a_pre = g_pre;
     p.Bm = x; p.sBk = x_rs; p.sBj = 1; p.Bmask = x_mask; p.b_pre = x_pre;
     p.C = dw; p.ldc = K; p.M = N; p.N = K; p.K = B; p.accumulate = 1;
+    p.ws = workspace; p.counter = tickets;
     e = gemm_run(p, st);
     if (e) return e;
     if (db) {

@@ -28,6 +28,21 @@ def counter_ptr(ref):
     return ent[0].data_ptr() + 4 * ent[1]
 
 
+def counters_ptr(ref, n):
+    """n consecutive zero-initialised uint32 slots (see counter_ptr)"""
+    if n > _N_COUNTERS:
+        raise ValueError('ibinn_b200: %d counters requested' % n)
+    key = (ref.device.type, ref.device.index)
+    if key not in _COUNTERS:
+        counter_ptr(ref)
+    ent = _COUNTERS[key]
+    if ent[1] + 1 + n > _N_COUNTERS:
+        ent[1] = -1
+    first = ent[1] + 1
+    ent[1] = first + n - 1
+    return ent[0].data_ptr() + 4 * first
+
+
 def _nchw(t):
     """(pointer, batch stride) of a (B,C,H,W) tensor that is contiguous within each image."""
     if t is None:
@@ -614,12 +629,26 @@ def permute_features(x, index):
 
 # ------------------------------------------------------------------------------------ linear
 
+def _linear_ws(ref, M, N, Kc):
+    """(workspace tensor | None, workspace pointer, tickets pointer) of a GEMM with an (M, N) result and contraction length Kc: with them
+    the split-K partial results are summed in a fixed order (bit-reproducible step) instead of with fp32 atomics"""
+    L = _lib.lib()
+    n = int(L.ibinn_linear_workspace_floats(M, N, Kc))
+    if n < 0:
+        check(n, 'linear_workspace_floats')
+    if n == 0:
+        return None, None, None
+    ws = torch.empty(n, dtype=torch.float32, device=ref.device)
+    return ws, ptr(ws), counters_ptr(ref, int(L.ibinn_linear_tickets(M, N, Kc)))
+
+
 def linear_forward(x, w, bias, *, x_pre=0, x_mask=None):
     B, K = x.shape
     N = w.shape[0]
     xp, xrs = _rows(x)
     y = torch.empty((B, N), dtype=torch.float32, device=x.device)
-    check(_lib.lib().ibinn_linear_forward(xp, xrs, ptr(x_mask), x_pre, ptr(w), ptr(bias), ptr(y), B, K, N, stream(x)),
+    ws, wsp, tk = _linear_ws(x, B, N, K)
+    check(_lib.lib().ibinn_linear_forward(xp, xrs, ptr(x_mask), x_pre, ptr(w), ptr(bias), ptr(y), B, K, N, wsp, tk, stream(x)),
           'linear_forward')
     return y
 
@@ -628,7 +657,8 @@ def linear_dgrad(g, w, dx, *, accumulate, g_pre=0, h=None, g_mask=None):
     B, N = g.shape
     K = w.shape[1]
     dp, drs = _rows(dx)
-    check(_lib.lib().ibinn_linear_dgrad(ptr(g), ptr(h), ptr(g_mask), g_pre, ptr(w), dp, drs, int(accumulate), B, K, N, stream(g)),
+    ws, wsp, tk = _linear_ws(g, B, K, N)
+    check(_lib.lib().ibinn_linear_dgrad(ptr(g), ptr(h), ptr(g_mask), g_pre, ptr(w), dp, drs, int(accumulate), B, K, N, wsp, tk, stream(g)),
           'linear_dgrad')
 
 
@@ -637,6 +667,7 @@ def linear_wgrad(g, x, dw, db, *, g_pre=0, h=None, g_mask=None, x_pre=0, x_mask=
     K = x.shape[1]
     xp, xrs = _rows(x)
     st = stream(g)
+    ws, wsp, tk = _linear_ws(g, N, K, B)
     if DEFERRED_WGRAD is not None and WGRAD_STREAMS and g.is_cuda:
         # like the convolution weight gradients: nothing downstream in the backward pass reads dw, so it leaves the critical path
         global _wgrad_rr
@@ -644,8 +675,8 @@ def linear_wgrad(g, x, dw, db, *, g_pre=0, h=None, g_mask=None, x_pre=0, x_mask=
         _wgrad_rr += 1
         side.wait_stream(torch.cuda.current_stream())
         st = side.cuda_stream
-        DEFERRED_WGRAD.append(((g, x, h, g_mask, x_mask, dw, db), None))      # operands stay referenced until the join
-    check(_lib.lib().ibinn_linear_wgrad(ptr(g), ptr(h), ptr(g_mask), g_pre, xp, xrs, ptr(x_mask), x_pre, ptr(dw), ptr(db), B, K, N, st),
+        DEFERRED_WGRAD.append(((g, x, h, g_mask, x_mask, dw, db, ws), None))      # operands stay referenced until the join
+    check(_lib.lib().ibinn_linear_wgrad(ptr(g), ptr(h), ptr(g_mask), g_pre, xp, xrs, ptr(x_mask), x_pre, ptr(dw), ptr(db), B, K, N, wsp, tk, st),
           'linear_wgrad')
 
 

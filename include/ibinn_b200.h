@@ -285,13 +285,20 @@ int ibinn_haar_inverse(const float* y, float* x, int B, int C, int H, int W, flo
 int ibinn_permute_features(const float* x, const int32_t* index, float* out, int B, int D, ibinn_stream_t stream);
 
 /* ---------------------------------------------------------------- fully connected subnets (fc_constr,
- * reference inn_architecture.py:112-120) and their autograd backward */
+ * reference inn_architecture.py:112-120) and their autograd backward.
+ * Small-batch GEMMs are split along the contraction to fill the SMs.  With `workspace` (ibinn_linear_workspace_floats(M, N, Kc)
+ * floats; (M, N) = shape of the result, Kc = contraction length: forward (B, N, K), dgrad (B, K, N), wgrad (N, K, B)) and `tickets`
+ * (ibinn_linear_tickets(M, N, Kc) zero-initialised uint32 slots, returned to zero) the partial results are summed in split order
+ * by the last CTA of each output tile: bit-reproducible.  workspace = NULL: fp32 atomics on the result (not reproducible). */
+int64_t ibinn_linear_workspace_floats(int M, int N, int Kc);
+int ibinn_linear_tickets(int M, int N, int Kc);
 int ibinn_linear_forward(const float* x, int64_t x_rs, const float* x_mask, int x_pre, const float* w, const float* bias,
-                         float* y, int B, int K, int N, ibinn_stream_t stream);
+                         float* y, int B, int K, int N, float* workspace, uint32_t* tickets, ibinn_stream_t stream);
 int ibinn_linear_dgrad(const float* g, const float* h, const float* g_mask, int g_pre, const float* w, float* dx,
-                       int64_t dx_rs, int accumulate, int B, int K, int N, ibinn_stream_t stream);
+                       int64_t dx_rs, int accumulate, int B, int K, int N, float* workspace, uint32_t* tickets, ibinn_stream_t stream);
 int ibinn_linear_wgrad(const float* g, const float* h, const float* g_mask, int g_pre, const float* x, int64_t x_rs,
-                       const float* x_mask, int x_pre, float* dw, float* db, int B, int K, int N, ibinn_stream_t stream);
+                       const float* x_mask, int x_pre, float* dw, float* db, int B, int K, int N, float* workspace, uint32_t* tickets,
+                       ibinn_stream_t stream);
 
 /* ---------------------------------------------------------------- GMM / Information-Bottleneck head
  * Replaces reference model.py:113-126 (`cluster_distances`) and model.py:144-163 (loss dict).

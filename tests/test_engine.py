@@ -315,3 +315,25 @@ def test_two_piece_backward_equals_single_pass(cuda_dev):
     flat = lambda r: torch.cat([r[k].flatten().double() for k in results[0]])
     for other in results[1:]:
         assert float((flat(other) - flat(results[0])).norm() / flat(results[0]).norm()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_training_step_is_bit_reproducible(cuda_dev):
+    """two engines from the same seed, the same batches, dropout on, CUDA graph, weight gradients on the side stream: every
+    parameter, momentum buffer and BatchNorm statistic ends up bit-identical (all reductions run in a fixed order; the split-K
+    GEMMs of the FC blocks sum their partial tiles in split order)"""
+    dev = cuda_dev
+    gen = torch.Generator().manual_seed(11)
+    batches = [_batch(16, 10, gen) for _ in range(3)]
+    res = []
+    for rep in range(2):
+        torch.cuda.manual_seed(0)
+        m = _model(dev, overrides={})                      # the default CIFAR-10 network, dropout as shipped
+        step = TrainStep(m, batch_size=16, beta=1.0, use_graph=True)
+        for x, y in batches:
+            step.step(x.to(dev), y.to(dev))
+        torch.cuda.synchronize()
+        res.append(({k: v.detach().clone() for k, v in m.state_dict().items()}, step.flat.buf.clone()))
+    for k in res[0][0]:
+        assert torch.equal(res[0][0][k], res[1][0][k]), k
+    assert torch.equal(res[0][1], res[1][1])

@@ -52,3 +52,24 @@ def test_linear_forward_dgrad_wgrad(dev, B, K, N):
     ops.linear_wgrad(gd, bigd[:, 4:4 + K], dw2, db2, g_pre=2, h=h.to(dev), g_mask=m2.to(dev))
     assert rel(dw2, gm.t() @ bigd[:, 4:4 + K].double().cpu()) < 1e-5
     assert rel(db2, gm.sum(0)) < 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('B,K,N', [(128, 1536, 1024), (16, 1024, 3072)])
+def test_split_k_is_bit_reproducible(cuda_dev, B, K, N):
+    """small-batch GEMMs are split along K; the partial tiles are summed in split order by the last CTA of a tile (workspace +
+    tickets), not with fp32 atomics: repeated launches give identical bits"""
+    dev = cuda_dev
+    g = torch.Generator().manual_seed(7)
+    x, w, b = torch.randn(B, K, generator=g).to(dev), (torch.randn(N, K, generator=g) * 0.1).to(dev), torch.randn(N, generator=g).to(dev)
+    gy = torch.randn(B, N, generator=g).to(dev)
+    from ibinn_b200 import _lib
+    assert _lib.lib().ibinn_linear_workspace_floats(B, N, K) > 0          # this shape does split
+    y0 = ops.linear_forward(x, w, b)
+    dx0 = torch.empty(B, K, device=dev)
+    ops.linear_dgrad(gy, w, dx0, accumulate=False)
+    for _ in range(8):
+        assert torch.equal(ops.linear_forward(x, w, b), y0)
+        dx = torch.empty(B, K, device=dev)
+        ops.linear_dgrad(gy, w, dx, accumulate=False)
+        assert torch.equal(dx, dx0)
