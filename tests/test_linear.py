@@ -73,3 +73,19 @@ def test_split_k_is_bit_reproducible(cuda_dev, B, K, N):
         dx = torch.empty(B, K, device=dev)
         ops.linear_dgrad(gy, w, dx, accumulate=False)
         assert torch.equal(dx, dx0)
+
+
+@pytest.mark.gpu
+def test_linear_without_workspace_uses_atomics(cuda_dev):
+    """the C ABI keeps its workspace-free mode (fp32 atomics on the result, zeroed by the library): same values to fp32 accuracy"""
+    from ibinn_b200 import _lib
+    dev = cuda_dev
+    B, K, N = 128, 1536, 1024
+    g = torch.Generator().manual_seed(9)
+    x, w, b = torch.randn(B, K, generator=g), torch.randn(N, K, generator=g) * 0.1, torch.randn(N, generator=g)
+    xd, wd, bd = x.to(dev), w.to(dev), b.to(dev)
+    y = torch.full((B, N), 7.0, device=dev)
+    _lib.check(_lib.lib().ibinn_linear_forward(_lib.ptr(xd), K, None, 0, _lib.ptr(wd), _lib.ptr(bd), _lib.ptr(y), B, K, N, None, None,
+                                               _lib.stream(xd)), 'linear_forward')
+    assert rel(y, x.double() @ w.double().t() + b.double()) < 1e-5
+    assert torch.equal(ops.linear_forward(xd, wd, bd) - y < 1e-3, torch.ones_like(y, dtype=torch.bool))
