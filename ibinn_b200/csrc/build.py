@@ -45,5 +45,26 @@ def build(force=False, verbose=False):
     return OUT
 
 
+def build_variant(name, defines, sources=('block_tc.cu',)):
+    """libibinn_b200_<name>.so: the shipped objects with `sources` recompiled under extra -D flags.  Measurement builds only
+    (scripts/blk_timeline.py: name 'dbg', -DIBINN_BLK_DBG; scripts/stage_rate.py with IBINN_B200_LIB: -DIBINN_EXP_NOMMA,
+    -DIBINN_EXP_SKIPLO); never loaded unless IBINN_B200_LIB points at it."""
+    build()
+    out = os.path.join(HERE, 'libibinn_b200_%s.so' % name)
+    objs = []
+    for s in SOURCES:
+        o = os.path.join(HERE, s.replace('.cu', '.o'))
+        if s in sources:
+            o = os.path.join(HERE, s.replace('.cu', '.%s.o' % name))
+            subprocess.check_call([NVCC] + FLAGS + ['-D' + d for d in defines] + ['-c', os.path.join(HERE, s), '-o', o])
+        objs.append(o)
+    subprocess.check_call([NVCC, '-shared', '-o', out] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a', '-lcudart_static', '-ldl', '-lrt', '-lpthread'])
+    return out
+
+
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    if '--variant' in sys.argv:          # python build.py --variant dbg IBINN_BLK_DBG
+        i = sys.argv.index('--variant')
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

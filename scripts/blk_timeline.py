@@ -1,6 +1,7 @@
 """Phase time line of the fused AIO-run kernel (csrc/block_tc.cu built with -DIBINN_BLK_DBG; globaltimer stamps of CTA 0,
-first image, first two blocks).  Usage on the GPU box:
-    IBINN_B200_LIB=ibinn_b200/csrc/libibinn_b200_dbg.so python scripts/blk_timeline.py"""
+first image, first two blocks).  Build the instrumented library here, run on the GPU box:
+    python ibinn_b200/csrc/build.py --variant dbg IBINN_BLK_DBG
+    IBINN_B200_LIB=$PWD/ibinn_b200/csrc/libibinn_b200_dbg.so python scripts/blk_timeline.py"""
 import ctypes
 import os
 import sys

@@ -1,6 +1,7 @@
 """Steady-state cost of one coupling block of the fused AIO-run kernel (csrc/block_tc.cu): kernel time at 1, 2 and 14 images per CTA,
 differences divided by the images and blocks added (host overhead of the Python call stays outside: the launch is bracketed inside a
-busy stream)."""
+busy stream).  With IBINN_B200_LIB pointing at a `python ibinn_b200/csrc/build.py --variant nomma IBINN_EXP_NOMMA` (or
+`--variant skiplo IBINN_EXP_SKIPLO`) build the differences give the marginal cost of the conv1 + conv2 MMAs."""
 import os
 import sys
 
