@@ -776,42 +776,37 @@ __global__ void __launch_bounds__(BT_THREADS, 1) aio_stage_kernel(const ibinn_ai
                         const int q = t * TM + row;
                         float* og = (d->out && pix >= 0) ? d->out + (size_t)b * g.C * g.HW + pix : nullptr;
                         const int nk4 = g.cin_p / 4;
-                        for (int c8 = half * 8; c8 < g.npC; c8 += 8 * NPART) {
-                            float a8[8], b8[8], o8[8];
-                            tc::tmem_ld8(lane_base + t * g.tile_cols + c8, a8);
-                            tc::tmem_ld8(lane_base + t * g.tile_cols + g.npC + c8, b8);
+                        for (int c4 = half * 4; c4 < g.npC; c4 += 4 * NPART) {      // groups of 4 channels: C = 12 / 48 split evenly over the NPART warps
+                            float a4[4], b4[4], o4[4];
+                            tc::tmem_ld4(lane_base + t * g.tile_cols + c4, a4);
+                            tc::tmem_ld4(lane_base + t * g.tile_cols + g.npC + c4, b4);
                             tc::tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int c = c8 + i;
-                                o8[i] = 0.f;
+                            for (int i = 0; i < 4; ++i) {
+                                const int c = c4 + i;
+                                o4[i] = 0.f;
                                 if (c < g.C) {
-                                    o8[i] = fmaf(a8[i] + b8[i], s_sc[c], s_of[c]);
+                                    o4[i] = fmaf(a4[i] + b4[i], s_sc[c], s_of[c]);
                                     if (pix >= 0) {
-                                        if (og) og[(size_t)c * g.HW] = o8[i];
-                                        if (!last) xs[c * g.HW + pix] = o8[i];
+                                        if (og) og[(size_t)c * g.HW] = o4[i];
+                                        if (!last) xs[c * g.HW + pix] = o4[i];
                                     }
                                 }
                             }
-                            if (!last && q < g.S) {
+                            const int k4 = c4 / 4;
+                            if (!last && q < g.S && k4 < nk4) {
                                 // next block's X1 image: [relu](out[:c1]), zeros at the padding positions
                                 const bool rf = rf_next;
+                                float hi[4], lo[4];
 #pragma unroll
-                                for (int h4 = 0; h4 < 2; ++h4) {
-                                    const int k4 = c8 / 4 + h4;
-                                    if (k4 < nk4) {
-                                        float hi[4], lo[4];
-#pragma unroll
-                                        for (int j = 0; j < 4; ++j) {
-                                            const int c = k4 * 4 + j;
-                                            float v = (c < g.c1 && pix >= 0) ? o8[h4 * 4 + j] : 0.f;
-                                            if (rf) v = fmaxf(v, 0.f);
-                                            tc::split_tf32(v, hi[j], lo[j]);
-                                        }
-                                        *reinterpret_cast<float4*>(x_hi + (size_t)k4 * g.lbo_img + (g.halo + q) * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                                        *reinterpret_cast<float4*>(x_lo + (size_t)k4 * g.lbo_img + (g.halo + q) * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                                    }
+                                for (int j = 0; j < 4; ++j) {
+                                    const int c = c4 + j;
+                                    float v = (c < g.c1 && pix >= 0) ? o4[j] : 0.f;
+                                    if (rf) v = fmaxf(v, 0.f);
+                                    tc::split_tf32(v, hi[j], lo[j]);
                                 }
+                                *reinterpret_cast<float4*>(x_hi + (size_t)k4 * g.lbo_img + (g.halo + q) * 16) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                                *reinterpret_cast<float4*>(x_lo + (size_t)k4 * g.lbo_img + (g.halo + q) * 16) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                             }
                         }
                         tc::fence_before_sync();
